@@ -1,0 +1,87 @@
+"""Oracle (CPU restatement) against the golden vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+from oracle.env_port import ClosedFormEnv, MazeTables, PortEnv
+from oracle.grid import ACTIONS, astar_len, bfs_dist, best_dir_vector
+
+
+def _replay(env_cls, z, m, max_shape=10**9):
+    i = m["id"]
+    if m["shape"] > max_shape:
+        pytest.skip("too slow for the A* port")
+    toroidal = m["topology"] == "torus"
+    env = env_cls(z[f"m{i}_grid"], m["start"], m["goal"], toroidal=toroidal, enrich=m["enrich"])
+    assert env.max_steps == m["max_steps"]
+    for j in m["tapes"]:
+        pre = f"m{i}_t{j}_"
+        obs, info = env.reset()
+        T = len(z[pre + "action"])
+
+        def check(t, obs, info):
+            if m["enrich"]:
+                assert obs["agent"].dtype == np.float64
+                np.testing.assert_array_equal(obs["agent"].view(np.uint64), z[pre + "agent"][t].view(np.uint64))
+                np.testing.assert_array_equal(obs["target"].view(np.uint64), z[pre + "target"][t].view(np.uint64))
+                np.testing.assert_array_equal(obs["window"].astype(np.uint8), z[pre + "window"][t])
+            else:
+                np.testing.assert_array_equal(obs["agent"], z[pre + "agent"][t])
+                np.testing.assert_array_equal(obs["target"], z[pre + "target"][t])
+            np.testing.assert_array_equal(obs["best dir"], z[pre + "best"][t])
+            assert info["distance"] == z[pre + "dist"][t]
+            np.testing.assert_array_equal(env.mask_direction(probs=True).astype(np.float32), z[pre + "mask"][t])
+
+        check(0, obs, info)
+        for t in range(T):
+            obs, r, trunc, term, info = env.step(int(z[pre + "action"][t]))
+            assert np.float64(r).view(np.uint64) == z[pre + "reward"][t].view(np.uint64), (t, r, z[pre + "reward"][t])
+            assert trunc == bool(z[pre + "trunc"][t]) and term == bool(z[pre + "term"][t]), t
+            check(t + 1, obs, info)
+
+
+def _metas():
+    from conftest import load_golden
+    return load_golden("steps")[1]
+
+
+@pytest.mark.parametrize("m", _metas(), ids=lambda m: f"{m['topology']}-{m['algo']}-{m['shape']}{'-v1' if m['enrich'] else ''}")
+def test_closed_form_env_matches_reference(golden_steps, m):
+    _replay(ClosedFormEnv, golden_steps[0], m)
+
+
+@pytest.mark.parametrize("m", _metas(), ids=lambda m: f"{m['topology']}-{m['algo']}-{m['shape']}{'-v1' if m['enrich'] else ''}")
+def test_port_env_matches_reference(golden_steps, m):
+    _replay(PortEnv, golden_steps[0], m, max_shape=21)
+
+
+def test_best_dir_table_matches_reference(golden_bestdir):
+    z, meta = golden_bestdir
+    for m in meta:
+        i = m["id"]
+        grid, nxt = z[f"m{i}_grid"], z[f"m{i}_next"]
+        toroidal = m["topology"] == "torus"
+        t = MazeTables(grid, m["start"], m["goal"], toroidal)
+        assert t.max_steps == m["max_steps"]
+        for r, c in zip(*np.nonzero(grid)):
+            v = best_dir_vector(int(t.code[r, c]), (r, c), grid.shape, toroidal)
+            assert (r - v[0], c - v[1]) == tuple(nxt[r, c]), (m, r, c)
+
+
+def test_astar_port_lengths_equal_bfs(golden_bestdir):
+    z, meta = golden_bestdir
+    rng = np.random.default_rng(0)
+    for m in meta[:12]:
+        grid = z[f"m{m['id']}_grid"]
+        toroidal = m["topology"] == "torus"
+        d = bfs_dist(grid, m["goal"], toroidal)
+        cells = np.argwhere(grid != 0)
+        for r, c in cells[rng.choice(len(cells), size=12, replace=False)]:
+            assert astar_len(grid, (r, c), m["goal"], toroidal=toroidal) == d[r, c] + 1
+            L = 6
+            assert astar_len(grid, (r, c), m["goal"], max_depth=L, toroidal=toroidal) == min(d[r, c], L) + 1
+
+
+def test_penalty_luts_saturate():
+    assert ClosedFormEnv.REVISIT_LUT[188] == -1.0 and ClosedFormEnv.REVISIT_LUT[255] == -1.0
+    assert ClosedFormEnv.INVALID_LUT[250] == -1.0 and ClosedFormEnv.INVALID_LUT[255] == -1.0
+    assert ClosedFormEnv.REVISIT_LUT[187] != -1.0 or ClosedFormEnv.REVISIT_LUT[186] != -1.0
