@@ -1,0 +1,142 @@
+/*
+ * maze_b200.h -- C ABI of the B200-native batched maze environment (libmaze_b200.so).
+ *
+ * The reference (Fabri000/Maze-Solving-Agent-Gymnasium) is pure Python and has no FFI; this
+ * header therefore *defines* the boundary a maintainer would bind (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller (PyTorch tensors' data_ptr());
+ *     the library allocates nothing across the boundary except the opaque maze_ctx, which owns
+ *     two small device-side reward look-up tables and a scratch counter block
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); the caller
+ *     serialises calls on one ctx
+ *   - return value: 0 ok, <0 argument error (MAZE_E_*), >0 a cudaError_t; never throws, never
+ *     exits; maze_last_error(ctx) gives the text of the last failure
+ *   - sm_100a only: there is no CPU fallback and no other architecture in the fatbin
+ *
+ * Block-grid vocabulary (reference lib/maze_generation.py:16-19,33): a maze is an H x W grid of
+ * blocks, 0 wall / 1 floor / 2 goal, H = W = 2N+1 for N x N logical cells.  A maze lives in a
+ * "slot" of `slot` bytes (>= H*W, row-major with pitch W).
+ */
+#ifndef MAZE_B200_H
+#define MAZE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAZE_ABI_VERSION 1
+
+/* argument errors */
+#define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
+#define MAZE_E_RANGE  (-2) /* size / shape / id out of range                  */
+#define MAZE_E_SHAPE  (-3) /* even or too small / too large block shape       */
+#define MAZE_E_ALGO   (-4) /* unknown generator id                            */
+#define MAZE_E_ALIGN  (-5) /* pointer not aligned as documented               */
+
+/* limits */
+#define MAZE_MAX_DIM      255  /* H, W <= 255 (positions are stored in one byte each)        */
+#define MAZE_GEN_MAX_DIM  131  /* generator / fields kernels stage one maze in shared memory */
+#define MAZE_WINDOW       15   /* simple_maze_env.py:130 WINDOW_DIM                          */
+
+/* generator ids: lib/maze_generation.py:24-30 */
+#define MAZE_ALGO_RPRIM     0  /* "r-prim"    random_prim_visit   :59-99   */
+#define MAZE_ALGO_DFS       1  /* "dfs"       deept_first_visit   :101-128 */
+#define MAZE_ALGO_PRIMKILL  2  /* "prim&kill" prim_and_kill_visit :130-185 */
+
+/* per-maze metadata record: int32[MAZE_META_WORDS], 32 bytes, 32-byte aligned */
+#define MAZE_META_WORDS 8
+#define MAZE_META_H          0
+#define MAZE_META_W          1
+#define MAZE_META_START      2  /* start_r | start_c << 16                                   */
+#define MAZE_META_GOAL       3  /* goal_r  | goal_c  << 16                                   */
+#define MAZE_META_MAX_STEPS  4  /* simple_maze_env.py:52-58 (written by maze_fields)         */
+#define MAZE_META_FLAGS      5  /* bit0 toroidal; bits 8-15 generator id                     */
+#define MAZE_META_SOL_LEN    6  /* len(path(start->goal)) in blocks (written by maze_fields) */
+#define MAZE_META_SPARE      7
+#define MAZE_FLAG_TOROIDAL 1
+
+/* step-table byte (one per block, written by maze_fields): everything the step needs */
+#define MAZE_TAB_OPEN      0x01 /* block is not a wall                                       */
+#define MAZE_TAB_CODE_SHIFT 1   /* bits 1-3: best-next action 0..3, 4 = none (best dir 0,0)  */
+#define MAZE_TAB_D4_SHIFT   4   /* bits 4-5: D_goal mod 4 (reward needs D[prev]-D[cur] only) */
+
+/* per-env packed state: one uint64, little-endian bytes
+ *   0 row | 1 col | 2 consecutive-invalid (saturating) | 3 flags | 4-5 steps_taken (u16)
+ *   6 visit epoch (1..255) | 7 step-table byte of the current block                         */
+#define MAZE_ST_NEEDS_RESET 0x01 /* episode ended on the previous step (autoreset pending)   */
+#define MAZE_ST_WON         0x02 /* ... and it ended by reaching the goal                    */
+#define MAZE_ST_MOVE_SHIFT  2    /* bits 2-3: last successful move                           */
+#define MAZE_ST_NMOVES_SHIFT 4   /* bits 4-5: successful moves this episode, saturating at 2 */
+
+/* maze_step mode bits */
+#define MAZE_STEP_AUTORESET   0x01 /* gymnasium next-step autoreset                          */
+#define MAZE_STEP_WIN_NEXT    0x02 /* on autoreset after a win move to maze (m + stride) % M */
+#define MAZE_STEP_WIN_QUEUE   0x04 /* on a win append the env's maze slot to the regen queue */
+
+typedef struct maze_ctx maze_ctx;
+
+/* Batch of environments, structure of arrays.  All device pointers. */
+typedef struct maze_env_batch {
+    int32_t   num_envs;    /* B                                                              */
+    int32_t   num_mazes;   /* M maze slots                                                   */
+    int32_t   slot;        /* bytes per maze slot in `table`; entries per env in `visits`    */
+    int32_t   pool_stride; /* MAZE_STEP_WIN_NEXT increment                                   */
+    const int32_t* meta;   /* [M, 8]                                                         */
+    const uint8_t* table;  /* [M, slot] step-table bytes                                     */
+    int32_t*  env_maze;    /* [B] maze slot of each env                                      */
+    uint64_t* state;       /* [B] packed state                                               */
+    uint16_t* visits;      /* [B, slot] epoch << 8 | saturating visit count                  */
+    /* outputs of step / reset (reference obs dict of base_maze_env.py:116-122) */
+    int32_t*  agent;       /* [B, 2] int32                                                   */
+    int32_t*  target;      /* [B, 2]                                                         */
+    int32_t*  best_dir;    /* [B, 2]  agent - best_next                                      */
+    double*   reward;      /* [B]                                                            */
+    uint8_t*  terminated;  /* [B]                                                            */
+    uint8_t*  truncated;   /* [B]                                                            */
+    /* optional episode statistics (may be NULL) */
+    double*   ep_return;   /* [B] running return of the current episode                      */
+    int64_t*  stats;       /* [4] episodes, wins, truncations, steps (atomic counters)       */
+    double*   stats_return;/* [1] sum of finished episodes' returns                          */
+    /* optional regeneration queue (MAZE_STEP_WIN_QUEUE) */
+    int32_t*  queue;       /* [B] maze slots whose env won                                   */
+    int32_t*  queue_count; /* [1]                                                            */
+} maze_env_batch;
+
+int  maze_abi_version(void);
+int  maze_ctx_create(maze_ctx** out, int device);
+void maze_ctx_destroy(maze_ctx* ctx);
+const char* maze_last_error(maze_ctx* ctx);
+
+/* Host-side copy of the float64 reward look-up tables the kernels use.
+ * kind 0: revisit penalty  0.0 - (1 - exp(-0.2  * count))   base_maze_env.py:194
+ * kind 1: invalid penalty  0.0 - (1 - exp(-0.15 * k))       base_maze_env.py:200
+ * kind 2: shaping reward   delta * 0.5 - 0.05, delta = -1,0,+1 in out[0..2]  :192
+ * `out` is a HOST pointer to 256 doubles. */
+int maze_reward_lut(maze_ctx* ctx, int kind, double* out);
+
+/* Per-maze fields: BFS from the goal over the block graph, then the step table and the step
+ * budget.  Replaces the per-step A* of base_maze_env.py:189-190,224-262 (lib/a_star_algos/*)
+ * and set_max_steps (simple_maze_env.py:52-58, metrics_calculator.py:16,22-26).
+ *   grids [M, slot] uint8 block grids (0/1/2); meta [M, 8] with H, W, START, GOAL, FLAGS set;
+ *   writes table [M, slot] and meta MAX_STEPS / SOL_LEN.
+ *   ids: optional [n] list of maze slots to process (NULL = slots 0..n-1). */
+int maze_fields(maze_ctx* ctx, const uint8_t* grids, int32_t* meta, uint8_t* table,
+                const int32_t* ids, int n, int slot, void* stream);
+
+/* One transition for every env: BaseMazeEnv.step (base_maze_env.py:163-210) with the move rule
+ * of lib/maze_view.py:167-180 / :184-197, plus the observation of :116-122.
+ * actions [B] uint8 in 0..3. */
+int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* actions, uint32_t mode, void* stream);
+
+/* BaseMazeEnv.reset (base_maze_env.py:136-161) for envs with mask[e] != 0 (mask NULL = all).
+ * Writes agent/target/best_dir; reward 0, flags 0. */
+int maze_reset(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAZE_B200_H */

@@ -1,0 +1,77 @@
+// Context management and host-side helpers of the C ABI.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "maze_common.cuh"
+
+int maze_fail_cuda(maze_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+int maze_fail_arg(maze_ctx* ctx, int code, const char* what) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "argument error %d: %s", code, what);
+    return code;
+}
+
+extern "C" int maze_abi_version(void) { return MAZE_ABI_VERSION; }
+
+extern "C" int maze_ctx_create(maze_ctx** out, int device) {
+    if (!out) return MAZE_E_NULL;
+    *out = nullptr;
+    maze_ctx* ctx = new (std::nothrow) maze_ctx();
+    if (!ctx) return MAZE_E_RANGE;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    // Same libm `exp` the reference's math.exp calls (base_maze_env.py:194,200), same
+    // expression order, so the tables are bit-identical to what the reference computes.
+    for (int i = 0; i < 256; ++i) {
+        ctx->h_lut_revisit[i] = 0.0 - (1 - std::exp(-0.2 * i));
+        ctx->h_lut_invalid[i] = 0.0 - (1 - std::exp(-0.15 * i));
+    }
+    ctx->h_shaping[0] = 0 * 0.5 - 0.05;    // base_maze_env.py:192
+    ctx->h_shaping[1] = 1 * 0.5 - 0.05;
+    ctx->h_shaping[2] = 0.0;               // unused (|delta| <= 1)
+    ctx->h_shaping[3] = -1 * 0.5 - 0.05;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_lut_revisit, 256 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_lut_invalid, 256 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_lut_revisit, ctx->h_lut_revisit, 256 * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_lut_invalid, ctx->h_lut_invalid, 256 * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {
+        int rc = (int)e;
+        cudaFree(ctx->d_lut_revisit);
+        cudaFree(ctx->d_lut_invalid);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void maze_ctx_destroy(maze_ctx* ctx) {
+    if (!ctx) return;
+    cudaFree(ctx->d_lut_revisit);
+    cudaFree(ctx->d_lut_invalid);
+    delete ctx;
+}
+
+extern "C" const char* maze_last_error(maze_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+// Host-only: usable without a GPU (the tables are plain libm arithmetic).
+extern "C" int maze_reward_lut(maze_ctx* ctx, int kind, double* out) {
+    if (!out) return MAZE_E_NULL;
+    double rev[256], inv[256];
+    for (int i = 0; i < 256; ++i) {
+        rev[i] = 0.0 - (1 - std::exp(-0.2 * i));
+        inv[i] = 0.0 - (1 - std::exp(-0.15 * i));
+    }
+    memset(out, 0, 256 * sizeof(double));
+    if (kind == 0) memcpy(out, rev, sizeof(rev));
+    else if (kind == 1) memcpy(out, inv, sizeof(inv));
+    else if (kind == 2) { out[0] = -1 * 0.5 - 0.05; out[1] = 0 * 0.5 - 0.05; out[2] = 1 * 0.5 - 0.05; }
+    else return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_reward_lut kind");
+    return 0;
+}

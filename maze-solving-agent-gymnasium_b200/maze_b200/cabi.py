@@ -1,0 +1,122 @@
+"""ctypes binding of include/maze_b200.h (the drop-in boundary)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+ABI_VERSION = 1
+
+# constants mirrored from include/maze_b200.h
+META_WORDS = 8
+META_H, META_W, META_START, META_GOAL, META_MAX_STEPS, META_FLAGS, META_SOL_LEN, META_SPARE = range(8)
+FLAG_TOROIDAL = 1
+TAB_OPEN, TAB_CODE_SHIFT, TAB_D4_SHIFT = 0x01, 1, 4
+ST_NEEDS_RESET, ST_WON, ST_MOVE_SHIFT, ST_NMOVES_SHIFT = 0x01, 0x02, 2, 4
+STEP_AUTORESET, STEP_WIN_NEXT, STEP_WIN_QUEUE = 0x01, 0x02, 0x04
+ALGO_RPRIM, ALGO_DFS, ALGO_PRIMKILL = 0, 1, 2
+MAX_DIM, GEN_MAX_DIM, WINDOW = 255, 131, 15
+E_NULL, E_RANGE, E_SHAPE, E_ALGO, E_ALIGN = -1, -2, -3, -4, -5
+
+
+class MazeEnvBatch(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("num_mazes", C.c_int32), ("slot", C.c_int32), ("pool_stride", C.c_int32),
+        ("meta", C.c_void_p), ("table", C.c_void_p), ("env_maze", C.c_void_p), ("state", C.c_void_p),
+        ("visits", C.c_void_p), ("agent", C.c_void_p), ("target", C.c_void_p), ("best_dir", C.c_void_p),
+        ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p),
+        ("ep_return", C.c_void_p), ("stats", C.c_void_p), ("stats_return", C.c_void_p),
+        ("queue", C.c_void_p), ("queue_count", C.c_void_p),
+    ]
+
+
+class MazeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol declared in include/maze_b200.h
+SIGNATURES = {
+    "maze_abi_version": (C.c_int, []),
+    "maze_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "maze_ctx_destroy": (None, [C.c_void_p]),
+    "maze_last_error": (C.c_char_p, [C.c_void_p]),
+    "maze_reward_lut": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "maze_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "maze_step": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_uint32, C.c_void_p]),
+    "maze_reset": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p]),
+}
+
+
+def lib():
+    """The loaded C-ABI library.  No fallback: a missing library is a hard error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MazeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        if l.maze_abi_version() != ABI_VERSION:
+            raise MazeError(f"ABI mismatch: library {l.maze_abi_version()} vs binding {ABI_VERSION}; rebuild")
+        _lib = l
+    return _lib
+
+
+class Context:
+    """One maze_ctx per (process, device)."""
+
+    _by_device: dict = {}
+
+    def __init__(self, device_index: int):
+        self.device_index = int(device_index)
+        self._h = C.c_void_p()
+        rc = lib().maze_ctx_create(C.byref(self._h), self.device_index)
+        if rc != 0:
+            raise MazeError(f"maze_ctx_create(device={device_index}) failed with code {rc} "
+                            "(a CUDA device is required; there is no CPU fallback)")
+
+    @classmethod
+    def for_device(cls, device) -> "Context":
+        import torch
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise MazeError(f"device {dev} is not CUDA: the maze kernels are sm_100a only, there is no CPU path")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if idx not in cls._by_device:
+            cls._by_device[idx] = cls(idx)
+        return cls._by_device[idx]
+
+    @property
+    def handle(self):
+        return self._h
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            msg = lib().maze_last_error(self._h)
+            raise MazeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def reward_lut(kind: int):
+    """Host copy of a reward LUT (works without a GPU)."""
+    import numpy as np
+    out = (C.c_double * 256)()
+    rc = lib().maze_reward_lut(None, kind, out)
+    if rc != 0:
+        raise MazeError(f"maze_reward_lut({kind}) -> {rc}")
+    return np.array(out, dtype=np.float64)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

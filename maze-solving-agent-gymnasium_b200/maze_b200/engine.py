@@ -1,0 +1,167 @@
+"""Host-side engine: device-resident maze pool + structure-of-arrays env batch.
+
+PyTorch is used for device memory and streams only; all compute goes through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import cabi
+
+ALGO_IDS = {"r-prim": cabi.ALGO_RPRIM, "dfs": cabi.ALGO_DFS, "prim&kill": cabi.ALGO_PRIMKILL}
+ALGO_NAMES = {v: k for k, v in ALGO_IDS.items()}
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def check_shape(shape, limit=cabi.MAX_DIM):
+    H, W = int(shape[0]), int(shape[1])
+    if H % 2 == 0 or W % 2 == 0:
+        # the reference crashes with IndexError on even shapes (lib/maze_generation.py:197,203)
+        raise ValueError(f"maze block shape must be odd (2N+1), got {(H, W)}")
+    if H < 5 or W < 5 or H > limit or W > limit:
+        raise ValueError(f"maze block shape {(H, W)} outside [5, {limit}]")
+    return H, W
+
+
+class MazePool:
+    """M maze slots on one GPU: block grids, metadata records and step tables."""
+
+    def __init__(self, num_mazes: int, max_shape, device="cuda"):
+        self.device = torch.device(device)
+        self.ctx = cabi.Context.for_device(self.device)
+        self.max_shape = check_shape(max_shape)
+        self.num_mazes = int(num_mazes)
+        self.slot = _round_up(self.max_shape[0] * self.max_shape[1], 16)
+        d = self.device
+        self.grids = torch.zeros((self.num_mazes, self.slot), dtype=torch.uint8, device=d)
+        self.table = torch.zeros((self.num_mazes, self.slot), dtype=torch.uint8, device=d)
+        self.meta = torch.zeros((self.num_mazes, cabi.META_WORDS), dtype=torch.int32, device=d)
+
+    # -- construction from host block grids (parity tests, reference-generated mazes)
+    @classmethod
+    def from_grids(cls, grids: Sequence[np.ndarray], starts, goals, toroidal, device="cuda", max_shape=None):
+        M = len(grids)
+        tor = [bool(toroidal)] * M if isinstance(toroidal, (bool, int)) else [bool(t) for t in toroidal]
+        shapes = [np.asarray(g).shape for g in grids]
+        if max_shape is None:
+            max_shape = (max(s[0] for s in shapes), max(s[1] for s in shapes))
+        pool = cls(M, max_shape, device)
+        pool.upload(range(M), grids, starts, goals, tor)
+        return pool
+
+    def upload(self, ids, grids, starts, goals, toroidal):
+        ids = list(ids)
+        hg = np.zeros((len(ids), self.slot), dtype=np.uint8)
+        hm = np.zeros((len(ids), cabi.META_WORDS), dtype=np.int32)
+        for k, (g, s, t, tor) in enumerate(zip(grids, starts, goals, toroidal)):
+            g = np.asarray(g, dtype=np.uint8)
+            H, W = check_shape(g.shape)
+            if H * W > self.slot:
+                raise ValueError(f"maze {g.shape} does not fit slot of {self.slot} bytes")
+            hg[k, :H * W] = g.reshape(-1)
+            hm[k, cabi.META_H], hm[k, cabi.META_W] = H, W
+            hm[k, cabi.META_START] = int(s[0]) | (int(s[1]) << 16)
+            hm[k, cabi.META_GOAL] = int(t[0]) | (int(t[1]) << 16)
+            hm[k, cabi.META_FLAGS] = cabi.FLAG_TOROIDAL if tor else 0
+        idx = torch.as_tensor(ids, dtype=torch.long, device=self.device)
+        self.grids[idx] = torch.from_numpy(hg).to(self.device)
+        self.meta[idx] = torch.from_numpy(hm).to(self.device)
+        self.compute_fields(ids)
+
+    def compute_fields(self, ids=None):
+        """Step table + step budget for the given slots (all if None)."""
+        if ids is None:
+            ids_t, n = None, self.num_mazes
+        else:
+            ids_t = torch.as_tensor(list(ids), dtype=torch.int32, device=self.device)
+            n = ids_t.numel()
+        rc = cabi.lib().maze_fields(self.ctx.handle, cabi.ptr(self.grids), cabi.ptr(self.meta), cabi.ptr(self.table),
+                                    cabi.ptr(ids_t), n, self.slot, cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_fields")
+
+    # -- host views (tests, facade)
+    def meta_host(self):
+        return self.meta.cpu().numpy()
+
+    def grid_host(self, m: int) -> np.ndarray:
+        mh = self.meta[m].cpu().numpy()
+        H, W = int(mh[cabi.META_H]), int(mh[cabi.META_W])
+        return self.grids[m, :H * W].cpu().numpy().reshape(H, W)
+
+    def table_host(self, m: int) -> np.ndarray:
+        mh = self.meta[m].cpu().numpy()
+        H, W = int(mh[cabi.META_H]), int(mh[cabi.META_W])
+        return self.table[m, :H * W].cpu().numpy().reshape(H, W)
+
+
+class MazeBatch:
+    """B environments over a MazePool; the SoA buffers of `maze_env_batch`."""
+
+    def __init__(self, pool: MazePool, num_envs: int, env_maze=None, stats: bool = False, pool_stride: int = 1,
+                 queue: bool = False):
+        self.pool = pool
+        self.device = pool.device
+        self.ctx = pool.ctx
+        B = self.num_envs = int(num_envs)
+        d = self.device
+        if env_maze is None:
+            env_maze = torch.arange(B, dtype=torch.int32, device=d) % pool.num_mazes
+        self.env_maze = torch.as_tensor(env_maze, dtype=torch.int32, device=d).contiguous()
+        assert self.env_maze.shape == (B,)
+        self.state = torch.zeros(B, dtype=torch.int64, device=d)
+        self.visits = torch.zeros((B, pool.slot), dtype=torch.int16, device=d)
+        self.agent = torch.zeros((B, 2), dtype=torch.int32, device=d)
+        self.target = torch.zeros((B, 2), dtype=torch.int32, device=d)
+        self.best_dir = torch.zeros((B, 2), dtype=torch.int32, device=d)
+        self.reward = torch.zeros(B, dtype=torch.float64, device=d)
+        self.terminated = torch.zeros(B, dtype=torch.uint8, device=d)
+        self.truncated = torch.zeros(B, dtype=torch.uint8, device=d)
+        self.ep_return = torch.zeros(B, dtype=torch.float64, device=d) if stats else None
+        self.stats = torch.zeros(4, dtype=torch.int64, device=d) if stats else None
+        self.stats_return = torch.zeros(1, dtype=torch.float64, device=d) if stats else None
+        self.queue = torch.zeros(B, dtype=torch.int32, device=d) if queue else None
+        self.queue_count = torch.zeros(1, dtype=torch.int32, device=d) if queue else None
+        self.pool_stride = int(pool_stride)
+        self._c = self._make_struct()
+
+    def _make_struct(self) -> cabi.MazeEnvBatch:
+        p = self.pool
+        return cabi.MazeEnvBatch(
+            num_envs=self.num_envs, num_mazes=p.num_mazes, slot=p.slot, pool_stride=self.pool_stride,
+            meta=p.meta.data_ptr(), table=p.table.data_ptr(), env_maze=self.env_maze.data_ptr(),
+            state=self.state.data_ptr(), visits=self.visits.data_ptr(), agent=self.agent.data_ptr(),
+            target=self.target.data_ptr(), best_dir=self.best_dir.data_ptr(), reward=self.reward.data_ptr(),
+            terminated=self.terminated.data_ptr(), truncated=self.truncated.data_ptr(),
+            ep_return=None if self.ep_return is None else self.ep_return.data_ptr(),
+            stats=None if self.stats is None else self.stats.data_ptr(),
+            stats_return=None if self.stats_return is None else self.stats_return.data_ptr(),
+            queue=None if self.queue is None else self.queue.data_ptr(),
+            queue_count=None if self.queue_count is None else self.queue_count.data_ptr())
+
+    def reset(self, mask: Optional[torch.Tensor] = None):
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        rc = cabi.lib().maze_reset(self.ctx.handle, C.byref(self._c), cabi.ptr(mask), cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_reset")
+
+    def step(self, actions: torch.Tensor, mode: int = 0):
+        """actions: uint8 [B] on the device."""
+        if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        assert actions.numel() == self.num_envs
+        rc = cabi.lib().maze_step(self.ctx.handle, C.byref(self._c), cabi.ptr(actions), mode,
+                                  cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_step")
+
+    def state_host(self):
+        s = self.state.cpu().numpy().view(np.uint64)
+        return dict(r=(s & 0xff).astype(int), c=((s >> 8) & 0xff).astype(int), consec=((s >> 16) & 0xff).astype(int),
+                    flags=((s >> 24) & 0xff).astype(int), steps=((s >> 32) & 0xffff).astype(int),
+                    epoch=((s >> 48) & 0xff).astype(int), tab=((s >> 56) & 0xff).astype(int))
