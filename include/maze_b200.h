@@ -136,6 +136,22 @@ int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* actions, ui
  * Writes agent/target/best_dir; reward 0, flags 0. */
 int maze_reset(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* mask, void* stream);
 
+/* Batched generation on the device: gen_maze (lib/maze_generation.py:6-35) and, for slots whose
+ * meta FLAGS has MAZE_FLAG_TOROIDAL, gen_maze_no_border (:37-56; generated at shape+2, goal
+ * chosen on the bordered maze, outer ring stripped).  Per slot the caller sets meta H, W (final
+ * block shape, odd) and FLAGS (toroidal bit, generator id in bits 8-15); the kernel writes the
+ * block grid (0/1/2; `grids` may be NULL), START, GOAL, SOL_LEN, MAX_STEPS, the step table, and
+ * increments SPARE (generation count of the slot, part of the RNG key).
+ *   ids       optional [n] slot list (NULL = slots 0..n-1)
+ *   count_dev optional device int32: number of valid entries of ids (then n = capacity); lets a
+ *             regeneration queue filled by maze_step be drained without a host round trip
+ *   max_h/w   largest final shape among the slots (sizes shared memory)
+ *   RNG       Philox4x32-10, key = seed, counter = (slot_id_base + slot, generation count):
+ *             results do not depend on how slots are sharded over GPUs. */
+int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8_t* table, const int32_t* ids,
+                  const int32_t* count_dev, int n, int slot, int max_h, int max_w,
+                  uint64_t seed, int64_t slot_id_base, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,7 +77,7 @@ __device__ __forceinline__ void st_cs(double* p, double v) { __stcs(p, v); }
 struct Philox {
     uint32_t k0, k1;
     uint32_t c0, c1, c2, c3;
-    uint32_t out[4];
+    uint32_t o0, o1, o2, o3;
     int have;
 
     __host__ __device__ void init(uint64_t seed, uint64_t seq) {
@@ -104,13 +104,16 @@ struct Philox {
             x0 = y0; x1 = y1; x2 = y2; x3 = y3;
             a += 0x9E3779B9u; b += 0xBB67AE85u;
         }
-        out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+        o0 = x0; o1 = x1; o2 = x2; o3 = x3;
         if (++c0 == 0) ++c1;
         have = 4;
     }
     __host__ __device__ uint32_t next() {
         if (have == 0) refill();
-        return out[4 - (have--)];
+        const uint32_t v = o0;
+        o0 = o1; o1 = o2; o2 = o3;
+        --have;
+        return v;
     }
     // uniform integer in [0, n) (multiply-shift; bias < n / 2^32)
     __host__ __device__ uint32_t below(uint32_t n) {

@@ -86,6 +86,53 @@ class MazePool:
                                     cabi.ptr(ids_t), n, self.slot, cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_fields")
 
+    def generate(self, ids=None, shapes=None, algorithms="r-prim", toroidal=False, seed=0, slot_id_base=0,
+                 count_dev=None, configure=True):
+        """Generate mazes on the device into the given slots (all if None).
+
+        shapes / algorithms / toroidal may be scalars or per-slot sequences.  With configure=False
+        the per-slot meta (H, W, FLAGS) already on the device is reused (regeneration)."""
+        if ids is None:
+            ids_list = list(range(self.num_mazes))
+            ids_t = None
+        elif isinstance(ids, torch.Tensor):
+            ids_list, ids_t = None, ids.to(device=self.device, dtype=torch.int32).contiguous()
+        else:
+            ids_list = [int(i) for i in ids]
+            ids_t = torch.as_tensor(ids_list, dtype=torch.int32, device=self.device)
+        n = self.num_mazes if ids_t is None else ids_t.numel()
+        max_h, max_w = self.max_shape
+        if configure:
+            assert ids_list is not None
+            k = len(ids_list)
+            if shapes is None:
+                shapes = self.max_shape
+            shp = [shapes] * k if isinstance(shapes[0], (int, np.integer)) else list(shapes)
+            alg = [algorithms] * k if isinstance(algorithms, (str, int)) else list(algorithms)
+            tor = [toroidal] * k if isinstance(toroidal, (bool, int)) else list(toroidal)
+            hm = np.zeros((k, 3), dtype=np.int32)
+            for q in range(k):
+                H, W = check_shape(shp[q], cabi.GEN_MAX_DIM - 2)
+                if H * W > self.slot:
+                    raise ValueError(f"shape {(H, W)} does not fit the pool slot")
+                a = alg[q]
+                if isinstance(a, str):
+                    if a not in ALGO_IDS:
+                        raise ValueError(f"unknown maze generation algorithm {a!r} (expected one of {list(ALGO_IDS)})")
+                    a = ALGO_IDS[a]
+                elif a not in ALGO_NAMES:
+                    raise ValueError(f"unknown maze generation algorithm id {a}")
+                hm[q] = (H, W, (cabi.FLAG_TOROIDAL if tor[q] else 0) | (int(a) << 8))
+            cfg = torch.from_numpy(hm).to(self.device)
+            idx = torch.as_tensor(ids_list, dtype=torch.long, device=self.device)
+            self.meta[idx, cabi.META_H] = cfg[:, 0]
+            self.meta[idx, cabi.META_W] = cfg[:, 1]
+            self.meta[idx, cabi.META_FLAGS] = cfg[:, 2]
+        rc = cabi.lib().maze_generate(self.ctx.handle, cabi.ptr(self.grids), cabi.ptr(self.meta), cabi.ptr(self.table),
+                                      cabi.ptr(ids_t), cabi.ptr(count_dev), n, self.slot, max_h, max_w,
+                                      int(seed) & (2**64 - 1), int(slot_id_base), cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_generate")
+
     # -- host views (tests, facade)
     def meta_host(self):
         return self.meta.cpu().numpy()

@@ -295,10 +295,31 @@ def make_qagent(out_path):
     np.savez_compressed(out_path, **out)
 
 
+def make_genstats(out_path):
+    """Samples of the reference generators' output distribution (fingerprints only)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.generation import maze_shape_stats
+    out = {}
+    for algo in ("r-prim", "dfs", "prim&kill"):
+        for shape, n in ((21, 400), (41, 300), (81, 60)):
+            random.seed(hash((algo, shape)) % 100000 + 5)
+            random.seed(5000 + shape + 1000 * ("r-prim", "dfs", "prim&kill").index(algo))
+            rows = []
+            t0 = time.time()
+            for _ in range(n):
+                start, goal, maze = gen_maze((shape, shape), algo)
+                st = maze_shape_stats(np.array(maze, dtype=np.uint8), start, goal)
+                rows.append((st["sol_len"], st["dead_ends"], st["junctions"], start[0], start[1]))
+            out[f"{algo}_{shape}"] = np.array(rows, dtype=np.int32)
+            print(f"genstats {algo} {shape} n={n} mean={np.mean(rows, axis=0)} {time.time()-t0:.0f}s", flush=True)
+    np.savez_compressed(out_path, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["steps", "bestdir", "metrics", "qagent"]
+    which = sys.argv[1:] or ["steps", "bestdir", "metrics", "qagent", "genstats"]
     for w in which:
         t0 = time.time()
-        {"steps": make_steps, "bestdir": make_bestdir, "metrics": make_metrics, "qagent": make_qagent}[w](
+        {"steps": make_steps, "bestdir": make_bestdir, "metrics": make_metrics, "qagent": make_qagent,
+         "genstats": make_genstats}[w](
             os.path.join(HERE, f"{w}.npz"))
         print(f"== {w}.npz written in {time.time()-t0:.0f}s", flush=True)
