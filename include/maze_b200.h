@@ -83,13 +83,13 @@ typedef struct maze_ctx maze_ctx;
 typedef struct maze_env_batch {
     int32_t   num_envs;    /* B                                                              */
     int32_t   num_mazes;   /* M maze slots                                                   */
-    int32_t   slot;        /* bytes per maze slot in `table`; entries per env in `visits`    */
+    int32_t   slot;        /* bytes per maze slot in `table`; cells per env in `visits`      */
     int32_t   pool_stride; /* MAZE_STEP_WIN_NEXT increment                                   */
     const int32_t* meta;   /* [M, 8]                                                         */
     const uint8_t* table;  /* [M, slot] step-table bytes                                     */
     int32_t*  env_maze;    /* [B] maze slot of each env                                      */
     uint64_t* state;       /* [B] packed state                                               */
-    uint16_t* visits;      /* [B, slot] epoch << 8 | saturating visit count                  */
+    uint16_t* visits;      /* [slot, B] cell-major: epoch << 8 | saturating visit count      */
     /* outputs of step / reset (reference obs dict of base_maze_env.py:116-122) */
     int32_t*  agent;       /* [B, 2] int32                                                   */
     int32_t*  target;      /* [B, 2]                                                         */

@@ -1,6 +1,7 @@
 // Context management and host-side helpers of the C ABI.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "maze_common.cuh"
@@ -46,6 +47,15 @@ extern "C" int maze_ctx_create(maze_ctx** out, int device) {
         cudaFree(ctx->d_lut_invalid);
         delete ctx;
         return rc;
+    }
+    ctx->step_ept = 2;
+    if (const char* v = getenv("MAZE_STEP_EPT")) ctx->step_ept = atoi(v);
+    if (const char* v = getenv("MAZE_L2_FETCH")) {
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[maze_b200] L2 fetch granularity %zu -> %zu (rc %d)\n", before, after, (int)le);
     }
     *out = ctx;
     return 0;

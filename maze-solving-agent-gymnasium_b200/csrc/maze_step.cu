@@ -1,8 +1,9 @@
 // Env step / reset kernels (sm_100a).
 //
-// One thread per env.  State is one packed 64-bit word per env (coalesced 8-byte load/store);
-// the maze is read through its one-byte-per-block step table (L2/L1 resident for a maze pool);
-// the only scattered DRAM access is the 2-byte visit counter of the block stepped onto.
+// One thread per env (optionally 2-4 envs per thread).  State is one packed 64-bit word per env
+// (coalesced 8-byte load/store); the maze is read through its one-byte-per-block step table
+// (L2/L1 resident for a maze pool); the only scattered DRAM access is the 2-byte visit counter of
+// the block stepped onto, fetched only for legal moves, from a cell-major array.
 // Reference semantics: gymnasium_env/envs/base_maze_env.py:136-210, lib/maze_view.py:165-197.
 #include "maze_common.cuh"
 
@@ -10,23 +11,24 @@ namespace {
 
 constexpr int STEP_THREADS = 256;
 
+// Visit counters are stored cell-major: entry (cell idx, env e) at idx * num_envs + e.  Envs that
+// share a maze are contiguous and start from the same block, so lanes of a warp standing on the
+// same block hit the same 64 bytes; lanes on different blocks cost one DRAM line each, exactly
+// like an env-major layout would.
+#define VISIT_AT(b, e, idx) ((b).visits + (size_t)(idx) * (b).num_envs + (e))
+
 struct StepLuts {
     const double* revisit;  // [256]
     const double* invalid;  // [256]
     double shaping_same, shaping_closer, shaping_farther;   // D[prev]-D[cur] = 0, +1, -1
 };
 
-// Warp-cooperative zeroing of the visit arrays of the lanes in `need` (epoch wrap-around:
-// once per 255 episodes per env).  Must be called by all 32 lanes.
-__device__ __forceinline__ void warp_clear_visits(unsigned need, uint16_t* my_visits, int slot) {
-    const int lane = threadIdx.x & 31;
-    while (need) {
-        int src = __ffs(need) - 1;
-        need &= need - 1;
-        unsigned long long base = __shfl_sync(0xffffffffu, (unsigned long long)my_visits, src);
-        uint32_t* p = reinterpret_cast<uint32_t*>(base);  // slot is even and rows are 4-byte aligned
-        for (int i = lane; i < slot / 2; i += 32) p[i] = 0u;
-    }
+// Zero the visit counters of the lanes in `need` (epoch wrap-around: once per 255 episodes per
+// env; envs sharing a maze wrap together, so the lanes of a warp usually clear side by side).
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_clear_visits(unsigned need, const maze_env_batch& b, int e) {
+    if (need & (1u << (threadIdx.x & 31)))
+        for (int i = 0; i < b.slot; ++i) *VISIT_AT(b, e, i) = 0;
 }
 
 // Episode (re)start: BaseMazeEnv.reset, base_maze_env.py:136-161.  The start block is NOT
@@ -43,121 +45,170 @@ __device__ __forceinline__ void begin_episode(EnvState& s, int start, int tab_at
     s.tab = tab_at_start;
 }
 
-template <bool kStats>
+// EPT environments per thread (env = base + k * STEP_THREADS keeps every access coalesced): the
+// loads of all EPT envs are issued phase by phase before anything waits on them.  The dependent
+// chain per env is state -> meta (L1) -> table byte (L2) -> visit counter (DRAM); the visit
+// counter is only fetched when the move is legal (a wall hit needs no counter), which matters
+// because every such fetch costs a whole DRAM line.
+template <int EPT, bool kStats>
 __global__ void __launch_bounds__(STEP_THREADS)
 maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t mode, StepLuts luts) {
-    const int e = blockIdx.x * STEP_THREADS + threadIdx.x;
-    const bool valid = e < b.num_envs;
-    const int ee = valid ? e : b.num_envs - 1;
+    const int base = blockIdx.x * (STEP_THREADS * EPT) + threadIdx.x;
 
-    EnvState s = unpack_state(b.state[ee]);
-    int m = b.env_maze[ee];
-    const int a = actions[ee] & 3;
-    uint16_t* my_visits = b.visits + (size_t)ee * b.slot;
-
-    const bool do_reset = valid && (mode & MAZE_STEP_AUTORESET) && (s.flags & MAZE_ST_NEEDS_RESET);
-    if (do_reset && (mode & MAZE_STEP_WIN_NEXT) && (s.flags & MAZE_ST_WON)) {
-        m += b.pool_stride;
-        if (m >= b.num_mazes) m -= b.num_mazes;
-        b.env_maze[e] = m;
+    // ---- phase 1: per-env words
+    uint64_t raw[EPT];
+    int m[EPT], a[EPT];
+    bool valid[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int e = base + k * STEP_THREADS;
+        valid[k] = e < b.num_envs;
+        const int ee = valid[k] ? e : b.num_envs - 1;
+        raw[k] = b.state[ee];
+        m[k] = b.env_maze[ee];
+        a[k] = actions[ee] & 3;
     }
 
-    const int4* mp = reinterpret_cast<const int4*>(b.meta + (size_t)m * MAZE_META_WORDS);
-    const int4 m0 = __ldg(mp);
-    const int4 m1 = __ldg(mp + 1);
-    const int H = m0.x, W = m0.y, start = m0.z, goal = m0.w;
-    const int max_steps = m1.x;
-    const bool tor = (m1.y & MAZE_FLAG_TOROIDAL) != 0;
-    const uint8_t* __restrict__ tab = b.table + (size_t)m * b.slot;
+    // ---- phase 2: maze metadata (L1/L2 resident: contiguous envs share a maze)
+    bool do_reset[EPT];
+    int hw[EPT], tor[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int flags = (int)((raw[k] >> 24) & 0xff);
+        do_reset[k] = valid[k] && (mode & MAZE_STEP_AUTORESET) && (flags & MAZE_ST_NEEDS_RESET);
+        if (do_reset[k] && (mode & MAZE_STEP_WIN_NEXT) && (flags & MAZE_ST_WON)) {
+            m[k] += b.pool_stride;
+            if (m[k] >= b.num_mazes) m[k] -= b.num_mazes;
+            b.env_maze[base + k * STEP_THREADS] = m[k];
+        }
+        const int2 shape = __ldg(reinterpret_cast<const int2*>(b.meta + (size_t)m[k] * MAZE_META_WORDS));
+        hw[k] = shape.x | (shape.y << 16);
+        tor[k] = __ldg(b.meta + (size_t)m[k] * MAZE_META_WORDS + MAZE_META_FLAGS) & MAZE_FLAG_TOROIDAL;
+    }
 
-    double reward = 0.0;
-    int term = 0, trunc = 0;
-    bool wrapped = false;
-
-    if (do_reset) {
-        const int sidx = (start & 0xffff) * W + (start >> 16);
-        begin_episode(s, start, __ldg(tab + sidx), wrapped);
-    } else if (valid) {
+    // ---- phase 3: the block stepped onto: table byte
+    int npos[EPT], idx[EPT], tb[EPT];
+    bool inb[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int H = hw[k] & 0xffff, W = hw[k] >> 16;
+        const int r = (int)(raw[k] & 0xff), c = (int)((raw[k] >> 8) & 0xff);
         int dr, dc;
-        action_delta(a, dr, dc);
-        int nr = s.r + dr, nc = s.c + dc;
-        bool inb;
-        if (tor) {  // lib/maze_view.py:185-186
+        action_delta(a[k], dr, dc);
+        int nr = r + dr, nc = c + dc;
+        if (tor[k]) {  // lib/maze_view.py:185-186
             nr = nr < 0 ? H - 1 : (nr >= H ? 0 : nr);
             nc = nc < 0 ? W - 1 : (nc >= W ? 0 : nc);
-            inb = true;
-        } else {    // lib/maze_view.py:169
-            inb = (nr > 0) & (nr < H - 1) & (nc > 0) & (nc < W - 1);
+            inb[k] = true;
+        } else {       // lib/maze_view.py:169
+            inb[k] = (nr > 0) & (nr < H - 1) & (nc > 0) & (nc < W - 1);
         }
-        const int idx = inb ? nr * W + nc : s.r * W + s.c;
-        const int tb = __ldg(tab + idx);
-        const uint32_t vis = my_visits[idx];
-        const bool moved = inb && (tb & MAZE_TAB_OPEN);
-        if (moved) {
-            const int cnt = ((int)(vis >> 8) == s.epoch) ? (int)(vis & 0xff) : 0;
-            if (cnt == 0) {
-                if ((nr | (nc << 16)) == goal) {
-                    reward = 1.0;   // base_maze_env.py:185-187
-                    term = 1;
-                } else {            // :189-192, len(path) = D_goal + 1
-                    const int dd = ((s.tab >> MAZE_TAB_D4_SHIFT) - (tb >> MAZE_TAB_D4_SHIFT)) & 3;
-                    reward = dd == 1 ? luts.shaping_closer : (dd == 3 ? luts.shaping_farther : luts.shaping_same);
-                }
-            } else {
-                reward = __ldg(luts.revisit + cnt);   // :194
-            }
-            my_visits[idx] = (uint16_t)((s.epoch << 8) | (cnt < 255 ? cnt + 1 : 255));   // :196
-            s.r = nr;
-            s.c = nc;
-            s.tab = tb;
-            s.consec = 0;
-            int nm = (s.flags >> MAZE_ST_NMOVES_SHIFT) & 3;
-            nm = nm < 2 ? nm + 1 : 2;
-            s.flags = (a << MAZE_ST_MOVE_SHIFT) | (nm << MAZE_ST_NMOVES_SHIFT);
-        } else {
-            s.consec = s.consec < 255 ? s.consec + 1 : 255;   // :199-200
-            reward = __ldg(luts.invalid + s.consec);
-            s.flags &= ~(MAZE_ST_NEEDS_RESET | MAZE_ST_WON);
+        if (do_reset[k]) {
+            const int start = __ldg(b.meta + (size_t)m[k] * MAZE_META_WORDS + MAZE_META_START);
+            nr = start & 0xffff;
+            nc = start >> 16;
+            inb[k] = true;
         }
-        s.steps = s.steps < 65535 ? s.steps + 1 : 65535;
-        if (s.steps > max_steps) {   // :205-208 (overrides a goal reward on the same step)
-            trunc = 1;
-            reward = -1.0;
-        }
-        if (term | trunc) s.flags |= MAZE_ST_NEEDS_RESET | (term ? MAZE_ST_WON : 0);
+        if (!inb[k]) { nr = r; nc = c; }
+        npos[k] = nr | (nc << 16);
+        idx[k] = nr * W + nc;
+        tb[k] = __ldg(b.table + (size_t)m[k] * b.slot + idx[k]);
     }
 
-    // epoch wrap-around: the visit array must really be cleared (rare)
-    const unsigned need = __ballot_sync(0xffffffffu, wrapped);
-    if (need) warp_clear_visits(need, my_visits, b.slot);
+    // ---- phase 4: visit counter, only for legal moves
+    uint32_t vis[EPT];
+    bool moved[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        moved[k] = valid[k] && !do_reset[k] && inb[k] && (tb[k] & MAZE_TAB_OPEN);
+        vis[k] = 0;
+        if (moved[k]) vis[k] = *VISIT_AT(b, base + k * STEP_THREADS, idx[k]);
+    }
 
-    if (!valid) return;
+    // ---- phase 5: transition + outputs
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int e = base + k * STEP_THREADS;
+        const int H = hw[k] & 0xffff, W = hw[k] >> 16;
+        const int goal = __ldg(b.meta + (size_t)m[k] * MAZE_META_WORDS + MAZE_META_GOAL);
+        const int max_steps = __ldg(b.meta + (size_t)m[k] * MAZE_META_WORDS + MAZE_META_MAX_STEPS);
+        double reward = 0.0;
+        int term = 0, trunc = 0;
+        bool wrapped = false;
+        EnvState st = unpack_state(raw[k]);
 
-    b.state[e] = pack_state(s);
-    st_cs(reinterpret_cast<int2*>(b.agent) + e, make_int2(s.r, s.c));
-    st_cs(reinterpret_cast<int2*>(b.target) + e, make_int2(goal & 0xffff, goal >> 16));
-    st_cs(reinterpret_cast<int2*>(b.best_dir) + e,
-          best_dir_from_code((s.tab >> MAZE_TAB_CODE_SHIFT) & 7, s.r, s.c, H, W, tor));
-    st_cs(b.reward + e, reward);
-    b.terminated[e] = (uint8_t)term;
-    b.truncated[e] = (uint8_t)trunc;
-
-    if (kStats) {
-        if (b.ep_return) {
-            double g = do_reset ? 0.0 : b.ep_return[e] + reward;
-            b.ep_return[e] = g;
-            if ((term | trunc) && b.stats_return) atomicAdd(b.stats_return, g);
-        }
-        if (b.stats) {
-            if (term | trunc) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 0), 1ull);
-                if (term) atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 1), 1ull);
-                else atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 2), 1ull);
+        if (do_reset[k]) {
+            begin_episode(st, npos[k], tb[k], wrapped);
+        } else if (valid[k]) {
+            if (moved[k]) {
+                const int cnt = ((int)(vis[k] >> 8) == st.epoch) ? (int)(vis[k] & 0xff) : 0;
+                if (cnt == 0) {
+                    if (npos[k] == goal) {
+                        reward = 1.0;   // base_maze_env.py:185-187
+                        term = 1;
+                    } else {            // :189-192, len(path) = D_goal + 1
+                        const int dd = ((st.tab >> MAZE_TAB_D4_SHIFT) - (tb[k] >> MAZE_TAB_D4_SHIFT)) & 3;
+                        reward = dd == 1 ? luts.shaping_closer : (dd == 3 ? luts.shaping_farther : luts.shaping_same);
+                    }
+                } else {
+                    reward = __ldg(luts.revisit + cnt);   // :194
+                }
+                *VISIT_AT(b, e, idx[k]) = (uint16_t)((st.epoch << 8) | (cnt < 255 ? cnt + 1 : 255));   // :196
+                st.r = npos[k] & 0xffff;
+                st.c = npos[k] >> 16;
+                st.tab = tb[k];
+                st.consec = 0;
+                int nm = (st.flags >> MAZE_ST_NMOVES_SHIFT) & 3;
+                nm = nm < 2 ? nm + 1 : 2;
+                st.flags = (a[k] << MAZE_ST_MOVE_SHIFT) | (nm << MAZE_ST_NMOVES_SHIFT);
+            } else {
+                st.consec = st.consec < 255 ? st.consec + 1 : 255;   // :199-200
+                reward = __ldg(luts.invalid + st.consec);
+                st.flags &= ~(MAZE_ST_NEEDS_RESET | MAZE_ST_WON);
             }
+            st.steps = st.steps < 65535 ? st.steps + 1 : 65535;
+            if (st.steps > max_steps) {   // :205-208 (overrides a goal reward on the same step)
+                trunc = 1;
+                reward = -1.0;
+            }
+            if (term | trunc) st.flags |= MAZE_ST_NEEDS_RESET | (term ? MAZE_ST_WON : 0);
         }
-        if (term && (mode & MAZE_STEP_WIN_QUEUE) && b.queue) {
-            int at = atomicAdd(b.queue_count, 1);
-            b.queue[at] = m;
+
+        // epoch wrap-around: the visit array must really be cleared (rare)
+        const unsigned need = __ballot_sync(0xffffffffu, wrapped);
+        if (need) warp_clear_visits(need, b, e);
+
+        if (!valid[k]) continue;
+
+        b.state[e] = pack_state(st);
+        st_cs(reinterpret_cast<int2*>(b.agent) + e, make_int2(st.r, st.c));
+        // `target` only changes when the env (re)starts on a possibly different maze; the buffer
+        // persists between steps, so it is rewritten on reset only
+        if (do_reset[k])
+            st_cs(reinterpret_cast<int2*>(b.target) + e, make_int2(goal & 0xffff, goal >> 16));
+        st_cs(reinterpret_cast<int2*>(b.best_dir) + e,
+              best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, H, W, tor[k] != 0));
+        st_cs(b.reward + e, reward);
+        b.terminated[e] = (uint8_t)term;
+        b.truncated[e] = (uint8_t)trunc;
+
+        if (kStats) {
+            if (b.ep_return) {
+                double g = do_reset[k] ? 0.0 : b.ep_return[e] + reward;
+                b.ep_return[e] = g;
+                if ((term | trunc) && b.stats_return) atomicAdd(b.stats_return, g);
+            }
+            if (b.stats) {
+                if (term | trunc) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 0), 1ull);
+                    if (term) atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 1), 1ull);
+                    else atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 2), 1ull);
+                }
+            }
+            if (term && (mode & MAZE_STEP_WIN_QUEUE) && b.queue) {
+                int at = atomicAdd(b.queue_count, 1);
+                b.queue[at] = m[k];
+            }
         }
     }
 }
@@ -168,7 +219,6 @@ maze_reset_kernel(maze_env_batch b, const uint8_t* __restrict__ mask) {
     const bool valid = e < b.num_envs;
     const int ee = valid ? e : b.num_envs - 1;
     const bool sel = valid && (mask == nullptr || mask[ee] != 0);
-    uint16_t* my_visits = b.visits + (size_t)ee * b.slot;
     bool wrapped = false;
     EnvState s;
     int H = 0, W = 0, goal = 0;
@@ -186,7 +236,7 @@ maze_reset_kernel(maze_env_batch b, const uint8_t* __restrict__ mask) {
         begin_episode(s, start, __ldg(b.table + (size_t)m * b.slot + sidx), wrapped);
     }
     const unsigned need = __ballot_sync(0xffffffffu, wrapped);
-    if (need) warp_clear_visits(need, my_visits, b.slot);
+    if (need) warp_clear_visits(need, b, ee);
     if (!sel) return;
     b.state[e] = pack_state(s);
     reinterpret_cast<int2*>(b.agent)[e] = make_int2(s.r, s.c);
@@ -225,11 +275,20 @@ extern "C" int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* 
     luts.shaping_same = ctx->h_shaping[0];
     luts.shaping_closer = ctx->h_shaping[1];
     luts.shaping_farther = ctx->h_shaping[3];
-    const int grid = (b->num_envs + STEP_THREADS - 1) / STEP_THREADS;
     const bool stats = b->ep_return || b->stats || ((mode & MAZE_STEP_WIN_QUEUE) && b->queue);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (stats) maze_step_kernel<true><<<grid, STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
-    else maze_step_kernel<false><<<grid, STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
+    int ept = ctx->step_ept;
+    if (b->num_envs < 64 * 1024) ept = 1;   // small batches: more CTAs beats more loads per thread
+    auto grid_for = [&](int e) { return (b->num_envs + STEP_THREADS * e - 1) / (STEP_THREADS * e); };
+    if (stats) {
+        if (ept >= 4) maze_step_kernel<4, true><<<grid_for(4), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
+        else if (ept == 2) maze_step_kernel<2, true><<<grid_for(2), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
+        else maze_step_kernel<1, true><<<grid_for(1), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
+    } else {
+        if (ept >= 4) maze_step_kernel<4, false><<<grid_for(4), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
+        else if (ept == 2) maze_step_kernel<2, false><<<grid_for(2), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
+        else maze_step_kernel<1, false><<<grid_for(1), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
+    }
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

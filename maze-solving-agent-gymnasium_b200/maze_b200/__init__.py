@@ -4,5 +4,6 @@ loudly when the library has not been built, and every compute entry point needs 
 """
 from . import cabi  # noqa: F401
 from .engine import ALGO_IDS, MazeBatch, MazePool  # noqa: F401
+from .vector_env import MazeVectorEnv  # noqa: F401
 
-__all__ = ["cabi", "MazePool", "MazeBatch", "ALGO_IDS"]
+__all__ = ["cabi", "MazePool", "MazeBatch", "MazeVectorEnv", "ALGO_IDS"]

@@ -163,7 +163,7 @@ class MazeBatch:
         self.env_maze = torch.as_tensor(env_maze, dtype=torch.int32, device=d).contiguous()
         assert self.env_maze.shape == (B,)
         self.state = torch.zeros(B, dtype=torch.int64, device=d)
-        self.visits = torch.zeros((B, pool.slot), dtype=torch.int16, device=d)
+        self.visits = torch.zeros((pool.slot, B), dtype=torch.int16, device=d)   # cell-major
         self.agent = torch.zeros((B, 2), dtype=torch.int32, device=d)
         self.target = torch.zeros((B, 2), dtype=torch.int32, device=d)
         self.best_dir = torch.zeros((B, 2), dtype=torch.int32, device=d)

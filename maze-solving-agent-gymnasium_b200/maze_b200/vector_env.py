@@ -1,0 +1,199 @@
+"""MazeVectorEnv: thousands to millions of maze environments per GPU behind the gymnasium
+VectorEnv protocol (reset / step / autoreset), backed by the sm_100a kernels.
+
+Semantics per env are the reference's (gymnasium_env/envs/base_maze_env.py): same observation
+dict keys and values, same reward, same termination / truncation rules.  `step` returns the
+standard gymnasium order (obs, reward, terminated, truncated, info); `reference_order=True`
+returns the reference's swapped order (obs, reward, truncated, terminated, info)
+(base_maze_env.py:210).
+
+Autoreset is gymnasium 1.x "next-step": the step after an episode ends ignores the action and
+returns the reset observation with reward 0.  What happens to the maze on that reset follows the
+reference's trainers (lib/trainers/off_policy_trainer.py:60-71): a truncated episode replays the
+same maze; after a win `on_win` decides: "keep" (BaseMazeEnv.reset never changes the maze),
+"next" (move to the next maze of the pool) or "regenerate" (a fresh maze is generated on the
+device into the env's own slot, the analogue of update_maze()).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import cabi
+from .engine import MazeBatch, MazePool
+
+try:  # gymnasium is optional (absent from the build image)
+    import gymnasium as _gym
+    _VectorBase = _gym.vector.VectorEnv
+except Exception:  # pragma: no cover
+    _gym = None
+    _VectorBase = object
+
+
+class _LazyInfo(dict):
+    """info dict whose 'distance' (base_maze_env.py:124-134) is computed on first access."""
+
+    def __init__(self, env):
+        super().__init__()
+        self._env = env
+
+    def __missing__(self, key):
+        if key == "distance":
+            b = self._env.batch
+            v = (b.agent - b.target).abs().sum(dim=1).to(torch.float64)
+            self[key] = v
+            return v
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return key == "distance" or super().__contains__(key)
+
+
+class _ActionSpace:
+    def __init__(self, n, num_envs=None, seed=None):
+        self.n = n
+        self._num = num_envs
+        self._rng = np.random.default_rng(seed)
+
+    def sample(self):
+        if self._num is None:
+            return int(self._rng.integers(self.n))
+        return self._rng.integers(0, self.n, size=self._num).astype(np.uint8)
+
+
+class MazeVectorEnv(_VectorBase):
+    def __init__(self, num_envs: int, shape=(81, 81), topology: str = "euclid", algorithms="r-prim",
+                 num_mazes: Optional[int] = None, device="cuda", seed: int = 0, autoreset: bool = True,
+                 on_win: str = "keep", reference_order: bool = False, stats: bool = True,
+                 slot_id_base: int = 0, pool: Optional[MazePool] = None, env_maze=None):
+        if topology not in ("euclid", "toroidal"):
+            raise ValueError("topology must be 'euclid' or 'toroidal'")
+        if on_win not in ("keep", "next", "regenerate"):
+            raise ValueError("on_win must be 'keep', 'next' or 'regenerate'")
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        self.topology = topology
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.seed = int(seed)
+        self.autoreset = bool(autoreset)
+        self.on_win = on_win
+        self.reference_order = bool(reference_order)
+        self.slot_id_base = int(slot_id_base)
+        if pool is None:
+            M = self.num_envs if num_mazes is None else int(num_mazes)
+            pool = MazePool(M, self.shape, self.device)
+            algos = algorithms
+            if not isinstance(algorithms, str):
+                algos = [algorithms[i % len(algorithms)] for i in range(M)]
+            pool.generate(shapes=self.shape, algorithms=algos, toroidal=(topology == "toroidal"),
+                          seed=self.seed, slot_id_base=self.slot_id_base)
+        self.pool = pool
+        if on_win == "regenerate" and pool.num_mazes != self.num_envs:
+            raise ValueError("on_win='regenerate' needs one maze slot per env (num_mazes == num_envs)")
+        if env_maze is None:
+            # contiguous envs share a maze: table reads of a warp hit the same lines
+            per = max(1, self.num_envs // pool.num_mazes)
+            env_maze = (torch.arange(self.num_envs, device=self.device, dtype=torch.int32) // per).clamp_(max=pool.num_mazes - 1)
+        self.batch = MazeBatch(pool, self.num_envs, env_maze=env_maze, stats=stats, queue=(on_win == "regenerate"))
+        self._mode = ((cabi.STEP_AUTORESET if self.autoreset else 0)
+                      | (cabi.STEP_WIN_NEXT if on_win == "next" else 0)
+                      | (cabi.STEP_WIN_QUEUE if on_win == "regenerate" else 0))
+        self.single_action_space = _ActionSpace(4)
+        self.action_space = _ActionSpace(4, self.num_envs, seed)
+        self.single_observation_space = None
+        self.observation_space = None
+        if _gym is not None:  # pragma: no cover
+            sp = _gym.spaces
+            hi = max(self.pool.max_shape)
+            self.single_action_space = sp.Discrete(4)
+            self.action_space = sp.MultiDiscrete([4] * self.num_envs)
+            self.single_observation_space = sp.Dict({
+                "agent": sp.Box(0, hi, shape=(2,), dtype=np.int32), "target": sp.Box(0, hi, shape=(2,), dtype=np.int32),
+                "best dir": sp.Box(-hi, hi, shape=(2,), dtype=np.int32)})
+        # pinned staging for the host-buffer path
+        self._h_actions = None
+        self._d_actions = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        self._h_out = None
+
+    # ------------------------------------------------------------------------------------------
+    def _obs(self):
+        b = self.batch
+        return {"agent": b.agent, "target": b.target, "best dir": b.best_dir}
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        """seed is accepted and ignored, like the reference (base_maze_env.py:136)."""
+        self.batch.reset()
+        return self._obs(), _LazyInfo(self)
+
+    def _device_actions(self, actions):
+        if isinstance(actions, torch.Tensor):
+            if actions.device == self.device and actions.dtype == torch.uint8 and actions.is_contiguous():
+                return actions
+            self._d_actions.copy_(actions.reshape(-1), non_blocking=True)
+            return self._d_actions
+        a = np.ascontiguousarray(actions, dtype=np.uint8).reshape(-1)
+        if self._h_actions is None:
+            self._h_actions = torch.empty(self.num_envs, dtype=torch.uint8, pin_memory=True)
+        self._h_actions.numpy()[:] = a
+        self._d_actions.copy_(self._h_actions, non_blocking=True)
+        return self._d_actions
+
+    def step(self, actions):
+        b = self.batch
+        b.step(self._device_actions(actions), self._mode)
+        if self.on_win == "regenerate":
+            self.pool.generate(ids=b.queue, count_dev=b.queue_count, configure=False, seed=self.seed,
+                               slot_id_base=self.slot_id_base)
+            b.queue_count.zero_()
+        term, trunc = b.terminated.view(torch.bool), b.truncated.view(torch.bool)
+        if self.reference_order:
+            return self._obs(), b.reward, trunc, term, _LazyInfo(self)
+        return self._obs(), b.reward, term, trunc, _LazyInfo(self)
+
+    # -- host-buffer path: numpy in, numpy out, all copies through pinned memory ---------------
+    def _host_out(self):
+        if self._h_out is None:
+            B = self.num_envs
+            pin = dict(pin_memory=True)
+            self._h_out = dict(agent=torch.empty((B, 2), dtype=torch.int32, **pin),
+                               target=torch.empty((B, 2), dtype=torch.int32, **pin),
+                               best_dir=torch.empty((B, 2), dtype=torch.int32, **pin),
+                               reward=torch.empty(B, dtype=torch.float64, **pin),
+                               terminated=torch.empty(B, dtype=torch.uint8, **pin),
+                               truncated=torch.empty(B, dtype=torch.uint8, **pin))
+        return self._h_out
+
+    def h2d_bytes_per_step(self):
+        return self.num_envs
+
+    def d2h_bytes_per_step(self):
+        return self.num_envs * (3 * 8 + 8 + 1 + 1)
+
+    def step_host(self, actions: np.ndarray):
+        """Same transition as step() with HOST buffers on both sides: actions are copied to the
+        device, every output is copied back; returns numpy views of the pinned result buffers."""
+        b = self.batch
+        self.step(actions)
+        h = self._host_out()
+        for k in ("agent", "target", "best_dir", "reward", "terminated", "truncated"):
+            h[k].copy_(getattr(b, k), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        obs = {"agent": h["agent"].numpy(), "target": h["target"].numpy(), "best dir": h["best_dir"].numpy()}
+        term, trunc = h["terminated"].numpy().view(np.bool_), h["truncated"].numpy().view(np.bool_)
+        info = {}
+        if self.reference_order:
+            return obs, h["reward"].numpy(), trunc, term, info
+        return obs, h["reward"].numpy(), term, trunc, info
+
+    def episode_statistics(self):
+        """(episodes, wins, truncations, sum of returns) since construction; one small D2H."""
+        b = self.batch
+        if b.stats is None:
+            return None
+        s = b.stats.cpu().numpy()
+        return dict(episodes=int(s[0]), wins=int(s[1]), truncations=int(s[2]), return_sum=float(b.stats_return.cpu()[0]))
+
+    def close(self):
+        pass
