@@ -1,0 +1,53 @@
+"""Oracle difficulty metrics vs values computed by the unmodified reference (metrics.npz),
+including the reference's only known-answer material: the literal 15x15 maze."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle.metrics import kim_crawfis, mcclendon
+
+
+def _rows():
+    return [m for m in load_golden("metrics")[1] if not m["no_border"]]
+
+
+def test_literal_maze_known_answers(golden_metrics):
+    z, meta = golden_metrics
+    m = meta[0]
+    assert m["algo"] == "literal"
+    # BASELINE.md section 2 / SURVEY.md section 8(c): reference outputs on testing_Mccledon.py:4-20
+    assert m["difficulty"] == 9.950639302928026 and m["complexity"] == 5.681612603202764
+    assert m["sol_len"] == 61 and m["L"] == 0.6288659793814433 and m["DE"] == 0.03278688524590164
+    d = mcclendon(z["m0_grid"], m["start"], m["goal"], details=True)
+    assert d["difficulty"] == pytest.approx(9.950639302928026, rel=1e-12)
+    assert d["complexity"] == pytest.approx(5.681612603202764, rel=1e-12)
+    assert d["n_hallways"] == 6 and d["n_branches"] == 3
+    k = kim_crawfis(z["m0_grid"], m["start"], m["goal"])
+    assert k["sol_len"] == 61 and k["L"] == 0.6288659793814433
+    assert k["DE"] == 0.03278688524590164 and k["D"] == 0.03278688524590164
+
+
+@pytest.mark.parametrize("m", _rows(), ids=lambda m: f"{m['algo']}-{m['shape']}-{m['id']}")
+def test_metrics_match_reference(golden_metrics, m):
+    z, _ = golden_metrics
+    grid = z[f"m{m['id']}_grid"]
+    d = mcclendon(grid, m["start"], m["goal"], details=True)
+    assert d["n_hallways"] == m["n_hallways"]
+    assert d["n_branches"] == m["n_branches"]
+    assert d["hall_sum"] == pytest.approx(m["hall_sum"], rel=1e-11)
+    assert d["difficulty"] == pytest.approx(m["difficulty"], rel=1e-11)
+    assert d["complexity"] == pytest.approx(m["complexity"], rel=1e-11)
+    k = kim_crawfis(grid, m["start"], m["goal"])
+    assert k["sol_len"] == m["sol_len"]
+    assert k["L"] == m["L"] and k["D"] == m["D"] and k["DE"] == m["DE"]   # exact: integer counts / same divisions
+
+
+def test_no_border_difficulty_is_taken_on_the_bordered_maze(golden_metrics):
+    """gen_maze_no_border (lib/maze_generation.py:48-56) evaluates difficulty before stripping."""
+    z, meta = golden_metrics
+    rows = [m for m in meta if m["no_border"]]
+    assert rows
+    for m in rows:
+        bordered = np.pad(z[f"m{m['id']}_grid"], 1)
+        d, _ = mcclendon(bordered, (m["start"][0] + 1, m["start"][1] + 1), (m["goal"][0] + 1, m["goal"][1] + 1))
+        assert d == pytest.approx(m["difficulty"], rel=1e-11)
