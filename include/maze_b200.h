@@ -152,6 +152,27 @@ int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8_t* table, 
                   const int32_t* count_dev, int n, int slot, int max_h, int max_w,
                   uint64_t seed, int64_t slot_id_base, void* stream);
 
+/* Difficulty metrics of pool mazes, one record of MAZE_METRIC_WORDS doubles per processed slot
+ * (out[k] belongs to ids[k], or to slot k when ids is NULL):
+ *   McClendon difficulty / complexity  lib/maze_difficulty_evaluation/maze_complexity_evaluation.py:310-329
+ *     (graph construction :57-91, hallways :186-221, branches :223-259, honouring the `break` of :209-214)
+ *   Kim-Crawfis L / DE / D              lib/maze_difficulty_evaluation/metrics_calculator.py:22-26,87-127,71-85
+ * These are the six columns of the README table (generation_algos_metrics_evaluations.py:31-43).
+ * Mazes must be perfect (spanning trees); toroidal slots are scored on the zero-padded grid, i.e.
+ * the bordered maze gen_maze_no_border scored (lib/maze_generation.py:48-56).  A slot whose goal
+ * cannot be reached from its start gets NaNs.  Floating-point sums run in a different order than
+ * networkx iteration: parity is to 1e-9 relative, L / DE / D are exact. */
+#define MAZE_METRIC_WORDS 8
+#define MAZE_METRIC_DIFFICULTY 0
+#define MAZE_METRIC_COMPLEXITY 1
+#define MAZE_METRIC_L          2
+#define MAZE_METRIC_DE         3
+#define MAZE_METRIC_D          4
+#define MAZE_METRIC_SOL_LEN    5  /* len(path(start->goal)) in blocks                          */
+#define MAZE_METRIC_DE_COUNT   6  /* dead ends counted by calculate_DE                         */
+int maze_difficulty(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids,
+                    int n, int slot, int max_h, int max_w, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,291 @@
+// Difficulty metrics of one bordered perfect maze held in shared memory (one CTA per maze).
+//
+// McClendon complexity / difficulty (maze_complexity_evaluation.py:38-329) and Kim-Crawfis
+// L / D / DE (metrics_calculator.py:11-26,71-173), restated on the maze's spanning tree rooted at
+// `start` (see oracle/metrics.py, which is the specification):
+//   - the reference's graph G is the maze tree compressed onto its nodes (start, dead ends,
+//     corners, >2-neighbour cells); every node is a logical cell, so all arrays are per cell
+//   - hallways >= 1 are the components of (plain nodes) with their adjacent 3-way junctions;
+//     each tree edge contributes (d, 1/(2d)) to at most one hallway; branch = the solution
+//     junction run / hanging subtree the component is attached to
+//   - difficulty = ln(C0 * prod_b (C_b + 1)), complexity = ln(C0 + sum_b C_b)
+// Input: f.grid (0 wall / !=0 open, goal marked 2) and f.dist = BFS distances from start.
+#pragma once
+#include "maze_fields.cuh"
+
+struct MetricsSmem {
+    unsigned short* pnode;    // [cells] parent node (cell index), 0xffff for start
+    unsigned short* dpar;     // [cells] blocks strictly between node and parent node
+    unsigned short* comp;     // [cells] component root of a plain node
+    unsigned short* minleaf;  // [cells] smallest off-solution dead-end rank in the subtree
+    uint8_t* flags;           // [cells]
+    unsigned int* dsum;       // [cells] sum of d over the hallway of component root
+    double* ssum;             // [cells] sum of 1/(2d)
+    double* bsum;             // [cells] branch complexity by branch key
+};
+
+constexpr int MF_NB = 0x07, MF_TURN = 0x08, MF_SOL = 0x10, MF_NODE = 0x20, MF_DP = 0x40;
+
+__host__ __device__ inline size_t metrics_smem_bytes(int cells) {
+    // 4 x u16 + u8 + u32 + 2 x f64 per cell, each array 16-byte aligned
+    auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    return 4 * up(2 * (size_t)cells) + up((size_t)cells) + up(4 * (size_t)cells) + 2 * up(8 * (size_t)cells);
+}
+
+__device__ inline MetricsSmem metrics_smem_carve(unsigned char* base, int cells) {
+    auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    MetricsSmem m;
+    size_t o = 0;
+    m.ssum = reinterpret_cast<double*>(base + o); o += up(8 * (size_t)cells);
+    m.bsum = reinterpret_cast<double*>(base + o); o += up(8 * (size_t)cells);
+    m.dsum = reinterpret_cast<unsigned int*>(base + o); o += up(4 * (size_t)cells);
+    m.pnode = reinterpret_cast<unsigned short*>(base + o); o += up(2 * (size_t)cells);
+    m.dpar = reinterpret_cast<unsigned short*>(base + o); o += up(2 * (size_t)cells);
+    m.comp = reinterpret_cast<unsigned short*>(base + o); o += up(2 * (size_t)cells);
+    m.minleaf = reinterpret_cast<unsigned short*>(base + o); o += up(2 * (size_t)cells);
+    m.flags = base + o;
+    return m;
+}
+
+// 16-bit atomic min on shared memory (two cells share a 32-bit word)
+__device__ __forceinline__ void atomic_min_u16(unsigned short* p, unsigned short v) {
+    unsigned int* w = reinterpret_cast<unsigned int*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const bool hi = (reinterpret_cast<uintptr_t>(p) & 2) != 0;
+    unsigned int old = *w;
+    for (;;) {
+        const unsigned short cur = hi ? (unsigned short)(old >> 16) : (unsigned short)(old & 0xffffu);
+        if (cur <= v) return;
+        const unsigned int repl = hi ? ((old & 0x0000ffffu) | ((unsigned int)v << 16)) : ((old & 0xffff0000u) | v);
+        const unsigned int seen = atomicCAS(w, old, repl);
+        if (seen == old) return;
+        old = seen;
+    }
+}
+
+struct MazeMetrics {
+    double difficulty, complexity, L, DE, D;
+    int sol_len, de_count;
+};
+
+// All threads of the CTA call this; the result is valid on thread 0.
+__device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, int Hb, int Wb,
+                                    int start_idx, int goal_idx, MazeMetrics& out) {
+    __shared__ double s_D0, s_S0, s_red[2][FIELD_THREADS / 32];
+    __shared__ int s_dcount;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2, cells = nr * nc;
+    auto cell_block = [&](int ci) { return (2 * (ci / nc) + 1) * Wb + 2 * (ci % nc) + 1; };
+    auto block_cell = [&](int bi) { return ((bi / Wb) >> 1) * nc + ((bi % Wb) >> 1); };
+    const int offs[4] = {-Wb, Wb, -1, 1};
+    const int start_c = block_cell(start_idx), goal_c = block_cell(goal_idx);
+    if (f.dist[goal_idx] == DIST_INF) {   // goal not reachable from start: not a maze the reference can score
+        if (tid == 0) {
+            out.difficulty = out.complexity = out.L = out.DE = out.D = nan("");
+            out.sol_len = 0;
+            out.de_count = 0;
+        }
+        __syncthreads();
+        return;
+    }
+    const int sol_len = (int)f.dist[goal_idx] + 1;
+
+    // ---- 1. per-cell neighbour count / turn / node flags
+    for (int ci = tid; ci < cells; ci += nthr) {
+        const int b = cell_block(ci);
+        const int up = f.grid[b - Wb] != 0, dn = f.grid[b + Wb] != 0, lf = f.grid[b - 1] != 0, rt = f.grid[b + 1] != 0;
+        const int nb = up + dn + lf + rt;
+        const int turn = (nb == 2) && !((up && dn) || (lf && rt));
+        const int node = ((nb != 2) || turn || ci == start_c) && f.dist[b] != DIST_INF;   // unreachable cells play no part
+        ms.flags[ci] = (uint8_t)(nb | (turn ? MF_TURN : 0) | (node ? MF_NODE : 0));
+        ms.dsum[ci] = 0u;
+        ms.ssum[ci] = 0.0;
+        ms.bsum[ci] = 0.0;
+        ms.minleaf[ci] = 0xffffu;
+        ms.comp[ci] = 0xffffu;
+        ms.pnode[ci] = 0xffffu;
+        ms.dpar[ci] = 0;
+    }
+    if (tid == 0) { s_D0 = 0.0; s_S0 = 0.0; s_dcount = 0; }
+    __syncthreads();
+
+    // ---- 2. mark the solution (goal -> start along BFS parents); D = decision cells on it
+    if (tid == 0) {
+        int b = goal_idx, dcount = 0;
+        for (;;) {
+            const int ci = block_cell(b);
+            ms.flags[ci] |= MF_SOL;
+            if ((ms.flags[ci] & MF_NB) > 2) ++dcount;   // metrics_calculator.py:71-85 (only cells can have > 2)
+            if (b == start_idx) break;
+            const int d = f.dist[b];
+            int step = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (f.grid[b + offs[k]] != 0 && (int)f.dist[b + offs[k]] == d - 1) step = offs[k];
+            b += 2 * step;   // passage block, then the next cell
+        }
+        s_dcount = dcount;
+    }
+    __syncthreads();
+
+    // ---- 3. parent node and edge length of every node (walk straight up to the next node)
+    for (int ci = tid; ci < cells; ci += nthr) {
+        if (!(ms.flags[ci] & MF_NODE) || ci == start_c) continue;
+        int b = cell_block(ci);
+        const int d = f.dist[b];
+        int step = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (f.grid[b + offs[k]] != 0 && (int)f.dist[b + offs[k]] == d - 1) step = offs[k];
+        int hops = 0, pc;
+        do {
+            b += 2 * step;
+            ++hops;
+            pc = block_cell(b);
+        } while (!(ms.flags[pc] & MF_NODE));
+        ms.pnode[ci] = (unsigned short)pc;
+        ms.dpar[ci] = (unsigned short)(2 * hops - 1);   // maze_complexity_evaluation.py:176-184
+    }
+    __syncthreads();
+
+    auto is_sol = [&](int ci) { return (ms.flags[ci] & MF_SOL) != 0; };
+    auto nbof = [&](int ci) { return ms.flags[ci] & MF_NB; };
+    auto is_plain = [&](int ci) { return !is_sol(ci) && nbof(ci) != 3; };
+    auto is_dead_end_off = [&](int ci) { return (ms.flags[ci] & MF_NODE) && nbof(ci) == 1 && !is_sol(ci); };
+    // unit direction (as a block offset) from node a to node b lying on one straight segment
+    auto dir_between = [&](int a, int b) {
+        const int ab = cell_block(a), bb = cell_block(b);
+        const int dr = bb / Wb - ab / Wb, dc = bb % Wb - ab % Wb;
+        return dr != 0 ? (dr > 0 ? Wb : -Wb) : (dc > 0 ? 1 : -1);
+    };
+
+    // ---- 4. Kim-Crawfis DE: sequential over dead ends in row-major order (metrics_calculator.py:87-173)
+    int alcoves = 0, forward = 0, backward = 0;
+    if (tid == 0) {
+        const int gr = goal_idx / Wb, gc = goal_idx % Wb;
+        for (int de = 0; de < cells; ++de) {
+            if (!is_dead_end_off(de)) continue;
+            // attachment A = first solution node above; cut iff it sits at path index <= sol_len - 2
+            int a = ms.pnode[de];
+            while (!is_sol(a)) a = ms.pnode[a];
+            const int j = (int)f.dist[cell_block(de)] - (int)f.dist[cell_block(a)];
+            const bool cut = j <= sol_len - 2;
+            bool blocked = false, has_turn = false;
+            int first_dp = -1, prev = de, y = ms.pnode[de], below_a = de;
+            // interior nodes: strictly above the dead end, up to (cut) the node below A or
+            // (uncut) the node below start
+            for (;;) {
+                if (cut ? (y == a) : (y == start_c)) break;
+                const int fl = ms.flags[y];
+                if (fl & MF_DP) blocked = true;
+                if ((fl & MF_NB) > 2 && first_dp < 0) first_dp = y;
+                if (dir_between(prev, y) != dir_between(y, ms.pnode[y])) has_turn = true;
+                if (!is_sol(y)) below_a = y;
+                prev = y;
+                y = ms.pnode[y];
+            }
+            if (blocked) continue;
+            if (first_dp >= 0) ms.flags[first_dp] |= MF_DP;
+            const int len = cut ? j : (int)f.dist[cell_block(de)] + 1;
+            const bool flag = len >= 3 && (has_turn || first_dp >= 0);   // type_of_DE :153-173
+            if (!flag) { ++alcoves; continue; }
+            int lr, lc;   // path[-1]
+            if (cut) {
+                const int ab = cell_block(a) + dir_between(a, below_a);
+                lr = ab / Wb; lc = ab % Wb;
+            } else {
+                lr = start_idx / Wb; lc = start_idx % Wb;
+            }
+            const int db = cell_block(de);
+            const int diff = (abs(lr - gr) + abs(lc - gc)) - (abs(db / Wb - gr) + abs(db % Wb - gc));
+            if (diff > 0) ++forward; else ++backward;
+        }
+    }
+
+    // ---- 5. smallest dead-end rank below every off-solution node (adjacency order of the reference)
+    for (int ci = tid; ci < cells; ci += nthr) {
+        if (!is_dead_end_off(ci)) continue;
+        int y = ci;
+        while (!is_sol(y)) {
+            atomic_min_u16(ms.minleaf + y, (unsigned short)ci);
+            y = ms.pnode[y];
+        }
+    }
+    // ---- 6. component root of every plain node
+    for (int ci = tid; ci < cells; ci += nthr) {
+        if (!(ms.flags[ci] & MF_NODE) || !is_plain(ci)) continue;
+        int r = ci;
+        while (is_plain(ms.pnode[r])) r = ms.pnode[r];
+        ms.comp[ci] = (unsigned short)r;
+    }
+    __syncthreads();
+
+    // ---- 7. every tree edge goes to at most one hallway (maze_complexity_evaluation.py:186-221)
+    for (int n = tid; n < cells; n += nthr) {
+        if (!(ms.flags[n] & MF_NODE) || n == start_c) continue;
+        const int p = ms.pnode[n];
+        const unsigned d = ms.dpar[n];
+        const double s = 1.0 / (double)(2 * d);
+        if (is_sol(n)) {                       // solution chain = hallway 0
+            atomicAdd(&s_D0, (double)d);
+            atomicAdd(&s_S0, s);
+        } else if (nbof(n) != 3) {             // plain child
+            if (is_plain(p) || nbof(p) == 3) {
+                atomicAdd(&ms.dsum[ms.comp[n]], d);
+                atomicAdd(&ms.ssum[ms.comp[n]], s);
+            }
+        } else if (is_plain(p)) {              // off-solution junction below a plain node
+            const int pp = ms.pnode[p];
+            const bool broke = nbof(pp) == 3 && is_sol(pp);   // :209-214 `break`
+            if (!broke || ms.minleaf[n] == ms.minleaf[p]) {
+                atomicAdd(&ms.dsum[ms.comp[p]], d);
+                atomicAdd(&ms.ssum[ms.comp[p]], s);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 8. hallway complexity -> branch (maze_complexity_evaluation.py:223-259,286-308)
+    for (int r = tid; r < cells; r += nthr) {
+        if (!(ms.flags[r] & MF_NODE) || ms.comp[r] != r) continue;
+        const double c = (double)ms.dsum[r] * ms.ssum[r];
+        int below = r, x = ms.pnode[r];
+        while (!is_sol(x)) { below = x; x = ms.pnode[x]; }
+        int key = below;
+        if (nbof(x) == 3) {                    // junction on the solution: key = head of its junction run
+            key = x;
+            while (key != start_c && nbof(ms.pnode[key]) == 3) key = ms.pnode[key];
+        }
+        atomicAdd(&ms.bsum[key], c);
+    }
+    __syncthreads();
+
+    // ---- 9. reduce: sum and product over branches
+    double tsum = 0.0, tprod = 1.0;
+    for (int k = tid; k < cells; k += nthr) {
+        const double v = ms.bsum[k];
+        tsum += v;
+        tprod *= v + 1.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+        tprod *= __shfl_xor_sync(0xffffffffu, tprod, o);
+    }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = tsum; s_red[1][tid >> 5] = tprod; }
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0, prod = 1.0;
+        for (int w = 0; w < nthr / 32; ++w) { sum += s_red[0][w]; prod *= s_red[1][w]; }
+        const double c0 = s_D0 * s_S0;
+        out.difficulty = log(c0 * prod);       // :319-329
+        out.complexity = log(c0 + sum);        // :310-317
+        const double ce = (double)((Hb - 1) * ((Wb - 1) / 2) - 1);   // metrics_calculator.py:16
+        out.L = __ddiv_rn((double)sol_len, ce);
+        out.D = __ddiv_rn((double)s_dcount, (double)sol_len);
+        out.DE = __dadd_rn(__dadd_rn(__ddiv_rn((double)alcoves, (double)sol_len), __ddiv_rn((double)forward, (double)sol_len)),
+                           __ddiv_rn((double)backward, (double)sol_len));   // AC + FDE + BDE, :97-98
+        out.sol_len = sol_len;
+        out.de_count = alcoves + forward + backward;
+    }
+    __syncthreads();
+}

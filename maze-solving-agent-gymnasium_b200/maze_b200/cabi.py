@@ -17,6 +17,8 @@ ST_NEEDS_RESET, ST_WON, ST_MOVE_SHIFT, ST_NMOVES_SHIFT = 0x01, 0x02, 2, 4
 STEP_AUTORESET, STEP_WIN_NEXT, STEP_WIN_QUEUE = 0x01, 0x02, 0x04
 ALGO_RPRIM, ALGO_DFS, ALGO_PRIMKILL = 0, 1, 2
 MAX_DIM, GEN_MAX_DIM, WINDOW = 255, 131, 15
+METRIC_WORDS = 8
+METRIC_NAMES = ("difficulty", "complexity", "L", "DE", "D", "sol_len", "de_count")
 E_NULL, E_RANGE, E_SHAPE, E_ALGO, E_ALIGN = -1, -2, -3, -4, -5
 
 
@@ -49,6 +51,8 @@ SIGNATURES = {
     "maze_reset": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p]),
     "maze_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_void_p]),
+    "maze_difficulty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
 }
 
 

@@ -133,6 +133,21 @@ class MazePool:
                                       int(seed) & (2**64 - 1), int(slot_id_base), cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_generate")
 
+    def difficulty(self, ids=None) -> torch.Tensor:
+        """float64 [n, 8] metric records (cabi.METRIC_NAMES) of the given slots (all if None):
+        McClendon difficulty / complexity, Kim-Crawfis L / DE / D, solution length, dead-end count."""
+        if ids is None:
+            ids_t, n = None, self.num_mazes
+        else:
+            ids_t = torch.as_tensor(ids, dtype=torch.int32, device=self.device).contiguous()
+            n = ids_t.numel()
+        out = torch.empty((n, cabi.METRIC_WORDS), dtype=torch.float64, device=self.device)
+        rc = cabi.lib().maze_difficulty(self.ctx.handle, cabi.ptr(self.grids), cabi.ptr(self.meta), cabi.ptr(ids_t), n,
+                                        self.slot, self.max_shape[0], self.max_shape[1], cabi.ptr(out),
+                                        cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_difficulty")
+        return out
+
     # -- host views (tests, facade)
     def meta_host(self):
         return self.meta.cpu().numpy()
