@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 1
+#define MAZE_ABI_VERSION 2
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -146,11 +146,16 @@ int maze_reset(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* mask, void
  *   count_dev optional device int32: number of valid entries of ids (then n = capacity); lets a
  *             regeneration queue filled by maze_step be drained without a host round trip
  *   max_h/w   largest final shape among the slots (sizes shared memory)
- *   RNG       Philox4x32-10, key = seed, counter = (slot_id_base + slot, generation count):
- *             results do not depend on how slots are sharded over GPUs. */
+ *   candidates 1 = the raw generator; k > 1 = BaseMazeEnv.generate_maze (base_maze_env.py:78-97,
+ *             toroidal_maze_env.py:40-54): draw k mazes, keep the one with the lowest McClendon
+ *             difficulty (strict <, the first wins ties); difficulty is taken on the bordered maze
+ *   difficulty optional [n] out: difficulty of the maze kept for ids[k] (NULL with candidates 1
+ *             skips the evaluation)
+ *   RNG       Philox4x32-10, key = seed, counter = (slot_id_base + slot, generation count,
+ *             candidate): results do not depend on how slots are sharded over GPUs. */
 int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8_t* table, const int32_t* ids,
                   const int32_t* count_dev, int n, int slot, int max_h, int max_w,
-                  uint64_t seed, int64_t slot_id_base, void* stream);
+                  uint64_t seed, int64_t slot_id_base, int candidates, double* difficulty, void* stream);
 
 /* Difficulty metrics of pool mazes, one record of MAZE_METRIC_WORDS doubles per processed slot
  * (out[k] belongs to ids[k], or to slot k when ids is NULL):

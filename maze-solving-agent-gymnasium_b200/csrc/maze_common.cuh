@@ -81,10 +81,11 @@ struct Philox {
     uint32_t o0, o1, o2, o3;
     int have;
 
-    __host__ __device__ void init(uint64_t seed, uint64_t seq) {
+    // `sub` selects one of 2^32 sub-streams of (seed, seq) (each 2^32 blocks long)
+    __host__ __device__ void init(uint64_t seed, uint64_t seq, uint32_t sub = 0) {
         k0 = (uint32_t)seed;
         k1 = (uint32_t)(seed >> 32);
-        c0 = 0; c1 = 0;
+        c0 = 0; c1 = sub;
         c2 = (uint32_t)seq;
         c3 = (uint32_t)(seq >> 32);
         have = 0;

@@ -12,7 +12,7 @@
 // RNG: Philox4x32-10 keyed by (seed, global slot id, generation count) -- the reference draws
 // from Python's global `random` through set iteration order, which cannot be replayed, so parity
 // for generators is structural (spanning tree) + distributional (see tests).
-#include "maze_fields.cuh"
+#include "maze_metrics.cuh"
 
 namespace {
 
@@ -28,6 +28,9 @@ struct GenParams {
     int n;
     int slot;
     int smem_hw;
+    int smem_cells;          // 0 when no metrics are needed
+    int candidates;          // best-of-k by McClendon difficulty (base_maze_env.py:78-97); 1 = raw generator
+    double* difficulty;      // [n] optional out: difficulty of the maze kept for item k
     unsigned long long seed;
     long long slot_id_base;
 };
@@ -229,14 +232,20 @@ __device__ void gen_prim_and_kill(uint8_t* grid, int Wb, int nr, int nc, int si,
     }
 }
 
+template <bool kScored>   // kScored: candidates > 1 or a difficulty output (keeps the raw path lean)
 __global__ void __launch_bounds__(GEN_THREADS)
 maze_generate_kernel(GenParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_start, s_goal;
+    __shared__ int s_start, s_goal, s_keep_start, s_keep_goal, s_take;
     __shared__ unsigned s_best;
+    __shared__ double s_keep_diff;
+    __shared__ MazeMetrics s_metrics;
     const int tid = threadIdx.x;
     const int n = p.count_dev ? min(*p.count_dev, p.n) : p.n;
     FieldSmem f = field_smem_carve(smem, p.smem_hw);
+    const size_t keep_bytes = ((size_t)p.smem_hw + 15) & ~(size_t)15;
+    uint8_t* keep = smem + field_smem_bytes(p.smem_hw);
+    MetricsSmem ms = metrics_smem_carve(keep + keep_bytes, p.smem_cells, f.queue);
 
     for (int item = blockIdx.x; item < n; item += gridDim.x) {
         const int m = p.ids ? p.ids[item] : item;
@@ -248,39 +257,63 @@ maze_generate_kernel(GenParams p) {
         const int gen_count = mm[MAZE_META_SPARE];
         const int Hb = tor ? H + 2 : H, Wb = tor ? W + 2 : W;   // :48 gen_maze(shape + 2)
         const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2;
-        __syncthreads();   // previous item fully written out before smem is reused
-        for (int i = tid; i < Hb * Wb; i += GEN_THREADS) f.grid[i] = 0;
-        __syncthreads();
 
-        if (tid < 32) {
-            Philox rng;
-            rng.init(p.seed, (unsigned long long)(p.slot_id_base + m) | ((unsigned long long)(unsigned)gen_count << 40));
-            const int si = (int)rng.below((unsigned)nr);   // :21 uniform logical cell
-            const int sj = (int)rng.below((unsigned)nc);
-            if (algo == MAZE_ALGO_RPRIM) gen_random_prim(f.grid, Wb, nr, nc, si, sj, rng);
-            else if (algo == MAZE_ALGO_DFS) gen_depth_first(f.grid, f.queue, Wb, nr, nc, si, sj, rng);
-            else gen_prim_and_kill(f.grid, Wb, nr, nc, si, sj, rng);
-            if (tid == 0) { s_start = (2 * si + 1) * Wb + 2 * sj + 1; s_best = 0u; }
+        for (int cand = 0; cand < p.candidates; ++cand) {
+            __syncthreads();   // previous item / candidate fully consumed before smem is reused
+            for (int i = tid; i < Hb * Wb; i += GEN_THREADS) f.grid[i] = 0;
+            __syncthreads();
+
+            if (tid < 32) {
+                Philox rng;
+                rng.init(p.seed, (unsigned long long)(p.slot_id_base + m) | ((unsigned long long)(unsigned)gen_count << 40),
+                         (unsigned)cand);
+                const int si = (int)rng.below((unsigned)nr);   // :21 uniform logical cell
+                const int sj = (int)rng.below((unsigned)nc);
+                if (algo == MAZE_ALGO_RPRIM) gen_random_prim(f.grid, Wb, nr, nc, si, sj, rng);
+                else if (algo == MAZE_ALGO_DFS) gen_depth_first(f.grid, f.queue, Wb, nr, nc, si, sj, rng);
+                else gen_prim_and_kill(f.grid, Wb, nr, nc, si, sj, rng);
+                if (tid == 0) { s_start = (2 * si + 1) * Wb + 2 * sj + 1; s_best = 0u; }
+            }
+            __syncthreads();
+
+            // goal = farthest leaf from start, first in row-major order on ties (:187-218)
+            const int start_idx = s_start;
+            block_bfs(f, Hb, Wb, false, start_idx);
+            for (int t = tid; t < nr * nc; t += GEN_THREADS) {
+                const int r = 2 * (t / nc) + 1, c = 2 * (t % nc) + 1;
+                const int idx = r * Wb + c;
+                if (idx == start_idx) continue;
+                const int open_nb = (f.grid[idx - Wb] != 0) + (f.grid[idx + Wb] != 0) + (f.grid[idx - 1] != 0) + (f.grid[idx + 1] != 0);
+                if (open_nb == 1) atomicMax(&s_best, ((unsigned)f.dist[idx] << 15) | (unsigned)(32767 - idx));
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned key = s_best;
+                s_goal = key ? 32767 - (int)(key & 32767u) : start_idx;
+                f.grid[s_goal] = 2;   // :33
+            }
+            __syncthreads();
+
+            if constexpr (kScored) {
+                // McClendon difficulty of the bordered maze (base_maze_env.py:86-92; for border-less
+                // mazes lib/maze_generation.py:51); f.dist still holds the distances from start
+                maze_metrics(f, ms, Hb, Wb, start_idx, s_goal, s_metrics, false);
+                if (tid == 0) {
+                    s_take = (cand == 0) || (s_metrics.difficulty < s_keep_diff);   // strict <, first wins ties
+                    if (s_take) { s_keep_diff = s_metrics.difficulty; s_keep_start = start_idx; s_keep_goal = s_goal; }
+                }
+                __syncthreads();
+                if (p.candidates > 1 && s_take)
+                    for (int i = tid; i < Hb * Wb; i += GEN_THREADS) keep[i] = f.grid[i];
+            }
         }
-        __syncthreads();
-
-        // goal = farthest leaf from start, first in row-major order on ties (:187-218)
+        if (kScored && p.candidates > 1) {
+            __syncthreads();
+            for (int i = tid; i < Hb * Wb; i += GEN_THREADS) f.grid[i] = keep[i];
+            if (tid == 0) { s_start = s_keep_start; s_goal = s_keep_goal; }
+            __syncthreads();
+        }
         const int start_idx = s_start;
-        block_bfs(f, Hb, Wb, false, start_idx);
-        for (int t = tid; t < nr * nc; t += GEN_THREADS) {
-            const int r = 2 * (t / nc) + 1, c = 2 * (t % nc) + 1;
-            const int idx = r * Wb + c;
-            if (idx == start_idx) continue;
-            const int open_nb = (f.grid[idx - Wb] != 0) + (f.grid[idx + Wb] != 0) + (f.grid[idx - 1] != 0) + (f.grid[idx + 1] != 0);
-            if (open_nb == 1) atomicMax(&s_best, ((unsigned)f.dist[idx] << 15) | (unsigned)(32767 - idx));
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned key = s_best;
-            s_goal = key ? 32767 - (int)(key & 32767u) : start_idx;
-            f.grid[s_goal] = 2;   // :33
-        }
-        __syncthreads();
         int sr = start_idx / Wb, sc = start_idx % Wb, gr = s_goal / Wb, gc = s_goal % Wb;
 
         if (tor) {   // :53-55 strip the outer ring
@@ -306,6 +339,7 @@ maze_generate_kernel(GenParams p) {
             mm[MAZE_META_SOL_LEN] = sol_len;
             mm[MAZE_META_MAX_STEPS] = max_steps_budget(H, W, sol_len);
             mm[MAZE_META_SPARE] = gen_count + 1;
+            if (kScored && p.difficulty) p.difficulty[item] = s_keep_diff;
         }
     }
 }
@@ -314,10 +348,11 @@ maze_generate_kernel(GenParams p) {
 
 extern "C" int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8_t* table, const int32_t* ids,
                              const int32_t* count_dev, int n, int slot, int max_h, int max_w,
-                             uint64_t seed, int64_t slot_id_base, void* stream) {
+                             uint64_t seed, int64_t slot_id_base, int candidates, double* difficulty, void* stream) {
     if (!ctx) return MAZE_E_NULL;
     if (!meta || !table) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_generate pointer");
     if (n <= 0 || slot <= 0) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_generate n / slot");
+    if (candidates < 1 || candidates > 64) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_generate candidates (1..64)");
     if (max_h < 5 || max_w < 5 || !(max_h & 1) || !(max_w & 1) || max_h + 2 > MAZE_GEN_MAX_DIM || max_w + 2 > MAZE_GEN_MAX_DIM)
         return maze_fail_arg(ctx, MAZE_E_SHAPE, "maze_generate: max shape must be odd, >= 5 and <= MAZE_GEN_MAX_DIM - 2");
     if (max_h * max_w > slot) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_generate: slot smaller than max shape");
@@ -325,15 +360,21 @@ extern "C" int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8
     p.grids = grids; p.meta = meta; p.table = table; p.ids = ids; p.count_dev = count_dev;
     p.n = n; p.slot = slot;
     p.smem_hw = (max_h + 2) * (max_w + 2);
+    const bool scored = candidates > 1 || difficulty != nullptr;
+    p.smem_cells = scored ? ((max_h + 1) / 2) * ((max_w + 1) / 2) : 0;
+    p.candidates = candidates;
+    p.difficulty = difficulty;
     p.seed = seed; p.slot_id_base = slot_id_base;
-    const size_t smem = field_smem_bytes(p.smem_hw);
-    MAZE_CHECK(cudaFuncSetAttribute(maze_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = field_smem_bytes(p.smem_hw);
+    if (scored) smem += (((size_t)p.smem_hw + 15) & ~(size_t)15) + metrics_smem_bytes(p.smem_cells);
+    auto kernel = scored ? maze_generate_kernel<true> : maze_generate_kernel<false>;
+    MAZE_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MAZE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, maze_generate_kernel, GEN_THREADS, smem));
+    MAZE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GEN_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const int resident = per_sm * (ctx->num_sms > 0 ? ctx->num_sms : 148);
     const int grid = n < resident ? n : resident;
-    maze_generate_kernel<<<grid, GEN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    kernel<<<grid, GEN_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

@@ -14,7 +14,7 @@ maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restr
     __shared__ MazeMetrics s_out;
     const int tid = threadIdx.x;
     FieldSmem f = field_smem_carve(smem, smem_hw);
-    MetricsSmem ms = metrics_smem_carve(smem + field_smem_bytes(smem_hw), smem_cells);
+    MetricsSmem ms = metrics_smem_carve(smem + field_smem_bytes(smem_hw), smem_cells, f.queue);
     for (int item = blockIdx.x; item < n; item += gridDim.x) {
         const int m = ids ? ids[item] : item;
         const int32_t* mm = meta + (size_t)m * MAZE_META_WORDS;

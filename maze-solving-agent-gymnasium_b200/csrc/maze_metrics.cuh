@@ -26,24 +26,25 @@ struct MetricsSmem {
 
 constexpr int MF_NB = 0x07, MF_TURN = 0x08, MF_SOL = 0x10, MF_NODE = 0x20, MF_DP = 0x40;
 
+// The four u16 arrays (8 bytes per cell) live in the BFS queue of FieldSmem, which is dead once
+// the distances from start exist (2 * H * W bytes > 8 * cells); the rest is carved from `base`.
 __host__ __device__ inline size_t metrics_smem_bytes(int cells) {
-    // 4 x u16 + u8 + u32 + 2 x f64 per cell, each array 16-byte aligned
     auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    return 4 * up(2 * (size_t)cells) + up((size_t)cells) + up(4 * (size_t)cells) + 2 * up(8 * (size_t)cells);
+    return 2 * up(8 * (size_t)cells) + up(4 * (size_t)cells) + up((size_t)cells);
 }
 
-__device__ inline MetricsSmem metrics_smem_carve(unsigned char* base, int cells) {
+__device__ inline MetricsSmem metrics_smem_carve(unsigned char* base, int cells, unsigned short* bfs_queue) {
     auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
     MetricsSmem m;
     size_t o = 0;
     m.ssum = reinterpret_cast<double*>(base + o); o += up(8 * (size_t)cells);
     m.bsum = reinterpret_cast<double*>(base + o); o += up(8 * (size_t)cells);
     m.dsum = reinterpret_cast<unsigned int*>(base + o); o += up(4 * (size_t)cells);
-    m.pnode = reinterpret_cast<unsigned short*>(base + o); o += up(2 * (size_t)cells);
-    m.dpar = reinterpret_cast<unsigned short*>(base + o); o += up(2 * (size_t)cells);
-    m.comp = reinterpret_cast<unsigned short*>(base + o); o += up(2 * (size_t)cells);
-    m.minleaf = reinterpret_cast<unsigned short*>(base + o); o += up(2 * (size_t)cells);
     m.flags = base + o;
+    m.pnode = bfs_queue;
+    m.dpar = bfs_queue + cells;
+    m.comp = bfs_queue + 2 * cells;
+    m.minleaf = bfs_queue + 3 * cells;
     return m;
 }
 
@@ -68,8 +69,9 @@ struct MazeMetrics {
 };
 
 // All threads of the CTA call this; the result is valid on thread 0.
+// with_kc = false skips the (sequential) Kim-Crawfis DE pass: DE / de_count are then 0.
 __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, int Hb, int Wb,
-                                    int start_idx, int goal_idx, MazeMetrics& out) {
+                                    int start_idx, int goal_idx, MazeMetrics& out, bool with_kc = true) {
     __shared__ double s_D0, s_S0, s_red[2][FIELD_THREADS / 32];
     __shared__ int s_dcount;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -160,7 +162,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
 
     // ---- 4. Kim-Crawfis DE: sequential over dead ends in row-major order (metrics_calculator.py:87-173)
     int alcoves = 0, forward = 0, backward = 0;
-    if (tid == 0) {
+    if (tid == 0 && with_kc) {
         const int gr = goal_idx / Wb, gc = goal_idx % Wb;
         for (int de = 0; de < cells; ++de) {
             if (!is_dead_end_off(de)) continue;

@@ -87,11 +87,13 @@ class MazePool:
         self.ctx.check(rc, "maze_fields")
 
     def generate(self, ids=None, shapes=None, algorithms="r-prim", toroidal=False, seed=0, slot_id_base=0,
-                 count_dev=None, configure=True):
+                 count_dev=None, configure=True, candidates=1, difficulty_out=None):
         """Generate mazes on the device into the given slots (all if None).
 
         shapes / algorithms / toroidal may be scalars or per-slot sequences.  With configure=False
-        the per-slot meta (H, W, FLAGS) already on the device is reused (regeneration)."""
+        the per-slot meta (H, W, FLAGS) already on the device is reused (regeneration).
+        candidates=6 reproduces BaseMazeEnv.generate_maze (keep the least difficult of six draws);
+        difficulty_out: optional float64 [n] device tensor receiving the kept maze's difficulty."""
         if ids is None:
             ids_list = list(range(self.num_mazes))
             ids_t = None
@@ -130,7 +132,8 @@ class MazePool:
             self.meta[idx, cabi.META_FLAGS] = cfg[:, 2]
         rc = cabi.lib().maze_generate(self.ctx.handle, cabi.ptr(self.grids), cabi.ptr(self.meta), cabi.ptr(self.table),
                                       cabi.ptr(ids_t), cabi.ptr(count_dev), n, self.slot, max_h, max_w,
-                                      int(seed) & (2**64 - 1), int(slot_id_base), cabi.current_stream(self.device))
+                                      int(seed) & (2**64 - 1), int(slot_id_base), int(candidates),
+                                      cabi.ptr(difficulty_out), cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_generate")
 
     def difficulty(self, ids=None) -> torch.Tensor:

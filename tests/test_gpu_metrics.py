@@ -87,3 +87,33 @@ def test_unreachable_goal_gives_nan():
     pool = mb.MazePool.from_grids([g], [(1, 1)], [(5, 5)], False)
     out = pool.difficulty().cpu().numpy()[0]
     assert np.isnan(out[:5]).all()
+
+
+@pytest.mark.parametrize("algo,toroidal", [("r-prim", False), ("dfs", False), ("prim&kill", True)])
+def test_best_of_k_selection(algo, toroidal):
+    """BaseMazeEnv.generate_maze (base_maze_env.py:78-97): keep the least difficult of 1 + 5 draws,
+    strict <.  Candidate c of a slot is the same maze for every k > c, so the kept difficulty is a
+    running minimum over k and the kept maze only changes when the minimum does."""
+    import maze_b200 as mb
+    n, shape = 48, (21, 21)
+    prev_d, prev_grids = None, None
+    for k in range(1, 7):
+        pool = mb.MazePool(n, shape)
+        dout = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+        pool.generate(algorithms=algo, toroidal=toroidal, seed=77, candidates=k, difficulty_out=dout)
+        d = dout.cpu().numpy()
+        rescored = pool.difficulty().cpu().numpy()[:, 0]
+        # the reported difficulty is the kept maze's (shared-memory float atomics: last-ulp run-to-run noise)
+        np.testing.assert_allclose(d, rescored, rtol=1e-12)
+        grids = [pool.grid_host(m).copy() for m in range(n)]
+        if prev_d is not None:
+            assert (d <= prev_d * (1 + 1e-12)).all()
+            for m in range(n):
+                if abs(d[m] - prev_d[m]) <= 1e-12 * prev_d[m]:
+                    np.testing.assert_array_equal(grids[m], prev_grids[m])
+        prev_d, prev_grids = d, grids
+    # six draws must have found easier mazes for most slots
+    pool1 = mb.MazePool(n, shape)
+    pool1.generate(algorithms=algo, toroidal=toroidal, seed=77)
+    d1 = pool1.difficulty().cpu().numpy()[:, 0]
+    assert (prev_d <= d1 * (1 + 1e-12)).all() and (prev_d < d1 * (1 - 1e-9)).mean() > 0.5
