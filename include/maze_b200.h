@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 2
+#define MAZE_ABI_VERSION 3
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -89,7 +89,10 @@ typedef struct maze_env_batch {
     const uint8_t* table;  /* [M, slot] step-table bytes                                     */
     int32_t*  env_maze;    /* [B] maze slot of each env                                      */
     uint64_t* state;       /* [B] packed state                                               */
-    uint16_t* visits;      /* [slot, B] cell-major: epoch << 8 | saturating visit count      */
+    uint16_t* visits;      /* epoch << 8 | saturating visit count of (block idx, env e) at
+                              idx * visit_cell_stride + e * visit_env_stride: cell-major
+                              [slot, B] (strides B, 1) for the -v0 step; env-major [B, slot]
+                              (strides 1, slot) when the 15x15 window is read every step      */
     /* outputs of step / reset (reference obs dict of base_maze_env.py:116-122) */
     int32_t*  agent;       /* [B, 2] int32                                                   */
     int32_t*  target;      /* [B, 2]                                                         */
@@ -104,6 +107,8 @@ typedef struct maze_env_batch {
     /* optional regeneration queue (MAZE_STEP_WIN_QUEUE) */
     int32_t*  queue;       /* [B] maze slots whose env won                                   */
     int32_t*  queue_count; /* [1]                                                            */
+    int64_t   visit_cell_stride;
+    int64_t   visit_env_stride;
 } maze_env_batch;
 
 int  maze_abi_version(void);
@@ -156,6 +161,24 @@ int maze_reset(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* mask, void
 int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8_t* table, const int32_t* ids,
                   const int32_t* count_dev, int n, int slot, int max_h, int max_w,
                   uint64_t seed, int64_t slot_id_base, int candidates, double* difficulty, void* stream);
+
+/* Enriched (-v1) observation: SimpleEnrichMazeEnv._get_obs (simple_maze_env.py:151-158) and the
+ * toroidal / variable-size variants (toroidal_maze_env.py:164-172, simple_variable_maze_env.py:
+ * 170-179, toroidal_variable_maze_env.py:186-194) for the current position of every env:
+ *   window      [B, 3, 15, 15] float32 = [maze == 0, maze == 1 (goal excluded), non_visited] of the
+ *               15 x 15 crop around the agent: lib/maze_handler.py:4-54 (euclid: clamped into the
+ *               grid, so not centred near the border), :56-80 (torus: centred, wraps), :82-99
+ *   agent_norm  [B, 2] float64 = agent / maze_shape, target_norm likewise (either may be NULL)
+ * Needs H, W >= 15.  Reads the step table, so the goal block must be the pool's goal (value 2). */
+int maze_window(maze_ctx* ctx, const maze_env_batch* b, float* window, double* agent_norm, double* target_norm,
+                void* stream);
+
+/* get_mask_direction (simple_maze_env.py:41-50, toroidal_maze_env.py:57-70; lib/maze_handler.py:
+ * 122-162): mask [B, 4] float32 in action order (down, up, right, left), 1 where the neighbour
+ * block is open.  probs != 0: once an episode has made two successful moves the entry pointing
+ * back to the previous block is overwritten with 0.25 (the toroidal env builds that direction
+ * column-first, so the 0.25 lands on a rotated index -- reproduced). */
+int maze_direction_mask(maze_ctx* ctx, const maze_env_batch* b, int probs, float* mask, void* stream);
 
 /* Difficulty metrics of pool mazes, one record of MAZE_METRIC_WORDS doubles per processed slot
  * (out[k] belongs to ids[k], or to slot k when ids is NULL):

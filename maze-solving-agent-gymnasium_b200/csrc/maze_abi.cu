@@ -16,6 +16,24 @@ int maze_fail_arg(maze_ctx* ctx, int code, const char* what) {
     return code;
 }
 
+// argument validation shared by every entry point that takes a maze_env_batch
+int maze_check_batch(maze_ctx* ctx, const maze_env_batch* b) {
+    if (!b) return maze_fail_arg(ctx, MAZE_E_NULL, "batch");
+    if (!b->meta || !b->table || !b->env_maze || !b->state || !b->visits || !b->agent || !b->target ||
+        !b->best_dir || !b->reward || !b->terminated || !b->truncated)
+        return maze_fail_arg(ctx, MAZE_E_NULL, "batch pointer");
+    if (b->num_envs <= 0 || b->num_mazes <= 0 || b->slot <= 0 || (b->slot & 1))
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "num_envs / num_mazes / slot (must be even)");
+    if (b->visit_cell_stride <= 0 || b->visit_env_stride <= 0)
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "visit strides (cell-major: B, 1; env-major: 1, slot)");
+    if (((uintptr_t)b->meta & 15) || ((uintptr_t)b->state & 7) || ((uintptr_t)b->agent & 7) ||
+        ((uintptr_t)b->target & 7) || ((uintptr_t)b->best_dir & 7) || ((uintptr_t)b->reward & 7) ||
+        ((uintptr_t)b->visits & 3))
+        return maze_fail_arg(ctx, MAZE_E_ALIGN, "batch pointer alignment");
+    return 0;
+}
+
+
 extern "C" int maze_abi_version(void) { return MAZE_ABI_VERSION; }
 
 extern "C" int maze_ctx_create(maze_ctx** out, int device) {

@@ -24,6 +24,7 @@ struct maze_ctx {
 
 int maze_fail_cuda(maze_ctx* ctx, cudaError_t e, const char* what);
 int maze_fail_arg(maze_ctx* ctx, int code, const char* what);
+int maze_check_batch(maze_ctx* ctx, const maze_env_batch* b);
 
 // ---------------------------------------------------------------------------------------------
 // packed per-env state (see include/maze_b200.h)

@@ -74,13 +74,6 @@ __device__ __forceinline__ int pick_uniform(unsigned long long s0, unsigned long
     return __shfl_sync(FULL, packed, owner);
 }
 
-__device__ __forceinline__ bool row_bit(const RowSets& s, int i, int j) {   // any lane may ask
-    const int lane = threadIdx.x & 31;
-    bool mine = false;
-    if ((i & 31) == lane) mine = (((i >> 5) ? s.a1 : s.a0) >> j) & 1ull;
-    return __shfl_sync(FULL, (int)mine, i & 31) != 0;
-}
-
 // 4-bit mask of lattice neighbours of (i, j) whose bit in `s` equals `want`:
 // bit0 up (i-1), bit1 down (i+1), bit2 left (j-1), bit3 right (j+1); out-of-lattice never counts
 __device__ __forceinline__ unsigned neighbour_mask(const RowSets& s, int i, int j, int nr, int nc, bool want) {

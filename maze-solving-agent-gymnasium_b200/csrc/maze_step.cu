@@ -15,7 +15,7 @@ constexpr int STEP_THREADS = 256;
 // share a maze are contiguous and start from the same block, so lanes of a warp standing on the
 // same block hit the same 64 bytes; lanes on different blocks cost one DRAM line each, exactly
 // like an env-major layout would.
-#define VISIT_AT(b, e, idx) ((b).visits + (size_t)(idx) * (b).num_envs + (e))
+#define VISIT_AT(b, e, idx) ((b).visits + (size_t)(idx) * (b).visit_cell_stride + (size_t)(e) * (b).visit_env_stride)
 
 struct StepLuts {
     const double* revisit;  // [256]
@@ -249,25 +249,11 @@ maze_reset_kernel(maze_env_batch b, const uint8_t* __restrict__ mask) {
     if (b.ep_return) b.ep_return[e] = 0.0;
 }
 
-int check_batch(maze_ctx* ctx, const maze_env_batch* b) {
-    if (!b) return maze_fail_arg(ctx, MAZE_E_NULL, "batch");
-    if (!b->meta || !b->table || !b->env_maze || !b->state || !b->visits || !b->agent || !b->target ||
-        !b->best_dir || !b->reward || !b->terminated || !b->truncated)
-        return maze_fail_arg(ctx, MAZE_E_NULL, "batch pointer");
-    if (b->num_envs <= 0 || b->num_mazes <= 0 || b->slot <= 0 || (b->slot & 1))
-        return maze_fail_arg(ctx, MAZE_E_RANGE, "num_envs / num_mazes / slot (must be even)");
-    if (((uintptr_t)b->meta & 15) || ((uintptr_t)b->state & 7) || ((uintptr_t)b->agent & 7) ||
-        ((uintptr_t)b->target & 7) || ((uintptr_t)b->best_dir & 7) || ((uintptr_t)b->reward & 7) ||
-        ((uintptr_t)b->visits & 3))
-        return maze_fail_arg(ctx, MAZE_E_ALIGN, "batch pointer alignment");
-    return 0;
-}
-
 }  // namespace
 
 extern "C" int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* actions, uint32_t mode, void* stream) {
     if (!ctx) return MAZE_E_NULL;
-    if (int rc = check_batch(ctx, b)) return rc;
+    if (int rc = maze_check_batch(ctx, b)) return rc;
     if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "actions");
     StepLuts luts;
     luts.revisit = ctx->d_lut_revisit;
@@ -295,7 +281,7 @@ extern "C" int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* 
 
 extern "C" int maze_reset(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* mask, void* stream) {
     if (!ctx) return MAZE_E_NULL;
-    if (int rc = check_batch(ctx, b)) return rc;
+    if (int rc = maze_check_batch(ctx, b)) return rc;
     const int grid = (b->num_envs + STEP_THREADS - 1) / STEP_THREADS;
     maze_reset_kernel<<<grid, STEP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, mask);
     MAZE_CHECK(cudaGetLastError());

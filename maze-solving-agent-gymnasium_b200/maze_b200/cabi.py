@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -30,6 +30,7 @@ class MazeEnvBatch(C.Structure):
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p),
         ("ep_return", C.c_void_p), ("stats", C.c_void_p), ("stats_return", C.c_void_p),
         ("queue", C.c_void_p), ("queue_count", C.c_void_p),
+        ("visit_cell_stride", C.c_int64), ("visit_env_stride", C.c_int64),
     ]
 
 
@@ -51,6 +52,8 @@ SIGNATURES = {
     "maze_reset": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p]),
     "maze_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "maze_window": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "maze_direction_mask": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_int, C.c_void_p, C.c_void_p]),
     "maze_difficulty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
 }

@@ -66,6 +66,7 @@ class MazePool:
             if H * W > self.slot:
                 raise ValueError(f"maze {g.shape} does not fit slot of {self.slot} bytes")
             hg[k, :H * W] = g.reshape(-1)
+            hg[k, int(t[0]) * W + int(t[1])] = 2   # the goal block carries 2 (lib/maze_generation.py:33)
             hm[k, cabi.META_H], hm[k, cabi.META_W] = H, W
             hm[k, cabi.META_START] = int(s[0]) | (int(s[1]) << 16)
             hm[k, cabi.META_GOAL] = int(t[0]) | (int(t[1]) << 16)
@@ -170,7 +171,12 @@ class MazeBatch:
     """B environments over a MazePool; the SoA buffers of `maze_env_batch`."""
 
     def __init__(self, pool: MazePool, num_envs: int, env_maze=None, stats: bool = False, pool_stride: int = 1,
-                 queue: bool = False):
+                 queue: bool = False, visit_layout: str = "cell"):
+        """visit_layout: "cell" = [slot, B] (best for the -v0 step: envs sharing a block share lines),
+        "env" = [B, slot] (best when the 15x15 window is read every step: rows are contiguous)."""
+        if visit_layout not in ("cell", "env"):
+            raise ValueError("visit_layout must be 'cell' or 'env'")
+        self.visit_layout = visit_layout
         self.pool = pool
         self.device = pool.device
         self.ctx = pool.ctx
@@ -181,7 +187,11 @@ class MazeBatch:
         self.env_maze = torch.as_tensor(env_maze, dtype=torch.int32, device=d).contiguous()
         assert self.env_maze.shape == (B,)
         self.state = torch.zeros(B, dtype=torch.int64, device=d)
-        self.visits = torch.zeros((pool.slot, B), dtype=torch.int16, device=d)   # cell-major
+        self.visits = torch.zeros((pool.slot, B) if visit_layout == "cell" else (B, pool.slot), dtype=torch.int16, device=d)
+        self.window = None       # float32 [B, 3, 15, 15], allocated by window()
+        self.agent_norm = None   # float64 [B, 2]
+        self.target_norm = None
+        self.dir_mask = None     # float32 [B, 4]
         self.agent = torch.zeros((B, 2), dtype=torch.int32, device=d)
         self.target = torch.zeros((B, 2), dtype=torch.int32, device=d)
         self.best_dir = torch.zeros((B, 2), dtype=torch.int32, device=d)
@@ -208,7 +218,9 @@ class MazeBatch:
             stats=None if self.stats is None else self.stats.data_ptr(),
             stats_return=None if self.stats_return is None else self.stats_return.data_ptr(),
             queue=None if self.queue is None else self.queue.data_ptr(),
-            queue_count=None if self.queue_count is None else self.queue_count.data_ptr())
+            queue_count=None if self.queue_count is None else self.queue_count.data_ptr(),
+            visit_cell_stride=self.num_envs if self.visit_layout == "cell" else 1,
+            visit_env_stride=1 if self.visit_layout == "cell" else p.slot)
 
     def reset(self, mask: Optional[torch.Tensor] = None):
         if mask is not None:
@@ -224,6 +236,28 @@ class MazeBatch:
         rc = cabi.lib().maze_step(self.ctx.handle, C.byref(self._c), cabi.ptr(actions), mode,
                                   cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_step")
+
+    def compute_window(self):
+        """Enriched observation of the current positions: fills self.window [B,3,15,15] float32 and
+        self.agent_norm / self.target_norm [B,2] float64 (agent / maze_shape, target / maze_shape)."""
+        if self.window is None:
+            d, B = self.device, self.num_envs
+            self.window = torch.empty((B, 3, cabi.WINDOW, cabi.WINDOW), dtype=torch.float32, device=d)
+            self.agent_norm = torch.empty((B, 2), dtype=torch.float64, device=d)
+            self.target_norm = torch.empty((B, 2), dtype=torch.float64, device=d)
+        rc = cabi.lib().maze_window(self.ctx.handle, C.byref(self._c), cabi.ptr(self.window), cabi.ptr(self.agent_norm),
+                                    cabi.ptr(self.target_norm), cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_window")
+        return self.window
+
+    def direction_mask(self, probs: bool = False):
+        """float32 [B, 4] get_mask_direction of every env (action order down, up, right, left)."""
+        if self.dir_mask is None:
+            self.dir_mask = torch.empty((self.num_envs, 4), dtype=torch.float32, device=self.device)
+        rc = cabi.lib().maze_direction_mask(self.ctx.handle, C.byref(self._c), int(bool(probs)), cabi.ptr(self.dir_mask),
+                                            cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_direction_mask")
+        return self.dir_mask
 
     def state_host(self):
         s = self.state.cpu().numpy().view(np.uint64)

@@ -1,0 +1,103 @@
+"""maze_window / maze_direction_mask through the C ABI vs the golden vectors recorded from the
+unmodified reference's -v1 ("Enrich") envs and get_mask_direction(probs=True).  Bit-exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden  # noqa: E402
+
+
+def _replay(meta, z, visit_layout, on_step):
+    import maze_b200 as mb
+    pool = mb.MazePool.from_grids([z[f"m{m['id']}_grid"] for m in meta], [m["start"] for m in meta],
+                                  [m["goal"] for m in meta], [m["topology"] == "torus" for m in meta])
+    pairs = [(k, m, j) for k, m in enumerate(meta) for j in m["tapes"]]
+    env_maze = torch.tensor([k for k, _, _ in pairs], dtype=torch.int32, device="cuda")
+    batch = mb.MazeBatch(pool, len(pairs), env_maze=env_maze, visit_layout=visit_layout)
+    tapes = [z[f"m{m['id']}_t{j}_action"] for _, m, j in pairs]
+    T = max(len(t) for t in tapes)
+    acts = np.zeros((T, len(pairs)), dtype=np.uint8)
+    for e, t in enumerate(tapes):
+        acts[:len(t), e] = t
+    acts_d = torch.from_numpy(acts).cuda()
+    batch.reset()
+    on_step(batch, pairs, 0)
+    for t in range(T):
+        batch.step(acts_d[t], mode=0)
+        on_step(batch, pairs, t + 1)
+
+
+@pytest.mark.parametrize("visit_layout", ["env", "cell"])
+def test_window_matches_reference_traces(golden_steps, visit_layout):
+    z, meta = golden_steps
+    meta = [m for m in meta if m["enrich"]]
+    assert len(meta) >= 5
+    checked = [0]
+
+    def on_step(batch, pairs, t):
+        win = batch.compute_window().cpu().numpy()
+        an, tn = batch.agent_norm.cpu().numpy(), batch.target_norm.cpu().numpy()
+        for e, (_, m, j) in enumerate(pairs):
+            pre = f"m{m['id']}_t{j}_"
+            if t > len(z[pre + "action"]):
+                continue
+            np.testing.assert_array_equal(win[e], z[pre + "window"][t].astype(np.float32), err_msg=f"{pre} step {t}")
+            np.testing.assert_array_equal(an[e].view(np.uint64), z[pre + "agent"][t].view(np.uint64), err_msg=f"{pre} step {t}")
+            np.testing.assert_array_equal(tn[e].view(np.uint64), z[pre + "target"][t].view(np.uint64))
+            checked[0] += 1
+
+    _replay(meta, z, visit_layout, on_step)
+    assert checked[0] > 2000
+
+
+def test_direction_mask_matches_reference_traces(golden_steps):
+    z, meta = golden_steps
+    checked = [0]
+
+    def on_step(batch, pairs, t):
+        probs = batch.direction_mask(probs=True).cpu().numpy()
+        plain = batch.direction_mask(probs=False).cpu().numpy()
+        for e, (_, m, j) in enumerate(pairs):
+            pre = f"m{m['id']}_t{j}_"
+            if t > len(z[pre + "action"]):
+                continue
+            ref = z[pre + "mask"][t]
+            np.testing.assert_array_equal(probs[e], ref, err_msg=f"{pre} step {t}")
+            assert set(np.unique(plain[e])) <= {0.0, 1.0}
+            np.testing.assert_array_equal(plain[e][ref != 0.25], ref[ref != 0.25])
+            checked[0] += 1
+
+    _replay(meta, z, "cell", on_step)
+    assert checked[0] > 5000
+
+
+def test_window_against_oracle_with_autoreset():
+    """Window after autoresets and revisits, both topologies, vs the closed-form oracle."""
+    from oracle.env_port import ClosedFormEnv
+    import maze_b200 as mb
+    z, meta = load_golden("bestdir")
+    rows = [m for m in meta if m["shape"] >= 15][:8]
+    mazes = [dict(grid=z[f"m{m['id']}_grid"], start=m["start"], goal=m["goal"], toroidal=m["topology"] == "torus") for m in rows]
+    pool = mb.MazePool.from_grids([m["grid"] for m in mazes], [m["start"] for m in mazes], [m["goal"] for m in mazes],
+                                  [m["toroidal"] for m in mazes])
+    B = len(mazes)
+    batch = mb.MazeBatch(pool, B, visit_layout="env")
+    envs = [ClosedFormEnv(m["grid"], m["start"], m["goal"], m["toroidal"], enrich=True) for m in mazes]
+    batch.reset()
+    obs = [e.reset()[0] for e in envs]
+    pending = [False] * B
+    rng = np.random.default_rng(3)
+    for t in range(500):
+        acts = rng.integers(0, 4, B).astype(np.uint8)
+        batch.step(torch.from_numpy(acts).cuda(), mode=mb.cabi.STEP_AUTORESET)
+        win = batch.compute_window().cpu().numpy()
+        for i, env in enumerate(envs):
+            if pending[i]:
+                o, _ = env.reset()
+                pending[i] = False
+            else:
+                o, _, tr, te, _ = env.step(int(acts[i]))
+                pending[i] = bool(tr or te)
+            np.testing.assert_array_equal(win[i], o["window"], err_msg=f"env {i} step {t}")
