@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 3
+#define MAZE_ABI_VERSION 4
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -179,6 +179,67 @@ int maze_window(maze_ctx* ctx, const maze_env_batch* b, float* window, double* a
  * back to the previous block is overwritten with 0.25 (the toroidal env builds that direction
  * column-first, so the 0.25 lands on a rotated index -- reproduced). */
 int maze_direction_mask(maze_ctx* ctx, const maze_env_batch* b, int probs, float* mask, void* stream);
+
+/* ---- tabular Q-learning / double Q-learning on the device -------------------------------------
+ * agents/q_agent.py:8-79 (QAgent) and agents/dq_agent.py:5-73 (DQAgent).  The reference keys its
+ * tables by str(obs) of {'agent', 'target', 'best dir'}; the device table is an open-addressing hash
+ * table keyed by the same triple (packed: agent row/col, target row/col, best-dir code, agent id),
+ * rows of 4 float64 that start at zero like the reference's defaultdict.  `envs_per_agent`
+ * consecutive envs share one agent (1 = independent replicas, the faithful reading of the
+ * reference; num_envs = one learner fed by every env: concurrent updates of one entry race and one
+ * wins, and gamma moves by eta / envs_per_agent per finished episode).
+ * Every env keeps its own `steps_done` for the epsilon schedule. */
+#define MAZE_Q_EMPTY     0xffffffffffffffffull
+#define MAZE_Q_NO_SLOT   0xffffffffu
+typedef struct maze_q_agent {
+    int64_t   capacity;        /* rows; power of two, <= 2^31                                   */
+    uint64_t* keys;            /* [capacity] packed observation keys, MAZE_Q_EMPTY when free    */
+    double*   q_a;             /* [capacity, 4]  q_values (QAgent) / q_a_values (DQAgent)       */
+    double*   q_b;             /* [capacity, 4]  q_b_values; NULL selects plain Q-learning      */
+    int32_t*  overflow;        /* [1] set when a key found no free row (grow the table)         */
+    int32_t   envs_per_agent;
+    int32_t   eps_len;
+    const double* eps_lut;     /* [eps_len] epsilon by steps_done (maze_q_epsilon_lut), the last
+                                  entry is used beyond the end                                  */
+    double*   gamma;           /* [ceil(B / envs_per_agent)] discount factor of each agent      */
+    double    lr;              /* learning rate                                                 */
+    double    eta;             /* update_hyperparameter step: gamma += eta if return > 0 else -= */
+    /* per-env learner state */
+    uint32_t* slot;            /* [B] row of the env's current observation, MAZE_Q_NO_SLOT = unknown */
+    uint32_t* steps_done;      /* [B] get_action calls made for this env                        */
+    uint8_t*  last_action;     /* [B] action chosen by maze_q_act (consumed by maze_q_update)   */
+    double*   ep_return;       /* [B] cumulative reward of the running episode                  */
+    /* randomness: Philox4x32-10 keyed by (seed, env_id_base + env, steps_done) ... */
+    uint64_t  seed;
+    int64_t   env_id_base;
+    /* ... unless replay tapes are given (tests: the reference's recorded numpy draws) */
+    const double*  u_tape;     /* [u_len, B] values np.random.random() returned, in call order  */
+    const uint8_t* a_tape;     /* [a_len, B] values action_space.sample() returned              */
+    uint32_t* tape_pos;        /* [2, B] cursors into u_tape / a_tape                           */
+    int32_t   u_len, a_len;
+} maze_q_agent;
+
+/* Host helper: out[i] = final + (initial - final) * exp(-1. * i / decay)  (q_agent.py:49), computed
+ * with libm exp on the host like the reference.  `out` is a HOST pointer to n doubles. */
+int maze_q_epsilon_lut(double initial_epsilon, double final_epsilon, double decay, double* out, int n);
+
+/* QAgent.get_action / DQAgent.get_action for every env (q_agent.py:44-54, dq_agent.py:36-47):
+ * epsilon-greedy on q_a at the env's current observation; writes actions[B] (uint8) and remembers
+ * them in agent->last_action.  Envs waiting for an autoreset make no decision (action 0). */
+int maze_q_act(maze_ctx* ctx, const maze_env_batch* b, const maze_q_agent* agent, uint8_t* actions, void* stream);
+
+/* QAgent.update / DQAgent.update (q_agent.py:56-72, dq_agent.py:49-66) for the transition maze_step
+ * just made with agent->last_action: obs = the row remembered in agent->slot, next_obs = the env's
+ * new state, reward / terminated from the batch outputs.  Envs whose step was an autoreset only
+ * re-anchor their row.  On episode end applies update_hyperparameter (gamma +- eta,
+ * off_policy_trainer.py:76-78: increment iff the episode return is > 0). */
+int maze_q_update(maze_ctx* ctx, const maze_env_batch* b, const maze_q_agent* agent, void* stream);
+
+/* Fused rollout: k_steps iterations of { get_action ; BaseMazeEnv.step ; update } per env in ONE
+ * launch (the loop of off_policy_trainer.py:38-51), state kept in registers, with next-step
+ * autoreset.  Leaves the batch outputs (obs, reward, terminated, truncated) of the last step. */
+int maze_q_rollout(maze_ctx* ctx, const maze_env_batch* b, const maze_q_agent* agent, int k_steps, uint32_t mode,
+                   void* stream);
 
 /* Difficulty metrics of pool mazes, one record of MAZE_METRIC_WORDS doubles per processed slot
  * (out[k] belongs to ids[k], or to slot k when ids is NULL):

@@ -5,45 +5,11 @@
 // (L2/L1 resident for a maze pool); the only scattered DRAM access is the 2-byte visit counter of
 // the block stepped onto, fetched only for legal moves, from a cell-major array.
 // Reference semantics: gymnasium_env/envs/base_maze_env.py:136-210, lib/maze_view.py:165-197.
-#include "maze_common.cuh"
+#include "maze_env.cuh"
 
 namespace {
 
 constexpr int STEP_THREADS = 256;
-
-// Visit counters are stored cell-major: entry (cell idx, env e) at idx * num_envs + e.  Envs that
-// share a maze are contiguous and start from the same block, so lanes of a warp standing on the
-// same block hit the same 64 bytes; lanes on different blocks cost one DRAM line each, exactly
-// like an env-major layout would.
-#define VISIT_AT(b, e, idx) ((b).visits + (size_t)(idx) * (b).visit_cell_stride + (size_t)(e) * (b).visit_env_stride)
-
-struct StepLuts {
-    const double* revisit;  // [256]
-    const double* invalid;  // [256]
-    double shaping_same, shaping_closer, shaping_farther;   // D[prev]-D[cur] = 0, +1, -1
-};
-
-// Zero the visit counters of the lanes in `need` (epoch wrap-around: once per 255 episodes per
-// env; envs sharing a maze wrap together, so the lanes of a warp usually clear side by side).
-// Must be called by all 32 lanes.
-__device__ __forceinline__ void warp_clear_visits(unsigned need, const maze_env_batch& b, int e) {
-    if (need & (1u << (threadIdx.x & 31)))
-        for (int i = 0; i < b.slot; ++i) *VISIT_AT(b, e, i) = 0;
-}
-
-// Episode (re)start: BaseMazeEnv.reset, base_maze_env.py:136-161.  The start block is NOT
-// marked visited (:159), only excluded from non_visited (:149).
-__device__ __forceinline__ void begin_episode(EnvState& s, int start, int tab_at_start, bool& wrapped) {
-    s.r = start & 0xffff;
-    s.c = start >> 16;
-    s.consec = 0;
-    s.flags = 0;
-    s.steps = 0;
-    s.epoch += 1;
-    wrapped = s.epoch > 255;
-    if (wrapped) s.epoch = 1;
-    s.tab = tab_at_start;
-}
 
 // EPT environments per thread (env = base + k * STEP_THREADS keeps every access coalesced): the
 // loads of all EPT envs are issued phase by phase before anything waits on them.  The dependent
@@ -255,12 +221,7 @@ extern "C" int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* 
     if (!ctx) return MAZE_E_NULL;
     if (int rc = maze_check_batch(ctx, b)) return rc;
     if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "actions");
-    StepLuts luts;
-    luts.revisit = ctx->d_lut_revisit;
-    luts.invalid = ctx->d_lut_invalid;
-    luts.shaping_same = ctx->h_shaping[0];
-    luts.shaping_closer = ctx->h_shaping[1];
-    luts.shaping_farther = ctx->h_shaping[3];
+    const StepLuts luts = step_luts(ctx);
     const bool stats = b->ep_return || b->stats || ((mode & MAZE_STEP_WIN_QUEUE) && b->queue);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int ept = ctx->step_ept;

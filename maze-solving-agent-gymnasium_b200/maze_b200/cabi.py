@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -34,6 +34,21 @@ class MazeEnvBatch(C.Structure):
     ]
 
 
+class MazeQAgent(C.Structure):
+    _fields_ = [
+        ("capacity", C.c_int64), ("keys", C.c_void_p), ("q_a", C.c_void_p), ("q_b", C.c_void_p), ("overflow", C.c_void_p),
+        ("envs_per_agent", C.c_int32), ("eps_len", C.c_int32), ("eps_lut", C.c_void_p), ("gamma", C.c_void_p),
+        ("lr", C.c_double), ("eta", C.c_double),
+        ("slot", C.c_void_p), ("steps_done", C.c_void_p), ("last_action", C.c_void_p), ("ep_return", C.c_void_p),
+        ("seed", C.c_uint64), ("env_id_base", C.c_int64),
+        ("u_tape", C.c_void_p), ("a_tape", C.c_void_p), ("tape_pos", C.c_void_p), ("u_len", C.c_int32), ("a_len", C.c_int32),
+    ]
+
+
+Q_EMPTY = 0xffffffffffffffff
+Q_NO_SLOT = 0xffffffff
+
+
 class MazeError(RuntimeError):
     pass
 
@@ -54,6 +69,10 @@ SIGNATURES = {
                                 C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "maze_window": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maze_direction_mask": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_int, C.c_void_p, C.c_void_p]),
+    "maze_q_epsilon_lut": (C.c_int, [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int]),
+    "maze_q_act": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.POINTER(MazeQAgent), C.c_void_p, C.c_void_p]),
+    "maze_q_update": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.POINTER(MazeQAgent), C.c_void_p]),
+    "maze_q_rollout": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.POINTER(MazeQAgent), C.c_int, C.c_uint32, C.c_void_p]),
     "maze_difficulty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
 }
