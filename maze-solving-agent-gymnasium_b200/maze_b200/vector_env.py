@@ -24,12 +24,12 @@ import torch
 from . import cabi
 from .engine import MazeBatch, MazePool
 
-try:  # gymnasium is optional (absent from the build image)
+from . import _gym as _gymshim
+
+_gym = None
+if _gymshim.HAVE_GYMNASIUM:  # pragma: no cover - gymnasium is absent from the build image
     import gymnasium as _gym
-    _VectorBase = _gym.vector.VectorEnv
-except Exception:  # pragma: no cover
-    _gym = None
-    _VectorBase = object
+_VectorBase = _gymshim.VectorEnv
 
 
 class _LazyInfo(dict):
@@ -67,7 +67,10 @@ class MazeVectorEnv(_VectorBase):
     def __init__(self, num_envs: int, shape=(81, 81), topology: str = "euclid", algorithms="r-prim",
                  num_mazes: Optional[int] = None, device="cuda", seed: int = 0, autoreset: bool = True,
                  on_win: str = "keep", reference_order: bool = False, stats: bool = True,
-                 slot_id_base: int = 0, pool: Optional[MazePool] = None, env_maze=None):
+                 slot_id_base: int = 0, pool: Optional[MazePool] = None, env_maze=None, enrich: bool = False,
+                 candidates: int = 1):
+        """enrich=True gives the -v1 observation (normalised agent / target, 15x15 window);
+        candidates=6 makes every generated maze the least difficult of six (generate_maze)."""
         if topology not in ("euclid", "toroidal"):
             raise ValueError("topology must be 'euclid' or 'toroidal'")
         if on_win not in ("keep", "next", "regenerate"):
@@ -81,6 +84,10 @@ class MazeVectorEnv(_VectorBase):
         self.on_win = on_win
         self.reference_order = bool(reference_order)
         self.slot_id_base = int(slot_id_base)
+        self.enrich = bool(enrich)
+        self.candidates = int(candidates)
+        if self.enrich and min(self.shape) < cabi.WINDOW:
+            raise ValueError(f"the enriched observation needs mazes of at least {cabi.WINDOW} x {cabi.WINDOW} blocks")
         if pool is None:
             M = self.num_envs if num_mazes is None else int(num_mazes)
             pool = MazePool(M, self.shape, self.device)
@@ -88,7 +95,7 @@ class MazeVectorEnv(_VectorBase):
             if not isinstance(algorithms, str):
                 algos = [algorithms[i % len(algorithms)] for i in range(M)]
             pool.generate(shapes=self.shape, algorithms=algos, toroidal=(topology == "toroidal"),
-                          seed=self.seed, slot_id_base=self.slot_id_base)
+                          seed=self.seed, slot_id_base=self.slot_id_base, candidates=self.candidates)
         self.pool = pool
         if on_win == "regenerate" and pool.num_mazes != self.num_envs:
             raise ValueError("on_win='regenerate' needs one maze slot per env (num_mazes == num_envs)")
@@ -96,7 +103,8 @@ class MazeVectorEnv(_VectorBase):
             # contiguous envs share a maze: table reads of a warp hit the same lines
             per = max(1, self.num_envs // pool.num_mazes)
             env_maze = (torch.arange(self.num_envs, device=self.device, dtype=torch.int32) // per).clamp_(max=pool.num_mazes - 1)
-        self.batch = MazeBatch(pool, self.num_envs, env_maze=env_maze, stats=stats, queue=(on_win == "regenerate"))
+        self.batch = MazeBatch(pool, self.num_envs, env_maze=env_maze, stats=stats, queue=(on_win == "regenerate"),
+                               visit_layout="env" if self.enrich else "cell")
         self._mode = ((cabi.STEP_AUTORESET if self.autoreset else 0)
                       | (cabi.STEP_WIN_NEXT if on_win == "next" else 0)
                       | (cabi.STEP_WIN_QUEUE if on_win == "regenerate" else 0))
@@ -120,7 +128,14 @@ class MazeVectorEnv(_VectorBase):
     # ------------------------------------------------------------------------------------------
     def _obs(self):
         b = self.batch
+        if self.enrich:
+            b.compute_window()
+            return {"agent": b.agent_norm, "target": b.target_norm, "best dir": b.best_dir, "window": b.window}
         return {"agent": b.agent, "target": b.target, "best dir": b.best_dir}
+
+    def get_mask_direction(self, probs: bool = False):
+        """float32 [B, 4] direction mask of every env (env.get_mask_direction of the reference)."""
+        return self.batch.direction_mask(probs)
 
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
         """seed is accepted and ignored, like the reference (base_maze_env.py:136)."""
@@ -145,7 +160,7 @@ class MazeVectorEnv(_VectorBase):
         b.step(self._device_actions(actions), self._mode)
         if self.on_win == "regenerate":
             self.pool.generate(ids=b.queue, count_dev=b.queue_count, configure=False, seed=self.seed,
-                               slot_id_base=self.slot_id_base)
+                               slot_id_base=self.slot_id_base, candidates=self.candidates)
             b.queue_count.zero_()
         term, trunc = b.terminated.view(torch.bool), b.truncated.view(torch.bool)
         if self.reference_order:
@@ -163,13 +178,20 @@ class MazeVectorEnv(_VectorBase):
                                reward=torch.empty(B, dtype=torch.float64, **pin),
                                terminated=torch.empty(B, dtype=torch.uint8, **pin),
                                truncated=torch.empty(B, dtype=torch.uint8, **pin))
+            if self.enrich:
+                self._h_out.update(window=torch.empty((B, 3, cabi.WINDOW, cabi.WINDOW), dtype=torch.float32, **pin),
+                                   agent_norm=torch.empty((B, 2), dtype=torch.float64, **pin),
+                                   target_norm=torch.empty((B, 2), dtype=torch.float64, **pin))
         return self._h_out
 
     def h2d_bytes_per_step(self):
         return self.num_envs
 
     def d2h_bytes_per_step(self):
-        return self.num_envs * (3 * 8 + 8 + 1 + 1)
+        per = 3 * 8 + 8 + 1 + 1
+        if self.enrich:
+            per += 3 * cabi.WINDOW * cabi.WINDOW * 4 + 2 * 16
+        return self.num_envs * per
 
     def step_host(self, actions: np.ndarray):
         """Same transition as step() with HOST buffers on both sides: actions are copied to the
@@ -177,10 +199,12 @@ class MazeVectorEnv(_VectorBase):
         b = self.batch
         self.step(actions)
         h = self._host_out()
-        for k in ("agent", "target", "best_dir", "reward", "terminated", "truncated"):
+        for k in h:
             h[k].copy_(getattr(b, k), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         obs = {"agent": h["agent"].numpy(), "target": h["target"].numpy(), "best dir": h["best_dir"].numpy()}
+        if self.enrich:
+            obs.update(agent=h["agent_norm"].numpy(), target=h["target_norm"].numpy(), window=h["window"].numpy())
         term, trunc = h["terminated"].numpy().view(np.bool_), h["truncated"].numpy().view(np.bool_)
         info = {}
         if self.reference_order:
