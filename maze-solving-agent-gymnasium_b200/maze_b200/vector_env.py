@@ -211,13 +211,18 @@ class MazeVectorEnv(_VectorBase):
             return obs, h["reward"].numpy(), trunc, term, info
         return obs, h["reward"].numpy(), term, trunc, info
 
-    def episode_statistics(self):
-        """(episodes, wins, truncations, sum of returns) since construction; one small D2H."""
+    def episode_statistics(self, reduce: bool = False):
+        """Episodes / wins / truncations / return sum since construction (one small D2H); with
+        reduce=True summed over all ranks of the torch.distributed job (the only collective of
+        the env path: five float64 scalars at the end of a rollout)."""
+        from . import dist as mdist
         b = self.batch
         if b.stats is None:
             return None
-        s = b.stats.cpu().numpy()
-        return dict(episodes=int(s[0]), wins=int(s[1]), truncations=int(s[2]), return_sum=float(b.stats_return.cpu()[0]))
+        vec = torch.cat([b.stats.to(torch.float64), b.stats_return])
+        if reduce:
+            vec = mdist.reduce_statistics(vec)
+        return mdist.statistics_dict(vec)
 
     def close(self):
         pass

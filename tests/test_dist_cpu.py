@@ -1,0 +1,65 @@
+"""Host-side multi-GPU logic on CPU: index sharding and the statistics reduction over a
+world_size-2 gloo group (the N>1 path of bench.py / MazeVectorEnv.episode_statistics)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from maze_b200 import dist as mdist
+
+
+@pytest.mark.parametrize("total,world", [(4096000, 8), (1000, 3), (7, 8), (0, 2), (65536, 1)])
+def test_shard_range_partitions_the_index_space(total, world):
+    shards = [mdist.shard_range(total, r, world) for r in range(world)]
+    assert shards[0].start == 0 and shards[-1].stop == total
+    for a, b in zip(shards[:-1], shards[1:]):
+        assert a.stop == b.start
+    assert max(s.count for s in shards) - min(s.count for s in shards) <= 1
+    with pytest.raises(ValueError):
+        mdist.shard_range(total, world, world)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, total_envs, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r, lr, w = mdist.env_from_torchrun()
+        assert (r, lr, w) == (rank, rank, world)
+        sh = mdist.shard_range(total_envs, r, w)
+        # each rank "finishes" one episode per owned env, wins on even global ids, return = global id
+        ids = torch.arange(sh.start, sh.stop, dtype=torch.float64)
+        local = torch.tensor([ids.numel(), (ids % 2 == 0).sum().item(), (ids % 2 == 1).sum().item(), 10.0 * ids.numel(), ids.sum().item()],
+                             dtype=torch.float64)
+        red = mdist.reduce_statistics(local)
+        out[rank] = mdist.statistics_dict(red)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_statistics_reduction_gloo_world2():
+    world, total = 2, 1001
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), total, out), nprocs=world, join=True)
+        res = dict(out)
+    want = dict(episodes=total, wins=501, truncations=500, steps=10 * total, return_sum=float(total * (total - 1) // 2))
+    for r in range(world):
+        for k, v in want.items():
+            assert res[r][k] == v, (r, k, res[r])
+        assert res[r]["win_rate"] == pytest.approx(501 / 1001)
+
+
+def test_reduce_is_identity_without_a_process_group():
+    v = torch.arange(5, dtype=torch.float64)
+    assert torch.equal(mdist.reduce_statistics(v), v)
+    with pytest.raises(ValueError):
+        mdist.reduce_statistics(torch.zeros(4, dtype=torch.float64))

@@ -131,3 +131,22 @@ def test_generate_argument_errors():
         pool.generate(shapes=(20, 20))
     with pytest.raises(ValueError):
         pool.generate(shapes=(41, 41))
+
+
+@pytest.mark.parametrize("algo", ALGORITHMS)
+def test_generation_is_invariant_to_sharding(algo):
+    """RNG streams are keyed by the GLOBAL slot id: two ranks owning halves of the slot range
+    generate exactly the mazes one rank owning all of it would."""
+    from maze_b200.dist import shard_range
+    import maze_b200 as mb
+    M, shape = 40, (21, 21)
+    whole = mb.MazePool(M, shape)
+    whole.generate(algorithms=algo, seed=31, slot_id_base=0, candidates=2)
+    for world in (2, 3):
+        for r in range(world):
+            sh = shard_range(M, r, world)
+            part = mb.MazePool(sh.count, shape)
+            part.generate(algorithms=algo, seed=31, slot_id_base=sh.start, candidates=2)
+            assert torch.equal(part.grids, whole.grids[sh.start:sh.stop])
+            assert torch.equal(part.table, whole.table[sh.start:sh.stop])
+            assert torch.equal(part.meta, whole.meta[sh.start:sh.stop])
