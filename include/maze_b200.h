@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 4
+#define MAZE_ABI_VERSION 5
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -109,6 +109,10 @@ typedef struct maze_env_batch {
     int32_t*  queue_count; /* [1]                                                            */
     int64_t   visit_cell_stride;
     int64_t   visit_env_stride;
+    int32_t   visit_tiled; /* 0: block idx = r * W + c.  1: 4 x 4 block tiles, one 32-byte sector each:
+                              idx = ((r >> 2) * ((W + 3) >> 2) + (c >> 2)) * 16 + (r & 3) * 4 + (c & 3),
+                              so an agent walking a corridor keeps hitting the same sector      */
+    int32_t   visit_slot;  /* visit entries per env (>= slot; tiled: >= 16 * ceil(H/4) * ceil(W/4)) */
 } maze_env_batch;
 
 int  maze_abi_version(void);

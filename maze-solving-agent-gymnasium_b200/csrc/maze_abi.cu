@@ -24,6 +24,8 @@ int maze_check_batch(maze_ctx* ctx, const maze_env_batch* b) {
         return maze_fail_arg(ctx, MAZE_E_NULL, "batch pointer");
     if (b->num_envs <= 0 || b->num_mazes <= 0 || b->slot <= 0 || (b->slot & 1))
         return maze_fail_arg(ctx, MAZE_E_RANGE, "num_envs / num_mazes / slot (must be even)");
+    if (b->visit_slot < b->slot || (b->visit_tiled != 0 && b->visit_tiled != 1))
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "visit_slot (>= slot) / visit_tiled (0 or 1)");
     if (b->visit_cell_stride <= 0 || b->visit_env_stride <= 0)
         return maze_fail_arg(ctx, MAZE_E_RANGE, "visit strides (cell-major: B, 1; env-major: 1, slot)");
     if (((uintptr_t)b->meta & 15) || ((uintptr_t)b->state & 7) || ((uintptr_t)b->agent & 7) ||

@@ -6,7 +6,7 @@
 // 30 contiguous bytes).  HBM-write bound.
 // maze_direction_mask: one thread per env, four table bytes (lib/maze_handler.py:122-162,
 // simple_maze_env.py:41-50, toroidal_maze_env.py:57-70).
-#include "maze_common.cuh"
+#include "maze_env.cuh"
 
 namespace {
 
@@ -51,7 +51,7 @@ maze_window_kernel(maze_env_batch b, float* __restrict__ window, double* __restr
         const bool open = (__ldg(tab + idx) & MAZE_TAB_OPEN) != 0;
         bool fresh = false;   // non_visited (base_maze_env.py:148-149,183-184)
         if (open && idx != start_idx) {
-            const unsigned v = b.visits[(size_t)idx * b.visit_cell_stride + (size_t)e * b.visit_env_stride];
+            const unsigned v = *VISIT_AT(b, e, visit_index(b, rr, cc, W));
             fresh = !((int)(v >> 8) == st.epoch && (v & 0xffu) != 0);
         }
         __stcs(out + i, open ? 0.0f : 1.0f);                                    // maze == 0

@@ -10,17 +10,24 @@
 namespace {
 
 constexpr int STEP_THREADS = 256;
+#ifndef MAZE_STEP_MINB1
+#define MAZE_STEP_MINB1 6
+#endif
+#ifndef MAZE_STEP_MINB2
+#define MAZE_STEP_MINB2 5
+#endif
 
 // EPT environments per thread (env = base + k * STEP_THREADS keeps every access coalesced): the
 // loads of all EPT envs are issued phase by phase before anything waits on them.  The dependent
 // chain per env is state -> meta (L1) -> table byte (L2) -> visit counter (DRAM); the visit
 // counter is only fetched when the move is legal (a wall hit needs no counter), which matters
 // because every such fetch costs a whole DRAM line.
-template <int EPT, bool kStats>
-__global__ void __launch_bounds__(STEP_THREADS)
+template <int EPT, bool kStats, bool kTiled>
+__global__ void __launch_bounds__(STEP_THREADS, EPT == 2 ? MAZE_STEP_MINB2 : (EPT == 1 ? MAZE_STEP_MINB1 : 1))
 maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t mode, StepLuts luts) {
     const int base = blockIdx.x * (STEP_THREADS * EPT) + threadIdx.x;
 
+    const uint64_t pol_state = l2_policy<MAZE_STATE_POLICY>(), pol_table = l2_policy<MAZE_TABLE_POLICY>();
     // ---- phase 1: per-env words
     uint64_t raw[EPT];
     int m[EPT], a[EPT];
@@ -30,9 +37,9 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
         const int e = base + k * STEP_THREADS;
         valid[k] = e < b.num_envs;
         const int ee = valid[k] ? e : b.num_envs - 1;
-        raw[k] = b.state[ee];
-        m[k] = b.env_maze[ee];
-        a[k] = actions[ee] & 3;
+        raw[k] = pol_load<MAZE_STATE_POLICY>(reinterpret_cast<const unsigned long long*>(b.state) + ee, pol_state);
+        m[k] = pol_load<MAZE_STATE_POLICY>(b.env_maze + ee, pol_state);
+        a[k] = __ldcs(actions + ee) & 3;
     }
 
     // ---- phase 2: maze metadata (L1/L2 resident: contiguous envs share a maze)
@@ -45,7 +52,7 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
         if (do_reset[k] && (mode & MAZE_STEP_WIN_NEXT) && (flags & MAZE_ST_WON)) {
             m[k] += b.pool_stride;
             if (m[k] >= b.num_mazes) m[k] -= b.num_mazes;
-            b.env_maze[base + k * STEP_THREADS] = m[k];
+            pol_store<MAZE_STATE_POLICY>(b.env_maze + base + k * STEP_THREADS, m[k], pol_state);
         }
         const int2 shape = __ldg(reinterpret_cast<const int2*>(b.meta + (size_t)m[k] * MAZE_META_WORDS));
         hw[k] = shape.x | (shape.y << 16);
@@ -53,7 +60,7 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
     }
 
     // ---- phase 3: the block stepped onto: table byte
-    int npos[EPT], idx[EPT], tb[EPT];
+    int npos[EPT], idx[EPT], vidx[EPT], tb[EPT];
     bool inb[EPT];
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
@@ -78,17 +85,19 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
         if (!inb[k]) { nr = r; nc = c; }
         npos[k] = nr | (nc << 16);
         idx[k] = nr * W + nc;
-        tb[k] = __ldg(b.table + (size_t)m[k] * b.slot + idx[k]);
+        vidx[k] = kTiled ? ((((nr >> 2) * ((W + 3) >> 2) + (nc >> 2)) << 4) | ((nr & 3) << 2) | (nc & 3)) : idx[k];
+        tb[k] = pol_load_nc<MAZE_TABLE_POLICY>(b.table + (size_t)m[k] * b.slot + idx[k], pol_table);
     }
 
     // ---- phase 4: visit counter, only for legal moves
+    const uint64_t pol = l2_policy<MAZE_VISIT_POLICY>();
     uint32_t vis[EPT];
     bool moved[EPT];
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
         moved[k] = valid[k] && !do_reset[k] && inb[k] && (tb[k] & MAZE_TAB_OPEN);
         vis[k] = 0;
-        if (moved[k]) vis[k] = *VISIT_AT(b, base + k * STEP_THREADS, idx[k]);
+        if (moved[k]) vis[k] = visit_load(VISIT_AT(b, base + k * STEP_THREADS, vidx[k]), pol);
     }
 
     // ---- phase 5: transition + outputs
@@ -119,7 +128,7 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
                 } else {
                     reward = __ldg(luts.revisit + cnt);   // :194
                 }
-                *VISIT_AT(b, e, idx[k]) = (uint16_t)((st.epoch << 8) | (cnt < 255 ? cnt + 1 : 255));   // :196
+                visit_store(VISIT_AT(b, e, vidx[k]), (unsigned)((st.epoch << 8) | (cnt < 255 ? cnt + 1 : 255)), pol);   // :196
                 st.r = npos[k] & 0xffff;
                 st.c = npos[k] >> 16;
                 st.tab = tb[k];
@@ -146,7 +155,7 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
 
         if (!valid[k]) continue;
 
-        b.state[e] = pack_state(st);
+        pol_store<MAZE_STATE_POLICY>(reinterpret_cast<unsigned long long*>(b.state) + e, (unsigned long long)pack_state(st), pol_state);
         st_cs(reinterpret_cast<int2*>(b.agent) + e, make_int2(st.r, st.c));
         // `target` only changes when the env (re)starts on a possibly different maze; the buffer
         // persists between steps, so it is rewritten on reset only
@@ -155,8 +164,8 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
         st_cs(reinterpret_cast<int2*>(b.best_dir) + e,
               best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, H, W, tor[k] != 0));
         st_cs(b.reward + e, reward);
-        b.terminated[e] = (uint8_t)term;
-        b.truncated[e] = (uint8_t)trunc;
+        __stcs(b.terminated + e, (uint8_t)term);
+        __stcs(b.truncated + e, (uint8_t)trunc);
 
         if (kStats) {
             if (b.ep_return) {
@@ -227,15 +236,17 @@ extern "C" int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* 
     int ept = ctx->step_ept;
     if (b->num_envs < 64 * 1024) ept = 1;   // small batches: more CTAs beats more loads per thread
     auto grid_for = [&](int e) { return (b->num_envs + STEP_THREADS * e - 1) / (STEP_THREADS * e); };
-    if (stats) {
-        if (ept >= 4) maze_step_kernel<4, true><<<grid_for(4), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
-        else if (ept == 2) maze_step_kernel<2, true><<<grid_for(2), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
-        else maze_step_kernel<1, true><<<grid_for(1), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
-    } else {
-        if (ept >= 4) maze_step_kernel<4, false><<<grid_for(4), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
-        else if (ept == 2) maze_step_kernel<2, false><<<grid_for(2), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
-        else maze_step_kernel<1, false><<<grid_for(1), STEP_THREADS, 0, st>>>(*b, actions, mode, luts);
-    }
+    auto launch = [&](auto kernel, int e) { kernel<<<grid_for(e), STEP_THREADS, 0, st>>>(*b, actions, mode, luts); };
+#define MAZE_STEP_DISPATCH(EPT_)                                                                          \
+    do {                                                                                                  \
+        if (stats) { if (tiled) launch(maze_step_kernel<EPT_, true, true>, EPT_); else launch(maze_step_kernel<EPT_, true, false>, EPT_); } \
+        else       { if (tiled) launch(maze_step_kernel<EPT_, false, true>, EPT_); else launch(maze_step_kernel<EPT_, false, false>, EPT_); } \
+    } while (0)
+    const bool tiled = b->visit_tiled != 0;
+    if (ept >= 4) MAZE_STEP_DISPATCH(4);
+    else if (ept == 2) MAZE_STEP_DISPATCH(2);
+    else MAZE_STEP_DISPATCH(1);
+#undef MAZE_STEP_DISPATCH
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

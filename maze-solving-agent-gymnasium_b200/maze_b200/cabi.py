@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -31,6 +31,7 @@ class MazeEnvBatch(C.Structure):
         ("ep_return", C.c_void_p), ("stats", C.c_void_p), ("stats_return", C.c_void_p),
         ("queue", C.c_void_p), ("queue_count", C.c_void_p),
         ("visit_cell_stride", C.c_int64), ("visit_env_stride", C.c_int64),
+        ("visit_tiled", C.c_int32), ("visit_slot", C.c_int32),
     ]
 
 

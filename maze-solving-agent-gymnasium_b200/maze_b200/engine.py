@@ -173,9 +173,10 @@ class MazeBatch:
     def __init__(self, pool: MazePool, num_envs: int, env_maze=None, stats: bool = False, pool_stride: int = 1,
                  queue: bool = False, visit_layout: str = "cell"):
         """visit_layout: "cell" = [slot, B] (best for the -v0 step: envs sharing a block share lines),
-        "env" = [B, slot] (best when the 15x15 window is read every step: rows are contiguous)."""
-        if visit_layout not in ("cell", "env"):
-            raise ValueError("visit_layout must be 'cell' or 'env'")
+        "env" = [B, slot] (best when the 15x15 window is read every step: rows are contiguous),
+        "tile" = env-major with 4x4 block tiles per 32-byte sector (a walking agent stays in a sector)."""
+        if visit_layout not in ("cell", "env", "tile"):
+            raise ValueError("visit_layout must be 'cell', 'env' or 'tile'")
         self.visit_layout = visit_layout
         self.pool = pool
         self.device = pool.device
@@ -187,7 +188,10 @@ class MazeBatch:
         self.env_maze = torch.as_tensor(env_maze, dtype=torch.int32, device=d).contiguous()
         assert self.env_maze.shape == (B,)
         self.state = torch.zeros(B, dtype=torch.int64, device=d)
-        self.visits = torch.zeros((pool.slot, B) if visit_layout == "cell" else (B, pool.slot), dtype=torch.int16, device=d)
+        mh, mw = pool.max_shape
+        self.visit_slot = pool.slot if visit_layout != "tile" else _round_up(16 * ((mh + 3) // 4) * ((mw + 3) // 4), 16)
+        self.visits = torch.zeros((self.visit_slot, B) if visit_layout == "cell" else (B, self.visit_slot),
+                                  dtype=torch.int16, device=d)
         self.window = None       # float32 [B, 3, 15, 15], allocated by window()
         self.agent_norm = None   # float64 [B, 2]
         self.target_norm = None
@@ -220,7 +224,8 @@ class MazeBatch:
             queue=None if self.queue is None else self.queue.data_ptr(),
             queue_count=None if self.queue_count is None else self.queue_count.data_ptr(),
             visit_cell_stride=self.num_envs if self.visit_layout == "cell" else 1,
-            visit_env_stride=1 if self.visit_layout == "cell" else p.slot)
+            visit_env_stride=1 if self.visit_layout == "cell" else self.visit_slot,
+            visit_tiled=1 if self.visit_layout == "tile" else 0, visit_slot=self.visit_slot)
 
     def reset(self, mask: Optional[torch.Tensor] = None):
         if mask is not None:

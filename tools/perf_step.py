@@ -1,36 +1,39 @@
-"""Scratch: time maze_step on replicated golden mazes (before the generators exist)."""
-import json, os, sys, time
-import numpy as np, torch
+"""Scratch: maze_step time per launch for visit layouts x batch sizes, steady state, CUDA-graph replay.
+usage: python tools/perf_step.py [layouts] [sizes]   e.g.  cell,env,tile 1048576,4096000"""
+import os, sys
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "maze-solving-agent-gymnasium_b200"))
 import maze_b200 as mb
 
-z = np.load(os.path.join(ROOT, "tests/golden/metrics.npz"))
-meta = json.loads(str(z["meta"]))
-ms = [m for m in meta if m["shape"] == 81]
-M = 1000
-grids = [z[f"m{ms[i % len(ms)]['id']}_grid"] for i in range(M)]
-starts = [ms[i % len(ms)]["start"] for i in range(M)]
-goals = [ms[i % len(ms)]["goal"] for i in range(M)]
-t0 = time.time()
-pool = mb.MazePool.from_grids(grids, starts, goals, False)
-torch.cuda.synchronize(); print("pool", time.time() - t0)
-for B in [int(x) for x in (sys.argv[1:] or ["1048576", "4194304"])]:
-    env_maze = (torch.arange(B, device="cuda", dtype=torch.int32) // (B // M)).clamp_(max=M - 1)
-    batch = mb.MazeBatch(pool, B, env_maze=env_maze)
-    batch.reset()
-    K = 64
-    acts = torch.randint(0, 4, (K, B), dtype=torch.uint8, device="cuda")
-    mode = mb.cabi.STEP_AUTORESET
-    for t in range(300):
-        batch.step(acts[t % K], mode)
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    n = 200
-    ev[0].record()
-    for t in range(n):
-        batch.step(acts[t % K], mode)
-    ev[1].record(); torch.cuda.synchronize()
-    ms_ = ev[0].elapsed_time(ev[1]) / n
-    print(f"B={B} {ms_*1e3:.1f} us/step  {B/ms_*1e3:.3e} steps/s  algorithmic {58*B/ms_/1e6:.0f} GB/s")
-    del batch
+layouts = (sys.argv[1] if len(sys.argv) > 1 else "cell,env,tile").split(",")
+sizes = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "1048576,4096000").split(",")]
+M, TAPE = 1000, 16
+pool = mb.MazePool(M, (81, 81))
+pool.generate(algorithms="r-prim", seed=1234)
+mode = mb.cabi.STEP_AUTORESET | mb.cabi.STEP_WIN_NEXT
+for B in sizes:
+    acts = torch.randint(0, 4, (TAPE, B), dtype=torch.uint8, device="cuda")
+    for lay in layouts:
+        env_maze = (torch.arange(B, device="cuda", dtype=torch.int32) // max(1, B // M)).clamp_(max=M - 1)
+        batch = mb.MazeBatch(pool, B, env_maze=env_maze, visit_layout=lay)
+        batch.reset()
+        for t in range(TAPE):
+            batch.step(acts[t], mode)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for t in range(TAPE):
+                batch.step(acts[t], mode)
+        for _ in range(600 // TAPE):
+            g.replay()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 400 // TAPE
+        ev[0].record()
+        for _ in range(reps):
+            g.replay()
+        ev[1].record(); torch.cuda.synchronize()
+        us = ev[0].elapsed_time(ev[1]) / (reps * TAPE) * 1e3
+        print(f"B={B:8d} layout={lay:5s} {us:7.1f} us/step  {B/us*1e6:.3e} steps/s  algorithmic {58*B/us/1e3:.0f} GB/s  frac {58*B/us/1e3/6545.3:.3f}", flush=True)
+        del batch, g
