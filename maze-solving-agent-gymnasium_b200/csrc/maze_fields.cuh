@@ -118,6 +118,7 @@ __device__ inline void encode_step_table(const FieldSmem& f, int H, int W, bool 
     const int hw = H * W;
     const int L = 2 * (H < W ? H : W);
     for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+        if (f.grid[i] == 0) { out[i] = 0; continue; }   // walls carry no step information
         const int r = i / W, c = i - r * W;
         int best = 0x7fffffff, code = 4;
 #pragma unroll

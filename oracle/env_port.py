@@ -235,7 +235,9 @@ class MazeTables:
         self.max_steps = max_steps_for(self.grid.shape, int(self.dgoal[self.start]) + 1)
         # one byte per block: bit0 open | bits1-3 best-dir code | bits4-5 D_goal mod 4
         d4 = (np.where(self.dgoal >= 0, self.dgoal, 0) & 3).astype(np.uint8)
-        self.table = ((self.grid != 0).astype(np.uint8) | (self.code << 1) | (d4 << 4)).astype(np.uint8)
+        # (wall blocks carry 0: the step never reads more than their open bit)
+        opn = (self.grid != 0).astype(np.uint8)
+        self.table = (opn | ((self.code << 1) | (d4 << 4)) * opn).astype(np.uint8)
 
 
 class ClosedFormEnv(_EnvBase):
