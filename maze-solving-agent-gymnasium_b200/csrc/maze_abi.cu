@@ -58,6 +58,7 @@ extern "C" int maze_ctx_create(maze_ctx** out, int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_lut_revisit, 256 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_lut_invalid, 256 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counter, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_lut_revisit, ctx->h_lut_revisit, 256 * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_lut_invalid, ctx->h_lut_invalid, 256 * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -65,6 +66,7 @@ extern "C" int maze_ctx_create(maze_ctx** out, int device) {
         int rc = (int)e;
         cudaFree(ctx->d_lut_revisit);
         cudaFree(ctx->d_lut_invalid);
+        cudaFree(ctx->d_counter);
         delete ctx;
         return rc;
     }
@@ -85,6 +87,7 @@ extern "C" void maze_ctx_destroy(maze_ctx* ctx) {
     if (!ctx) return;
     cudaFree(ctx->d_lut_revisit);
     cudaFree(ctx->d_lut_invalid);
+    cudaFree(ctx->d_counter);
     delete ctx;
 }
 

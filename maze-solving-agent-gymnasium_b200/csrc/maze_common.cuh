@@ -14,6 +14,7 @@ struct maze_ctx {
     int device;
     double* d_lut_revisit;   // [256]
     double* d_lut_invalid;   // [256]
+    int*    d_counter;       // [4] work-distribution counters (zeroed before each use)
     double h_lut_revisit[256];
     double h_lut_invalid[256];
     double h_shaping[4];     // index = (D[prev]-D[cur]) & 3 : 0 -> 0, 1 -> +1, 3 -> -1

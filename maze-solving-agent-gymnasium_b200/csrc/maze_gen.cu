@@ -59,6 +59,7 @@ struct GenParams {
     int smem_cells;          // 0 when no metrics are needed
     int candidates;          // best-of-k by McClendon difficulty (base_maze_env.py:78-97); 1 = raw generator
     int only_toroidal;       // CTA kernel: skip bordered slots (the warp kernel did them)
+    int* work_counter;       // warp kernel: next unclaimed item (mazes differ in cost: claim dynamically)
     double* difficulty;      // [n] optional out: difficulty of the maze kept for item k
     unsigned long long seed;
     long long slot_id_base;
@@ -439,9 +440,12 @@ __device__ __forceinline__ void encode_bordered(const Walls& w, const GoalField&
 __global__ void __launch_bounds__(WARP_GEN_THREADS, 4)
 maze_generate_warp_kernel(GenParams p) {
     const int lane = lane_id();
-    const int warps_total = gridDim.x * (WARP_GEN_THREADS / 32);
     const int n = p.count_dev ? min(*p.count_dev, p.n) : p.n;
-    for (int item = blockIdx.x * (WARP_GEN_THREADS / 32) + (threadIdx.x >> 5); item < n; item += warps_total) {
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n) break;
         const int m = p.ids ? p.ids[item] : item;
         int32_t* mm = p.meta + (size_t)m * MAZE_META_WORDS;
         const int H = mm[MAZE_META_H], W = mm[MAZE_META_W];
@@ -627,6 +631,7 @@ extern "C" int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8
     p.candidates = candidates;
     p.only_toroidal = scored ? 0 : 1;
     p.difficulty = difficulty;
+    p.work_counter = nullptr;
     p.seed = seed; p.slot_id_base = slot_id_base;
 
     if (!scored) {   // bordered slots: one warp per maze, persistent over the items
@@ -636,6 +641,8 @@ extern "C" int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8
         const int warps_per_cta = WARP_GEN_THREADS / 32;
         const int want = (n + warps_per_cta - 1) / warps_per_cta;
         const int grid = want < per_sm * sms ? want : per_sm * sms;
+        p.work_counter = ctx->d_counter;
+        MAZE_CHECK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
         maze_generate_warp_kernel<<<grid, WARP_GEN_THREADS, 0, st>>>(p);
         MAZE_CHECK(cudaGetLastError());
     }
