@@ -147,6 +147,68 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+def measure_extras(mb, torch, device):
+    """Secondary numbers of the same path, one GPU (rank 0), CUDA events: valid mazes generated/s
+    (BASELINE.json's second metric), difficulty-metric throughput, the -v1 (window) step and the
+    fused Q-learning rollout.  Each is a few hundred milliseconds."""
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    out = {"per_gpu": True}
+    M = 131072
+    pool = mb.MazePool(M, SHAPE, device)
+    gen = {}
+    for algo in ("r-prim", "dfs", "prim&kill"):
+        seed = [7]
+
+        def go():
+            seed[0] += 1
+            pool.generate(algorithms=algo, seed=seed[0])
+        gen[algo] = M / timed(go, 2)
+    out["mazes_per_s_81x81"] = gen
+    seed = [100]
+
+    def go6():
+        seed[0] += 1
+        pool.generate(ids=torch.arange(16384, device=device, dtype=torch.int32), algorithms="r-prim", seed=seed[0],
+                      candidates=6, configure=False)
+    pool.generate(algorithms="r-prim", seed=5)
+    out["best_of_6_mazes_per_s_81x81"] = 16384 / timed(go6, 1)
+    ids = torch.arange(32768, device=device, dtype=torch.int32)
+    out["difficulty_mazes_per_s_81x81"] = 32768 / timed(lambda: pool.difficulty(ids), 2)
+    del pool
+    # -v1 observation: step + 15x15 window (2 700 B written per env-step)
+    Bv = 262144
+    venv = mb.MazeVectorEnv(Bv, shape=SHAPE, num_mazes=1000, enrich=True, seed=1234, on_win="next", stats=False, device=device)
+    venv.reset()
+    acts = torch.randint(0, 4, (Bv,), dtype=torch.uint8, device=device)
+    t = timed(lambda: venv.step(acts), 100)
+    out["v1_window_env_steps_per_s"] = Bv / t
+    out["v1_window_write_GBps"] = Bv * 2700 / t / 1e9
+    del venv
+    # fused tabular Q-learning rollout (policy + step + update per env, 64 steps per launch)
+    from maze_b200.agents import QAgent
+    Bq = 1048576
+    qenv = mb.MazeVectorEnv(Bq, shape=SHAPE, num_mazes=1000, seed=1234, on_win="next", stats=True, device=device)
+    agent = QAgent(qenv, learning_rate=0.1, initial_epsilon=0.9, epsilon_decay=2000, final_epsilon=0.05,
+                   discount_factor=0.7, eta=1e-3, envs_per_agent=Bq, capacity=1 << 24)
+    qenv.reset()
+    K = 64
+    t = timed(lambda: agent.rollout(K), 3)
+    agent.core.check_overflow()
+    out["q_rollout_env_steps_per_s"] = Bq * K / t
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -214,6 +276,11 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_value = world * B * e2e_steps / e2e_s
 
+    extra = None
+    if rank == 0 and not args.no_extras:
+        extra = measure_extras(mb, torch, device)
+    barrier()
+
     # independent check that the timed kernel did the work: episode bookkeeping must be moving
     st = env.batch.state_host()
     assert st["steps"].max() > 0 and int(rew.shape[0]) == B
@@ -225,7 +292,7 @@ def run_ours(args, rank, local_rank, world):
         prof = ncu_traffic_per_step_byte()
         traffic = None
         if prof and prof.get("dram_bytes_per_env_step") is not None:
-            traffic = prof["dram_bytes_per_env_step"] * B
+            traffic = prof["dram_bytes_per_env_step"] * B   # ncu --set full capture of a steady-state launch
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle.baseline import time_env_steps
@@ -257,6 +324,7 @@ def run_ours(args, rank, local_rank, world):
                     "d2h_bytes_per_step": env.d2h_bytes_per_step(), "steps": e2e_steps},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
+            "extra": extra,
         }
     if world > 1:
         dist.destroy_process_group()
@@ -274,6 +342,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
