@@ -86,7 +86,13 @@ template <int kPolicy> __device__ __forceinline__ void pol_store(uint16_t* p, un
     asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"((unsigned short)v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ unsigned visit_load(const uint16_t* p, uint64_t pol) { return pol_load<MAZE_VISIT_POLICY>(p, pol); }
-__device__ __forceinline__ void visit_store(uint16_t* p, unsigned v, uint64_t pol) { pol_store<MAZE_VISIT_POLICY>(p, v, pol); }
+#ifndef MAZE_VISIT_STORE_POLICY
+#define MAZE_VISIT_STORE_POLICY MAZE_VISIT_POLICY
+#endif
+__device__ __forceinline__ void visit_store(uint16_t* p, unsigned v, uint64_t pol) {
+    if (MAZE_VISIT_STORE_POLICY == MAZE_VISIT_POLICY) pol_store<MAZE_VISIT_POLICY>(p, v, pol);
+    else pol_store<MAZE_VISIT_STORE_POLICY>(p, v, l2_policy<MAZE_VISIT_STORE_POLICY>());
+}
 
 // index of block (r, c) in an env's visit array (see maze_env_batch.visit_tiled)
 __device__ __forceinline__ int visit_index(const maze_env_batch& b, int r, int c, int W) {

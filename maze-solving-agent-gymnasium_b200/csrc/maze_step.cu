@@ -86,7 +86,11 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
         npos[k] = nr | (nc << 16);
         idx[k] = nr * W + nc;
         vidx[k] = kTiled ? ((((nr >> 2) * ((W + 3) >> 2) + (nc >> 2)) << 4) | ((nr & 3) << 2) | (nc & 3)) : idx[k];
+#ifdef MAZE_EXP_NOTABLE
+        tb[k] = 1 | ((idx[k] & 3) << 1) | ((idx[k] & 3) << 4);
+#else
         tb[k] = pol_load_nc<MAZE_TABLE_POLICY>(b.table + (size_t)m[k] * b.slot + idx[k], pol_table);
+#endif
     }
 
     // ---- phase 4: visit counter, only for legal moves
@@ -97,7 +101,9 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
     for (int k = 0; k < EPT; ++k) {
         moved[k] = valid[k] && !do_reset[k] && inb[k] && (tb[k] & MAZE_TAB_OPEN);
         vis[k] = 0;
+#ifndef MAZE_EXP_NOVISIT
         if (moved[k]) vis[k] = visit_load(VISIT_AT(b, base + k * STEP_THREADS, vidx[k]), pol);
+#endif
     }
 
     // ---- phase 5: transition + outputs
@@ -128,7 +134,9 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
                 } else {
                     reward = __ldg(luts.revisit + cnt);   // :194
                 }
+#ifndef MAZE_EXP_NOVISIT
                 visit_store(VISIT_AT(b, e, vidx[k]), (unsigned)((st.epoch << 8) | (cnt < 255 ? cnt + 1 : 255)), pol);   // :196
+#endif
                 st.r = npos[k] & 0xffff;
                 st.c = npos[k] >> 16;
                 st.tab = tb[k];
