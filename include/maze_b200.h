@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 5
+#define MAZE_ABI_VERSION 6
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -165,6 +165,15 @@ int maze_reset(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* mask, void
 int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8_t* table, const int32_t* ids,
                   const int32_t* count_dev, int n, int slot, int max_h, int max_w,
                   uint64_t seed, int64_t slot_id_base, int candidates, double* difficulty, void* stream);
+
+/* Curriculum step for the slots whose env just won (drain of the maze_step regeneration queue, run
+ * before maze_generate):  wins[slot] += 1; variable-size envs grow the slot's shape by `grow` blocks
+ * per axis while it stays <= (max_h, max_w) (simple_variable_maze_env.py:93-112: +(4, 4) per win);
+ * the generator id becomes algo_a once wins >= wins_a and algo_b once wins >= wins_b
+ * (off_policy_trainer.py:302-310: prim&kill after 5 wins, dfs after 10; pass -1 to keep the id).
+ *   ids / count_dev / n as for maze_generate; wins [M] int32. */
+int maze_curriculum(maze_ctx* ctx, int32_t* meta, int32_t* wins, const int32_t* ids, const int32_t* count_dev,
+                    int n, int grow, int max_h, int max_w, int wins_a, int algo_a, int wins_b, int algo_b, void* stream);
 
 /* Enriched (-v1) observation: SimpleEnrichMazeEnv._get_obs (simple_maze_env.py:151-158) and the
  * toroidal / variable-size variants (toroidal_maze_env.py:164-172, simple_variable_maze_env.py:

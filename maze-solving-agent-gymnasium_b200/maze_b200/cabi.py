@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -68,6 +68,7 @@ SIGNATURES = {
     "maze_reset": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p]),
     "maze_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "maze_curriculum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
     "maze_window": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maze_direction_mask": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_int, C.c_void_p, C.c_void_p]),
     "maze_q_epsilon_lut": (C.c_int, [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int]),

@@ -137,6 +137,19 @@ class MazePool:
                                       cabi.ptr(difficulty_out), cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_generate")
 
+    def curriculum(self, ids, count_dev, wins: torch.Tensor, grow: int = 0, schedule=((5, "prim&kill"), (10, "dfs"))):
+        """Advance the curriculum of the queued slots on the device (see maze_curriculum): wins += 1,
+        shape += grow while it fits the pool, generator switched by the win thresholds of `schedule`
+        (None / () keeps the generator)."""
+        sched = list(schedule or ())
+        (wa, aa), (wb, ab) = (sched + [(0, None), (0, None)])[:2]
+        code = lambda a: -1 if a is None else (ALGO_IDS[a] if isinstance(a, str) else int(a))  # noqa: E731
+        ids_t = ids.to(device=self.device, dtype=torch.int32).contiguous()
+        rc = cabi.lib().maze_curriculum(self.ctx.handle, cabi.ptr(self.meta), cabi.ptr(wins), cabi.ptr(ids_t), cabi.ptr(count_dev),
+                                        ids_t.numel(), int(grow), self.max_shape[0], self.max_shape[1], int(wa), code(aa),
+                                        int(wb), code(ab), cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_curriculum")
+
     def difficulty(self, ids=None) -> torch.Tensor:
         """float64 [n, 8] metric records (cabi.METRIC_NAMES) of the given slots (all if None):
         McClendon difficulty / complexity, Kim-Crawfis L / DE / D, solution length, dead-end count."""

@@ -68,9 +68,14 @@ class MazeVectorEnv(_VectorBase):
                  num_mazes: Optional[int] = None, device="cuda", seed: int = 0, autoreset: bool = True,
                  on_win: str = "keep", reference_order: bool = False, stats: bool = True,
                  slot_id_base: int = 0, pool: Optional[MazePool] = None, env_maze=None, enrich: bool = False,
-                 candidates: int = 1):
+                 candidates: int = 1, start_shape=None, grow: int = 0, algorithm_schedule=None):
         """enrich=True gives the -v1 observation (normalised agent / target, 15x15 window);
-        candidates=6 makes every generated maze the least difficult of six (generate_maze)."""
+        candidates=6 makes every generated maze the least difficult of six (generate_maze).
+        Curriculum (on_win="regenerate"): `shape` is the maximum block shape; mazes start at
+        `start_shape` (one shape or one per maze) and grow by `grow` blocks per win
+        (variable-size envs: START_SHAPE and +(4, 4), simple_variable_maze_env.py:17,97);
+        `algorithm_schedule` = ((wins, algorithm), ...) switches a slot's generator by its win count
+        (off_policy_trainer.py:302-310: ((5, "prim&kill"), (10, "dfs")))."""
         if topology not in ("euclid", "toroidal"):
             raise ValueError("topology must be 'euclid' or 'toroidal'")
         if on_win not in ("keep", "next", "regenerate"):
@@ -94,11 +99,19 @@ class MazeVectorEnv(_VectorBase):
             algos = algorithms
             if not isinstance(algorithms, str):
                 algos = [algorithms[i % len(algorithms)] for i in range(M)]
-            pool.generate(shapes=self.shape, algorithms=algos, toroidal=(topology == "toroidal"),
+            shapes0 = self.shape if start_shape is None else start_shape
+            if not isinstance(shapes0[0], (int, np.integer)):
+                shapes0 = [tuple(shapes0[i % len(shapes0)]) for i in range(M)]
+            pool.generate(shapes=shapes0, algorithms=algos, toroidal=(topology == "toroidal"),
                           seed=self.seed, slot_id_base=self.slot_id_base, candidates=self.candidates)
         self.pool = pool
         if on_win == "regenerate" and pool.num_mazes != self.num_envs:
             raise ValueError("on_win='regenerate' needs one maze slot per env (num_mazes == num_envs)")
+        self.grow = int(grow)
+        self.algorithm_schedule = tuple(algorithm_schedule) if algorithm_schedule else ()
+        if (self.grow or self.algorithm_schedule) and on_win != "regenerate":
+            raise ValueError("grow / algorithm_schedule act when a maze is regenerated: use on_win='regenerate'")
+        self.wins = torch.zeros(pool.num_mazes, dtype=torch.int32, device=self.device)
         if env_maze is None:
             # contiguous envs share a maze: table reads of a warp hit the same lines
             per = max(1, self.num_envs // pool.num_mazes)
@@ -159,6 +172,8 @@ class MazeVectorEnv(_VectorBase):
         b = self.batch
         b.step(self._device_actions(actions), self._mode)
         if self.on_win == "regenerate":
+            if self.grow or self.algorithm_schedule:
+                self.pool.curriculum(b.queue, b.queue_count, self.wins, self.grow, self.algorithm_schedule)
             self.pool.generate(ids=b.queue, count_dev=b.queue_count, configure=False, seed=self.seed,
                                slot_id_base=self.slot_id_base, candidates=self.candidates)
             b.queue_count.zero_()
