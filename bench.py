@@ -121,7 +121,7 @@ def run_reference(args, rank):
     gymnasium_env/envs/base_maze_env.py; the Python reference itself cannot travel to the GPU box),
     one worker process per host core, each 'step' a bounded sample."""
     if rank != 0:
-        return
+        return None
     from oracle.baseline import time_env_steps
     cores = os.cpu_count() or 1
     mazes = reference_mazes(min(cores, 8))
@@ -135,7 +135,7 @@ def run_reference(args, rank):
     value = steps / secs
     sample = (f"{args.steps} samples x {per:.2f} s, {cores} worker processes each stepping the oracle port (A* per step) "
               f"of the reference env on an 81x81 r-prim maze, random actions, reset on done")
-    print(json.dumps({
+    return ({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -143,7 +143,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -328,8 +328,28 @@ def run_ours(args, rank, local_rank, world):
         }
     if world > 1:
         dist.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line))
+    return line
+
+
+class JsonOnlyStdout:
+    """The driver parses stdout as ONE JSON line: everything else a library prints there (NCCL's
+    version banner, for one) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self._real, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+        return False
 
 
 def main():
@@ -349,10 +369,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args, rank)
-    else:
-        run_ours(args, rank, local_rank, world)
+    with JsonOnlyStdout() as out:
+        if args.impl == "reference":
+            line = run_reference(args, rank)
+        else:
+            line = run_ours(args, rank, local_rank, world)
+        if line is not None:
+            out.emit(json.dumps(line))
 
 
 if __name__ == "__main__":
