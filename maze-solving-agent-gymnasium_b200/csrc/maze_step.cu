@@ -13,6 +13,9 @@ constexpr int STEP_THREADS = 256;
 #ifndef MAZE_STEP_MINB1
 #define MAZE_STEP_MINB1 6
 #endif
+#ifndef MAZE_STEP_MINB4
+#define MAZE_STEP_MINB4 2
+#endif
 #ifndef MAZE_STEP_MINB2
 #define MAZE_STEP_MINB2 5
 #endif
@@ -23,7 +26,7 @@ constexpr int STEP_THREADS = 256;
 // counter is only fetched when the move is legal (a wall hit needs no counter), which matters
 // because every such fetch costs a whole DRAM line.
 template <int EPT, bool kStats, bool kTiled>
-__global__ void __launch_bounds__(STEP_THREADS, EPT == 2 ? MAZE_STEP_MINB2 : (EPT == 1 ? MAZE_STEP_MINB1 : 1))
+__global__ void __launch_bounds__(STEP_THREADS, EPT == 2 ? MAZE_STEP_MINB2 : (EPT == 1 ? MAZE_STEP_MINB1 : MAZE_STEP_MINB4))
 maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t mode, StepLuts luts) {
     const int base = blockIdx.x * (STEP_THREADS * EPT) + threadIdx.x;
 

@@ -315,11 +315,33 @@ def make_genstats(out_path):
     np.savez_compressed(out_path, **out)
 
 
+def _metric_table_job(args):
+    algo, seed = args
+    random.seed(seed)
+    start, goal, maze = gen_maze((81, 81), algo)
+    r = metric_row(maze, start, goal)
+    return (r["difficulty"], r["complexity"], r["L"], r["DE"], r["D"])
+
+
+def make_metric_table(out_path, n=120):
+    """The README table (generation_algos_metrics_evaluations.py:31-43) as per-maze samples: n mazes
+    of (81, 81) per generator from the unmodified reference, columns difficulty, complexity, L, DE, D."""
+    import multiprocessing as mp
+    out = {}
+    with mp.get_context("fork").Pool(os.cpu_count() or 1) as pool:
+        for k, algo in enumerate(("r-prim", "prim&kill", "dfs")):
+            t0 = time.time()
+            rows = pool.map(_metric_table_job, [(algo, 70000 + 1000 * k + i) for i in range(n)])
+            out[algo] = np.array(rows, dtype=np.float64)
+            print(f"metric_table {algo} n={n} mean={out[algo].mean(axis=0)} max_difficulty={out[algo][:, 0].max():.2f} {time.time()-t0:.0f}s", flush=True)
+    np.savez_compressed(out_path, **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["steps", "bestdir", "metrics", "qagent", "genstats"]
+    which = sys.argv[1:] or ["steps", "bestdir", "metrics", "qagent", "genstats", "metric_table"]
     for w in which:
         t0 = time.time()
         {"steps": make_steps, "bestdir": make_bestdir, "metrics": make_metrics, "qagent": make_qagent,
-         "genstats": make_genstats}[w](
+         "genstats": make_genstats, "metric_table": make_metric_table}[w](
             os.path.join(HERE, f"{w}.npz"))
         print(f"== {w}.npz written in {time.time()-t0:.0f}s", flush=True)

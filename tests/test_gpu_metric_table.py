@@ -1,0 +1,51 @@
+"""North-star correctness check 3: the generators' difficulty-metric distributions over 1000
+40x40 (81x81 block) mazes must match the reference.
+
+The reference's README table (README.md:29-33; columns defined at
+generation_algos_metrics_evaluations.py:43) gives, per generator, MD = mean McClendon difficulty,
+Max D, MC = mean complexity, ML = mean L, MDE = mean DE, MDs = mean D over 1000 mazes.  RNG streams
+differ by construction, so parity is distributional:
+
+  (a) against per-maze samples of the unmodified reference (tests/golden/metric_table.npz, 120
+      mazes per generator, made by make_golden.py): |mean_ours - mean_ref| <= 4.5 standard errors of
+      the difference of means, for every column;
+  (b) against the README's published means: within 4.5 standard errors of our own 1000-sample
+      mean, plus one unit of the README's last printed digit (its two-decimal figures are
+      truncated, not rounded: the reference code itself gives MDs = 0.040 for dfs where the README
+      prints 0.03), plus 3 % slack for the README's unknown sampling error.
+Mazes are generated AND scored on the device (maze_generate + maze_difficulty).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN  # noqa: E402
+
+COLUMNS = ("difficulty", "complexity", "L", "DE", "D")
+README = {   # MD, MC, ML, MDE, MDs (README.md:31-33); Max D is informational: 103.43 / 157.15 / 152.22
+    "r-prim": (71.90, 8.43, 0.04, 1.34, 0.33),
+    "prim&kill": (99.08, 10.16, 0.14, 0.14, 0.07),
+    "dfs": (106.41, 12.24, 0.47, 0.05, 0.03),
+}
+
+
+@pytest.mark.parametrize("algo", ["r-prim", "prim&kill", "dfs"])
+def test_metric_table_of_1000_mazes_matches_reference(algo):
+    import maze_b200 as mb
+    n = 1000
+    pool = mb.MazePool(n, (81, 81))
+    pool.generate(algorithms=algo, seed=20261018)
+    ours = pool.difficulty().cpu().numpy()[:, :5]
+    assert np.isfinite(ours).all()
+    ref = np.load(f"{GOLDEN}/metric_table.npz")[algo]
+    for c, name in enumerate(COLUMNS):
+        a, b = ours[:, c], ref[:, c]
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 4.5 * se, (algo, name, a.mean(), b.mean(), se)
+        published = README[algo][c]
+        tol = 4.5 * a.std(ddof=1) / np.sqrt(n) + 0.01 + 0.03 * abs(published)
+        assert abs(a.mean() - published) <= tol, (algo, name, a.mean(), published, tol)
+    # spread of the difficulty too (two-sample check on the standard deviation, generous)
+    assert 0.7 < ours[:, 0].std() / ref[:, 0].std() < 1.4
