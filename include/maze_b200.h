@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 6
+#define MAZE_ABI_VERSION 7
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -253,6 +253,50 @@ int maze_q_update(maze_ctx* ctx, const maze_env_batch* b, const maze_q_agent* ag
  * autoreset.  Leaves the batch outputs (obs, reward, terminated, truncated) of the last step. */
 int maze_q_rollout(maze_ctx* ctx, const maze_env_batch* b, const maze_q_agent* agent, int k_steps, uint32_t mode,
                    void* stream);
+
+/* ---- DQN / DDQN data path (the steps either side of the env in the neural trainers) ------------
+ * lib/replay_memory.py:8-24 (ReplayMemory: deque + uniform sample), agents/ddqn_agent.py:95-108
+ * (epsilon-greedy whose exploration draws from get_mask_direction(probs=True)), and the state the
+ * trainer builds from the -v1 observation (lib/trainers/off_policy_trainer.py:153-171):
+ * state = (float32[6] = agent / shape, target / shape, best dir ; float32[3, 15, 15] window).
+ * The ring keeps windows BIT-PACKED (3 channels x 8 words of 32 blocks = 96 B instead of 2 700 B)
+ * and unpacks them when a batch is sampled. */
+#define MAZE_WINDOW_WORDS 24   /* 3 channels x 8 uint32 (225 of 256 bits used per channel)        */
+typedef struct maze_replay {
+    int64_t   capacity;     /* transitions in the ring                                            */
+    unsigned long long* pushed; /* [1] device counter: transitions pushed so far                  */
+    float*    vec;          /* [capacity, 6]  state vector                                        */
+    float*    next_vec;     /* [capacity, 6]                                                      */
+    uint32_t* win;          /* [capacity, MAZE_WINDOW_WORDS] packed window of the state           */
+    uint32_t* next_win;     /* [capacity, MAZE_WINDOW_WORDS]                                      */
+    uint8_t*  action;       /* [capacity]                                                         */
+    float*    reward;       /* [capacity]                                                         */
+    /* per-env staging: the observation the env's next transition starts from */
+    float*    stage_vec;    /* [B, 6]                                                             */
+    uint32_t* stage_win;    /* [B, MAZE_WINDOW_WORDS]                                             */
+} maze_replay;
+
+/* Encode the current observation of every env into the staging area (after maze_reset). */
+int maze_dqn_observe(maze_ctx* ctx, const maze_env_batch* b, const maze_replay* r, void* stream);
+
+/* agent.memorize(state, action, reward, next_state) for the transition maze_step just made with
+ * `actions` (off_policy_trainer.py:171; next_state is never None there, terminal states included):
+ * appends (staged observation, action, reward, new observation) to the ring and re-stages the new
+ * observation.  Envs whose step was an autoreset only re-stage. */
+int maze_dqn_push(maze_ctx* ctx, const maze_env_batch* b, const maze_replay* r, const uint8_t* actions, void* stream);
+
+/* memory.sample(n): n transitions drawn uniformly (with replacement; Philox keyed by seed / draw)
+ * from the filled part of the ring, unpacked into dense tensors: vec / next_vec [n, 6] float32,
+ * win / next_win [n, 3, 15, 15] float32, action [n] int64, reward [n] float32. */
+int maze_dqn_sample(maze_ctx* ctx, const maze_replay* r, int n, uint64_t seed, uint64_t draw, float* vec, float* win,
+                    float* next_vec, float* next_win, int64_t* action, float* reward, void* stream);
+
+/* DDQNAgent.get_action for every env (ddqn_agent.py:98-108): with probability eps_lut[steps_done[e]]
+ * a random action drawn from get_mask_direction(probs=True) / sum, otherwise argmax of q_values[e]
+ * ([B, 4] float32, the policy network's output).  steps_done [B] uint32 is advanced for every env
+ * that makes a decision (not for envs waiting for an autoreset). */
+int maze_dqn_select(maze_ctx* ctx, const maze_env_batch* b, const float* q_values, const double* eps_lut, int eps_len,
+                    uint32_t* steps_done, uint64_t seed, int64_t env_id_base, uint8_t* actions, void* stream);
 
 /* Difficulty metrics of pool mazes, one record of MAZE_METRIC_WORDS doubles per processed slot
  * (out[k] belongs to ids[k], or to slot k when ids is NULL):

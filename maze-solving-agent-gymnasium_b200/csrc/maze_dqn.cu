@@ -1,0 +1,283 @@
+// DQN / DDQN data path on the device (sm_100a): bit-packed observation encode, replay ring,
+// uniform sampling with unpack, and the masked epsilon-greedy action selection.
+// Reference: lib/replay_memory.py:8-24, agents/ddqn_agent.py:95-108, lib/maze_handler.py:4-162,
+// lib/trainers/off_policy_trainer.py:153-171.
+//
+// A -v1 observation is 6 floats + a 3 x 15 x 15 window of {0, 1}: the window is kept as 24 words
+// (one ballot per 32 blocks and channel), so a transition costs 2 x (24 + 96) + 5 = 245 B of HBM
+// instead of 5.5 KB, and a 1 M-transition ring fits in 245 MB.
+#include "maze_env.cuh"
+
+namespace {
+
+constexpr int DQN_THREADS = 256;
+constexpr int WIN = MAZE_WINDOW;
+constexpr int WIN_CELLS = WIN * WIN;
+constexpr int WORDS = MAZE_WINDOW_WORDS;
+constexpr unsigned FULL = 0xffffffffu;
+
+// Observation of env e by one warp: vec[6] (lanes 0-5 hold the values) and the packed window
+// (lane w < 24 holds word w).  Same rules as maze_window_kernel (maze_obs.cu).
+struct PackedObs {
+    float vec;       // lane < 6
+    unsigned word;   // lane < 24
+};
+
+__device__ __forceinline__ PackedObs encode_obs(const maze_env_batch& b, int e) {
+    const int lane = threadIdx.x & 31;
+    const EnvState st = unpack_state(b.state[e]);
+    const int m = b.env_maze[e];
+    const MazeView mz = load_maze(b, m);
+    const int H = mz.H, W = mz.W;
+    const int start_idx = (mz.start & 0xffff) * W + (mz.start >> 16);
+    const int goal_idx = (mz.goal & 0xffff) * W + (mz.goal >> 16);
+    const bool ok = H >= WIN && W >= WIN;
+    int r0 = st.r - WIN / 2, c0 = st.c - WIN / 2;
+    if (!mz.tor) {
+        r0 = min(max(r0, 0), H - WIN);
+        c0 = min(max(c0, 0), H - WIN);
+    }
+    PackedObs o;
+    o.word = 0;
+#pragma unroll
+    for (int k = 0; k < (WIN_CELLS + 31) / 32; ++k) {
+        const int i = k * 32 + lane;
+        bool wall = false, floor = false, fresh = false;
+        if (ok && i < WIN_CELLS) {
+            int rr = r0 + i / WIN, cc = c0 + i % WIN;
+            if (mz.tor) {
+                rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
+                cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
+            }
+            const int idx = rr * W + cc;
+            const bool open = (__ldg(mz.tab + idx) & MAZE_TAB_OPEN) != 0;
+            wall = !open;
+            floor = open && idx != goal_idx;
+            if (open && idx != start_idx) {
+                const unsigned v = *VISIT_AT(b, e, visit_index(b, rr, cc, W));
+                fresh = !((int)(v >> 8) == st.epoch && (v & 0xffu) != 0);
+            }
+        }
+        const unsigned w0 = __ballot_sync(FULL, wall), w1 = __ballot_sync(FULL, floor), w2 = __ballot_sync(FULL, fresh);
+        if (lane == k) o.word = w0;
+        if (lane == 8 + k) o.word = w1;
+        if (lane == 16 + k) o.word = w2;
+    }
+    // float32 of the float64 quotient, like torch.tensor(np.concatenate([...]), dtype=float32)
+    const int2 bd = best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, H, W, mz.tor);
+    double v = 0.0;
+    switch (lane) {
+        case 0: v = __ddiv_rn((double)st.r, (double)H); break;
+        case 1: v = __ddiv_rn((double)st.c, (double)W); break;
+        case 2: v = __ddiv_rn((double)(mz.goal & 0xffff), (double)H); break;
+        case 3: v = __ddiv_rn((double)(mz.goal >> 16), (double)W); break;
+        case 4: v = (double)bd.x; break;
+        case 5: v = (double)bd.y; break;
+        default: break;
+    }
+    o.vec = (float)v;
+    return o;
+}
+
+__global__ void __launch_bounds__(DQN_THREADS)
+maze_dqn_observe_kernel(maze_env_batch b, maze_replay r) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (DQN_THREADS / 32) + (threadIdx.x >> 5);
+    if (e >= b.num_envs) return;
+    const PackedObs o = encode_obs(b, e);
+    if (lane < 6) r.stage_vec[(size_t)e * 6 + lane] = o.vec;
+    if (lane < WORDS) r.stage_win[(size_t)e * WORDS + lane] = o.word;
+}
+
+__global__ void __launch_bounds__(DQN_THREADS)
+maze_dqn_push_kernel(maze_env_batch b, maze_replay r, const uint8_t* __restrict__ actions) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (DQN_THREADS / 32) + (threadIdx.x >> 5);
+    if (e >= b.num_envs) return;
+    const PackedObs o = encode_obs(b, e);
+    const EnvState st = unpack_state(b.state[e]);
+    if (st.steps != 0) {   // a real transition (steps == 0 only right after a reset)
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(r.pushed, 1ull);
+        at = __shfl_sync(FULL, at, 0);
+        const size_t slot = (size_t)(at % (unsigned long long)r.capacity);
+        if (lane < 6) {
+            r.vec[slot * 6 + lane] = r.stage_vec[(size_t)e * 6 + lane];
+            r.next_vec[slot * 6 + lane] = o.vec;
+        }
+        if (lane < WORDS) {
+            r.win[slot * WORDS + lane] = r.stage_win[(size_t)e * WORDS + lane];
+            r.next_win[slot * WORDS + lane] = o.word;
+        }
+        if (lane == 0) {
+            r.action[slot] = actions[e] & 3;
+            r.reward[slot] = (float)b.reward[e];
+        }
+    }
+    __syncwarp();
+    if (lane < 6) r.stage_vec[(size_t)e * 6 + lane] = o.vec;
+    if (lane < WORDS) r.stage_win[(size_t)e * WORDS + lane] = o.word;
+}
+
+__device__ __forceinline__ void unpack_window(const uint32_t* __restrict__ words, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const unsigned w = lane < WORDS ? words[lane] : 0u;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned word = __shfl_sync(FULL, w, ch * 8 + k);
+            const int i = k * 32 + lane;
+            if (i < WIN_CELLS) __stcs(out + ch * WIN_CELLS + i, (float)((word >> lane) & 1u));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DQN_THREADS)
+maze_dqn_sample_kernel(maze_replay r, int n, unsigned long long seed, unsigned long long draw, float* __restrict__ vec,
+                       float* __restrict__ win, float* __restrict__ next_vec, float* __restrict__ next_win,
+                       int64_t* __restrict__ action, float* __restrict__ reward) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (DQN_THREADS / 32) + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const unsigned long long pushed = *r.pushed;
+    const unsigned long long filled = pushed < (unsigned long long)r.capacity ? pushed : (unsigned long long)r.capacity;
+    if (filled == 0) return;
+    Philox rng;
+    rng.init(seed, draw, (uint32_t)k);
+    rng.refill();
+    const unsigned long long u = ((unsigned long long)rng.o0 << 32) | rng.o1;
+    const size_t slot = (size_t)__umul64hi(u, filled);   // uniform in [0, filled)
+    if (lane < 6) {
+        vec[(size_t)k * 6 + lane] = r.vec[slot * 6 + lane];
+        next_vec[(size_t)k * 6 + lane] = r.next_vec[slot * 6 + lane];
+    }
+    if (lane == 0) {
+        action[k] = (int64_t)r.action[slot];
+        reward[k] = r.reward[slot];
+    }
+    unpack_window(r.win + slot * WORDS, win + (size_t)k * 3 * WIN_CELLS);
+    unpack_window(r.next_win + slot * WORDS, next_win + (size_t)k * 3 * WIN_CELLS);
+}
+
+__global__ void __launch_bounds__(DQN_THREADS)
+maze_dqn_select_kernel(maze_env_batch b, const float4* __restrict__ q_values, const double* __restrict__ eps_lut, int eps_len,
+                       uint32_t* __restrict__ steps_done, unsigned long long seed, long long env_id_base,
+                       uint8_t* __restrict__ actions) {
+    const int e = blockIdx.x * DQN_THREADS + threadIdx.x;
+    if (e >= b.num_envs) return;
+    const EnvState st = unpack_state(b.state[e]);
+    if (st.flags & MAZE_ST_NEEDS_RESET) { actions[e] = 0; return; }   // the next step is an autoreset
+    const uint32_t sd = steps_done[e];
+    steps_done[e] = sd + 1;
+    const double eps = __ldg(eps_lut + (sd < (uint32_t)eps_len ? (int)sd : eps_len - 1));
+    Philox rng;
+    rng.init(seed, (uint64_t)(env_id_base + e), sd);
+    rng.refill();
+    const double u = (double)(((uint64_t)(rng.o0 >> 5) << 26) | (uint64_t)(rng.o1 >> 6)) * (1.0 / 9007199254740992.0);
+    int a;
+    if (u < eps) {   // ps = mask / mask.sum(); np.random.choice(4, p=ps)  (ddqn_agent.py:102-104)
+        const MazeView mz = load_maze(b, b.env_maze[e]);
+        float w[4];
+        float total = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int dr, dc;
+            action_delta(k, dr, dc);
+            int nr = st.r + dr, nc = st.c + dc;
+            bool open;
+            if (mz.tor) {
+                nr = nr < 0 ? mz.H - 1 : (nr >= mz.H ? 0 : nr);
+                nc = nc < 0 ? mz.W - 1 : (nc >= mz.W ? 0 : nc);
+                open = (__ldg(mz.tab + nr * mz.W + nc) & MAZE_TAB_OPEN) != 0;
+            } else {
+                open = nr >= 0 && nr < mz.H && nc >= 0 && nc < mz.W && (__ldg(mz.tab + nr * mz.W + nc) & MAZE_TAB_OPEN) != 0;
+            }
+            w[k] = open ? 1.f : 0.f;
+        }
+        if (((st.flags >> MAZE_ST_NMOVES_SHIFT) & 3) >= 2) {
+            const int last = (st.flags >> MAZE_ST_MOVE_SHIFT) & 3;
+            w[mz.tor ? 3 - last : (last ^ 1)] = 0.25f;   // see maze_direction_mask
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) total += w[k];
+        const float x = (float)(rng.o2 * (1.0 / 4294967296.0)) * total;   // inverse CDF over the four weights
+        a = 3;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc += w[k];
+            if (x < acc) { a = k; break; }
+        }
+        if (total == 0.f) a = (int)(rng.o2 >> 30);
+        else if (w[a] == 0.f) {   // x fell on the upper edge through rounding: take the last allowed action
+            for (int k = 3; k >= 0; --k) if (w[k] > 0.f) { a = k; break; }
+        }
+    } else {          // source_net(state).max(1)[1]: first maximum
+        const float4 q = __ldg(q_values + e);
+        a = 0;
+        float best = q.x;
+        if (q.y > best) { best = q.y; a = 1; }
+        if (q.z > best) { best = q.z; a = 2; }
+        if (q.w > best) { best = q.w; a = 3; }
+    }
+    actions[e] = (uint8_t)a;
+}
+
+int check_replay(maze_ctx* ctx, const maze_replay* r, bool need_stage) {
+    if (!r) return maze_fail_arg(ctx, MAZE_E_NULL, "replay");
+    if (!r->pushed || !r->vec || !r->next_vec || !r->win || !r->next_win || !r->action || !r->reward)
+        return maze_fail_arg(ctx, MAZE_E_NULL, "replay pointer");
+    if (need_stage && (!r->stage_vec || !r->stage_win)) return maze_fail_arg(ctx, MAZE_E_NULL, "replay staging pointer");
+    if (r->capacity < 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "replay capacity");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int maze_dqn_observe(maze_ctx* ctx, const maze_env_batch* b, const maze_replay* r, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = maze_check_batch(ctx, b)) return rc;
+    if (int rc = check_replay(ctx, r, true)) return rc;
+    const int per = DQN_THREADS / 32;
+    maze_dqn_observe_kernel<<<(b->num_envs + per - 1) / per, DQN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int maze_dqn_push(maze_ctx* ctx, const maze_env_batch* b, const maze_replay* r, const uint8_t* actions, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = maze_check_batch(ctx, b)) return rc;
+    if (int rc = check_replay(ctx, r, true)) return rc;
+    if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_push: actions");
+    const int per = DQN_THREADS / 32;
+    maze_dqn_push_kernel<<<(b->num_envs + per - 1) / per, DQN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r, actions);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int maze_dqn_sample(maze_ctx* ctx, const maze_replay* r, int n, uint64_t seed, uint64_t draw, float* vec, float* win,
+                               float* next_vec, float* next_win, int64_t* action, float* reward, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = check_replay(ctx, r, false)) return rc;
+    if (n < 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_sample: n");
+    if (!vec || !win || !next_vec || !next_win || !action || !reward) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_sample output");
+    const int per = DQN_THREADS / 32;
+    maze_dqn_sample_kernel<<<(n + per - 1) / per, DQN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        *r, n, seed, draw, vec, win, next_vec, next_win, action, reward);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int maze_dqn_select(maze_ctx* ctx, const maze_env_batch* b, const float* q_values, const double* eps_lut, int eps_len,
+                               uint32_t* steps_done, uint64_t seed, int64_t env_id_base, uint8_t* actions, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = maze_check_batch(ctx, b)) return rc;
+    if (!q_values || !eps_lut || !steps_done || !actions) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_select pointer");
+    if (eps_len < 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_select: eps_len");
+    if ((uintptr_t)q_values & 15) return maze_fail_arg(ctx, MAZE_E_ALIGN, "maze_dqn_select: q_values must be 16-byte aligned");
+    maze_dqn_select_kernel<<<(b->num_envs + DQN_THREADS - 1) / DQN_THREADS, DQN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        *b, reinterpret_cast<const float4*>(q_values), eps_lut, eps_len, steps_done, seed, env_id_base, actions);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -46,6 +46,15 @@ class MazeQAgent(C.Structure):
     ]
 
 
+class MazeReplay(C.Structure):
+    _fields_ = [
+        ("capacity", C.c_int64), ("pushed", C.c_void_p), ("vec", C.c_void_p), ("next_vec", C.c_void_p),
+        ("win", C.c_void_p), ("next_win", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
+        ("stage_vec", C.c_void_p), ("stage_win", C.c_void_p),
+    ]
+
+
+WINDOW_WORDS = 24
 Q_EMPTY = 0xffffffffffffffff
 Q_NO_SLOT = 0xffffffff
 
@@ -75,6 +84,11 @@ SIGNATURES = {
     "maze_q_act": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.POINTER(MazeQAgent), C.c_void_p, C.c_void_p]),
     "maze_q_update": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.POINTER(MazeQAgent), C.c_void_p]),
     "maze_q_rollout": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.POINTER(MazeQAgent), C.c_int, C.c_uint32, C.c_void_p]),
+    "maze_dqn_observe": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.POINTER(MazeReplay), C.c_void_p]),
+    "maze_dqn_push": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.POINTER(MazeReplay), C.c_void_p, C.c_void_p]),
+    "maze_dqn_sample": (C.c_int, [C.c_void_p, C.POINTER(MazeReplay), C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 7),
+    "maze_dqn_select": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "maze_difficulty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
 }
