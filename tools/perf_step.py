@@ -9,7 +9,8 @@ import maze_b200 as mb
 layouts = (sys.argv[1] if len(sys.argv) > 1 else "cell,env,tile").split(",")
 sizes = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "1048576,4096000").split(",")]
 M, TAPE = 1000, 16
-pool = mb.MazePool(M, (81, 81))
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 81
+pool = mb.MazePool(M, (S, S))
 pool.generate(algorithms="r-prim", seed=1234)
 mode = mb.cabi.STEP_AUTORESET | mb.cabi.STEP_WIN_NEXT
 for B in sizes:
@@ -35,5 +36,5 @@ for B in sizes:
             g.replay()
         ev[1].record(); torch.cuda.synchronize()
         us = ev[0].elapsed_time(ev[1]) / (reps * TAPE) * 1e3
-        print(f"B={B:8d} layout={lay:5s} {us:7.1f} us/step  {B/us*1e6:.3e} steps/s  algorithmic {58*B/us/1e3:.0f} GB/s  frac {58*B/us/1e3/6545.3:.3f}", flush=True)
+        print(f"S={S} B={B:8d} layout={lay:5s} {us:7.1f} us/step  {B/us*1e6:.3e} steps/s  algorithmic {58*B/us/1e3:.0f} GB/s  frac {58*B/us/1e3/6545.3:.3f}", flush=True)
         del batch, g
