@@ -110,22 +110,33 @@ class MazePool:
             k = len(ids_list)
             if shapes is None:
                 shapes = self.max_shape
-            shp = [shapes] * k if isinstance(shapes[0], (int, np.integer)) else list(shapes)
-            alg = [algorithms] * k if isinstance(algorithms, (str, int)) else list(algorithms)
-            tor = [toroidal] * k if isinstance(toroidal, (bool, int)) else list(toroidal)
-            hm = np.zeros((k, 3), dtype=np.int32)
-            for q in range(k):
-                H, W = check_shape(shp[q], cabi.GEN_MAX_DIM - 2)
+            def record(shape, a, t):
+                H, W = check_shape(shape, cabi.GEN_MAX_DIM - 2)
                 if H * W > self.slot:
                     raise ValueError(f"shape {(H, W)} does not fit the pool slot")
-                a = alg[q]
                 if isinstance(a, str):
                     if a not in ALGO_IDS:
                         raise ValueError(f"unknown maze generation algorithm {a!r} (expected one of {list(ALGO_IDS)})")
                     a = ALGO_IDS[a]
                 elif a not in ALGO_NAMES:
                     raise ValueError(f"unknown maze generation algorithm id {a}")
-                hm[q] = (H, W, (cabi.FLAG_TOROIDAL if tor[q] else 0) | (int(a) << 8))
+                return (H, W, (cabi.FLAG_TOROIDAL if t else 0) | (int(a) << 8))
+
+            uniform = (isinstance(shapes[0], (int, np.integer)) and isinstance(algorithms, (str, int))
+                       and isinstance(toroidal, (bool, int)))
+            if uniform:   # one record for every slot: no per-slot host work
+                hm = np.tile(np.array(record(shapes, algorithms, toroidal), dtype=np.int32), (k, 1))
+            else:
+                shp = [shapes] * k if isinstance(shapes[0], (int, np.integer)) else list(shapes)
+                alg = [algorithms] * k if isinstance(algorithms, (str, int)) else list(algorithms)
+                tor = [toroidal] * k if isinstance(toroidal, (bool, int)) else list(toroidal)
+                cache = {}
+                hm = np.zeros((k, 3), dtype=np.int32)
+                for q in range(k):
+                    key = (tuple(shp[q]), alg[q], bool(tor[q]))
+                    if key not in cache:
+                        cache[key] = record(*key)
+                    hm[q] = cache[key]
             cfg = torch.from_numpy(hm).to(self.device)
             idx = torch.as_tensor(ids_list, dtype=torch.long, device=self.device)
             self.meta[idx, cabi.META_H] = cfg[:, 0]
