@@ -22,7 +22,7 @@
 //
 // Reference: lib/maze_generation.py:6-35 (gen_maze), :37-56 (gen_maze_no_border), :59-99 (r-prim),
 // :101-128 (dfs), :130-185 (prim&kill), :187-218 (goal = farthest leaf, row-major tie-break).
-// RNG: Philox4x32-10 keyed by (seed, global slot id, generation count, candidate) -- the reference
+// RNG: PCG32 seeded by Philox4x32-10 keyed by (seed, global slot id, generation count, candidate) -- the reference
 // draws from Python's global `random` through set iteration order, which cannot be replayed, so
 // parity for generators is structural (spanning tree) + distributional (see tests).
 #include "maze_metrics.cuh"
@@ -63,6 +63,29 @@ struct GenParams {
     double* difficulty;      // [n] optional out: difficulty of the maze kept for item k
     unsigned long long seed;
     long long slot_id_base;
+};
+
+// Per-maze random stream: PCG-XSH-RR 64/32 whose state and increment come from one Philox4x32-10
+// block keyed by (seed, global slot id | generation count, candidate).  The key makes streams
+// independent of how slots are sharded over GPUs; the sequential generator costs ~12 instructions
+// per draw inside the carving loop (a Philox block per two draws was 20 % of the kernel).
+struct GenRng {
+    u64 state, inc;
+    __device__ __forceinline__ void init(unsigned long long seed, u64 seq, unsigned sub) {
+        Philox p;
+        p.init(seed, seq, sub);
+        p.refill();
+        state = ((u64)p.o1 << 32) | p.o0;
+        inc = ((((u64)p.o3 << 32) | p.o2) << 1) | 1ull;
+        next();
+    }
+    __device__ __forceinline__ unsigned next() {
+        const u64 old = state;
+        state = old * 6364136223846793005ull + inc;
+        const unsigned xs = (unsigned)(((old >> 18) ^ old) >> 27);
+        return __funnelshift_r(xs, xs, (unsigned)(old >> 59));
+    }
+    __device__ __forceinline__ unsigned below(unsigned n) { return __umulhi(next(), n); }   // bias < n / 2^32
 };
 
 // ---- row bit-planes in registers (warp-uniform i, j everywhere) -------------------------------
@@ -109,7 +132,7 @@ __device__ __forceinline__ int select64_warp(u64 w, int k) {
 }
 
 // uniformly random set bit over the two rows of all lanes; returns (i << 8) | j, or -1 if empty
-__device__ __forceinline__ int pick_uniform(u64 s0, u64 s1, Philox& rng) {
+__device__ __forceinline__ int pick_uniform(u64 s0, u64 s1, GenRng& rng) {
     const int c0 = __popcll(s0), c1 = __popcll(s1);
     const int incl = warp_incl_scan(c0 + c1);
     const int total = __shfl_sync(FULL, incl, 31);
@@ -143,7 +166,7 @@ __device__ __forceinline__ int select4(unsigned nb, int k) {
     const u64 t = idx < 32 ? 0x2409080204010000ull : 0xe439380e340d0c03ull;
     return (int)((t >> (2 * (idx & 31))) & 3ull);
 }
-__device__ __forceinline__ int pick_direction(unsigned nb, Philox& rng) {
+__device__ __forceinline__ int pick_direction(unsigned nb, GenRng& rng) {
     return select4(nb, (int)rng.below((unsigned)__popc(nb)));
 }
 
@@ -161,7 +184,7 @@ __device__ __forceinline__ void open_wall(Walls& w, int i, int j, int d) {
 // ---- generators (all 32 lanes, uniform control flow) -----------------------------------------
 
 // lib/maze_generation.py:59-99: uniformly random frontier cell, then a uniformly random tree neighbour
-__device__ __forceinline__ void gen_random_prim(Walls& w, int nr, int nc, int si, int sj, Philox& rng) {
+__device__ __forceinline__ void gen_random_prim(Walls& w, int nr, int nc, int si, int sj, GenRng& rng) {
     const int lane = lane_id();
     const u64 colmask = nc >= 64 ? ~0ull : ((1ull << nc) - 1ull);
     RowSets in = {0ull, 0ull}, fr = {0ull, 0ull};
@@ -196,7 +219,7 @@ __device__ __forceinline__ void gen_random_prim(Walls& w, int nr, int nc, int si
 // lib/maze_generation.py:101-128 (first unvisited neighbour of a fresh shuffle == uniform choice).
 // The explicit stack is replaced by a 2-bit "direction back to the parent" plane: popping the
 // stack is walking to the parent.
-__device__ __forceinline__ void gen_depth_first(Walls& w, int nr, int nc, int si, int sj, Philox& rng) {
+__device__ __forceinline__ void gen_depth_first(Walls& w, int nr, int nc, int si, int sj, GenRng& rng) {
     RowSets vis = {0ull, 0ull}, b0 = {0ull, 0ull}, b1 = {0ull, 0ull};
     row_or(vis, si, 1ull << sj);
     int i = si, j = sj;
@@ -221,7 +244,7 @@ __device__ __forceinline__ void gen_depth_first(Walls& w, int nr, int nc, int si
 }
 
 // lib/maze_generation.py:130-185
-__device__ __forceinline__ void gen_prim_and_kill(Walls& w, int nr, int nc, int si, int sj, Philox& rng) {
+__device__ __forceinline__ void gen_prim_and_kill(Walls& w, int nr, int nc, int si, int sj, GenRng& rng) {
     const int lane = lane_id();
     const u64 colmask = nc >= 64 ? ~0ull : ((1ull << nc) - 1ull);
     // marked rows; bits / rows outside the lattice read as "marked" so they never look eligible
@@ -266,7 +289,7 @@ __device__ __forceinline__ void gen_prim_and_kill(Walls& w, int nr, int nc, int 
 // both kernels, so a slot's candidate c is the same maze whichever kernel draws it.
 __device__ __forceinline__ void generate_walls(Walls& w, int algo, int nr, int nc, unsigned long long seed, u64 seq,
                                                unsigned cand, int& si, int& sj) {
-    Philox rng;
+    GenRng rng;
     rng.init(seed, seq, cand);
     si = (int)rng.below((unsigned)nr);   // :21 uniform logical cell
     sj = (int)rng.below((unsigned)nc);
