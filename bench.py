@@ -147,6 +147,17 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(index):
+    """Run this rank on the CPUs next to its GPU, so that the pinned staging buffers of the e2e path
+    are allocated on the GPU's NUMA node (8 ranks sharing one node's memory halve the copy rate)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception as exc:   # not fatal: only the host-copy rate depends on it
+        print(f"[bench] no CPU affinity for GPU {index}: {exc}", file=sys.stderr)
+
+
 def measure_extras(mb, torch, device):
     """Secondary numbers of the same path, one GPU (rank 0), CUDA events: valid mazes generated/s
     (BASELINE.json's second metric), difficulty-metric throughput, the -v1 (window) step and the
@@ -219,6 +230,7 @@ def run_ours(args, rank, local_rank, world):
     import maze_b200 as mb
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    pin_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
