@@ -152,8 +152,13 @@ def pin_to_gpu_numa_node(index):
     are allocated on the GPU's NUMA node (8 ranks sharing one node's memory halve the copy rate)."""
     try:
         import pynvml
+        import torch
         pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        try:      # CUDA_VISIBLE_DEVICES may renumber the devices: go through the UUID
+            handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
     except Exception as exc:   # not fatal: only the host-copy rate depends on it
         print(f"[bench] no CPU affinity for GPU {index}: {exc}", file=sys.stderr)
 
