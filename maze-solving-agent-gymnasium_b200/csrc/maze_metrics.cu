@@ -4,6 +4,15 @@
 // (lib/maze_generation.py:48-56; trainers pad the same way, off_policy_trainer.py:63-64).
 #include "maze_metrics.cuh"
 
+#ifdef MAZE_METRICS_PROFILE
+extern "C" int maze_debug_metrics_profile(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_met_prof, sizeof(g_met_prof));
+    if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(g_met_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 namespace {
 
 __global__ void __launch_bounds__(FIELD_THREADS)
@@ -31,7 +40,11 @@ maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restr
         __syncthreads();
         const int start_idx = ((start & 0xffff) + pad) * Wb + (start >> 16) + pad;
         const int goal_idx = ((goal & 0xffff) + pad) * Wb + (goal >> 16) + pad;
+#ifdef MAZE_METRICS_PROFILE
+        long long _mt = clock64();
+#endif
         block_bfs(f, Hb, Wb, false, start_idx);
+        MET_TICK(0);
         maze_metrics(f, ms, Hb, Wb, start_idx, goal_idx, s_out);
         if (tid == 0) {
             double* o = out + (size_t)item * MAZE_METRIC_WORDS;

@@ -63,6 +63,13 @@ __device__ __forceinline__ void atomic_min_u16(unsigned short* p, unsigned short
     }
 }
 
+#ifdef MAZE_METRICS_PROFILE
+static __device__ unsigned long long g_met_prof[12];
+#define MET_TICK(i) do { __syncthreads(); if (threadIdx.x == 0) { long long _n = clock64(); atomicAdd(&g_met_prof[i], (unsigned long long)(_n - _mt)); _mt = _n; } } while (0)
+#else
+#define MET_TICK(i) do {} while (0)
+#endif
+
 struct MazeMetrics {
     double difficulty, complexity, L, DE, D;
     int sol_len, de_count;
@@ -90,6 +97,9 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
         return;
     }
     const int sol_len = (int)f.dist[goal_idx] + 1;
+#ifdef MAZE_METRICS_PROFILE
+    long long _mt = clock64();
+#endif
 
     // ---- 1. per-cell neighbour count / turn / node flags
     for (int ci = tid; ci < cells; ci += nthr) {
@@ -110,6 +120,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
     if (tid == 0) { s_D0 = 0.0; s_S0 = 0.0; s_dcount = 0; }
     __syncthreads();
 
+    MET_TICK(1);
     // ---- 2. mark the solution (goal -> start along BFS parents); D = decision cells on it
     if (tid == 0) {
         int b = goal_idx, dcount = 0;
@@ -129,6 +140,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
     }
     __syncthreads();
 
+    MET_TICK(2);
     // ---- 3. parent node and edge length of every node (walk straight up to the next node)
     for (int ci = tid; ci < cells; ci += nthr) {
         if (!(ms.flags[ci] & MF_NODE) || ci == start_c) continue;
@@ -145,64 +157,95 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
             pc = block_cell(b);
         } while (!(ms.flags[pc] & MF_NODE));
         ms.pnode[ci] = (unsigned short)pc;
-        ms.dpar[ci] = (unsigned short)(2 * hops - 1);   // maze_complexity_evaluation.py:176-184
+        // low byte: blocks strictly between (maze_complexity_evaluation.py:176-184); bits 8-9: direction towards the parent
+        const int dcode = step == -Wb ? 0 : (step == Wb ? 1 : (step == -1 ? 2 : 3));
+        ms.dpar[ci] = (unsigned short)((2 * hops - 1) | (dcode << 8));
     }
     __syncthreads();
 
+    MET_TICK(3);
     auto is_sol = [&](int ci) { return (ms.flags[ci] & MF_SOL) != 0; };
     auto nbof = [&](int ci) { return ms.flags[ci] & MF_NB; };
     auto is_plain = [&](int ci) { return !is_sol(ci) && nbof(ci) != 3; };
     auto is_dead_end_off = [&](int ci) { return (ms.flags[ci] & MF_NODE) && nbof(ci) == 1 && !is_sol(ci); };
-    // unit direction (as a block offset) from node a to node b lying on one straight segment
-    auto dir_between = [&](int a, int b) {
-        const int ab = cell_block(a), bb = cell_block(b);
-        const int dr = bb / Wb - ab / Wb, dc = bb % Wb - ab % Wb;
-        return dr != 0 ? (dr > 0 ? Wb : -Wb) : (dc > 0 ? 1 : -1);
-    };
 
-    // ---- 4. Kim-Crawfis DE: sequential over dead ends in row-major order (metrics_calculator.py:87-173)
+    // ---- 4. Kim-Crawfis DE (metrics_calculator.py:87-173).  Whether a dead end counts depends on the
+    // decision points recorded by the dead ends before it in row-major order, so the final pass is
+    // sequential; everything that does not depend on that order is done in parallel first:
+    //   4a  nearest node with more than two open neighbours above every node (ms.minleaf as scratch)
+    //   4b  per dead end: cut or not, alcove / forward / backward (ms.comp as scratch)
+    //   4c  thread 0: walk only the chain of decision points above each dead end, stop at the first
+    //       recorded one
     int alcoves = 0, forward = 0, backward = 0;
-    if (tid == 0 && with_kc) {
+    if (with_kc) {
+        unsigned short* jup = ms.minleaf;
+        unsigned short* kind = ms.comp;
+        auto dcode = [&](int ci) { return (ms.dpar[ci] >> 8) & 3; };
+        for (int ci = tid; ci < cells; ci += nthr) {
+            if (!(ms.flags[ci] & MF_NODE)) continue;
+            int y = ms.pnode[ci];
+            while (y != 0xffff && (ms.flags[y] & MF_NB) <= 2) y = ms.pnode[y];
+            jup[ci] = (unsigned short)y;
+        }
+        __syncthreads();
         const int gr = goal_idx / Wb, gc = goal_idx % Wb;
-        for (int de = 0; de < cells; ++de) {
+        for (int de = tid; de < cells; de += nthr) {
             if (!is_dead_end_off(de)) continue;
             // attachment A = first solution node above; cut iff it sits at path index <= sol_len - 2
             int a = ms.pnode[de];
             while (!is_sol(a)) a = ms.pnode[a];
-            const int j = (int)f.dist[cell_block(de)] - (int)f.dist[cell_block(a)];
+            const int db = cell_block(de);
+            const int j = (int)f.dist[db] - (int)f.dist[cell_block(a)];
             const bool cut = j <= sol_len - 2;
-            bool blocked = false, has_turn = false;
-            int first_dp = -1, prev = de, y = ms.pnode[de], below_a = de;
-            // interior nodes: strictly above the dead end, up to (cut) the node below A or
-            // (uncut) the node below start
-            for (;;) {
-                if (cut ? (y == a) : (y == start_c)) break;
-                const int fl = ms.flags[y];
-                if (fl & MF_DP) blocked = true;
-                if ((fl & MF_NB) > 2 && first_dp < 0) first_dp = y;
-                if (dir_between(prev, y) != dir_between(y, ms.pnode[y])) has_turn = true;
+            // interior nodes: strictly above the dead end, up to (cut) the node below A or (uncut) the node below start
+            bool has_turn = false;
+            int prev = de, below_a = de;
+            for (int y = ms.pnode[de]; cut ? (y != a) : (y != start_c); y = ms.pnode[y]) {
+                if (dcode(prev) != dcode(y)) has_turn = true;
                 if (!is_sol(y)) below_a = y;
                 prev = y;
-                y = ms.pnode[y];
             }
-            if (blocked) continue;
-            if (first_dp >= 0) ms.flags[first_dp] |= MF_DP;
-            const int len = cut ? j : (int)f.dist[cell_block(de)] + 1;
-            const bool flag = len >= 3 && (has_turn || first_dp >= 0);   // type_of_DE :153-173
-            if (!flag) { ++alcoves; continue; }
-            int lr, lc;   // path[-1]
-            if (cut) {
-                const int ab = cell_block(a) + dir_between(a, below_a);
-                lr = ab / Wb; lc = ab % Wb;
-            } else {
-                lr = start_idx / Wb; lc = start_idx % Wb;
+            const int fj = jup[de];
+            const bool has_dp = fj != 0xffff && (cut ? !is_sol(fj) : fj != start_c);
+            const int len = cut ? j : (int)f.dist[db] + 1;
+            int k = 0;   // 0 alcove, 1 forward, 2 backward (type_of_DE :153-173)
+            if (len >= 3 && (has_turn || has_dp)) {
+                int lr, lc;   // path[-1]
+                if (cut) {
+                    const int back[4] = {Wb, -Wb, 1, -1};   // from A one block towards the node below it
+                    const int ab = cell_block(a) + back[dcode(below_a)];
+                    lr = ab / Wb; lc = ab % Wb;
+                } else {
+                    lr = start_idx / Wb; lc = start_idx % Wb;
+                }
+                const int diff = (abs(lr - gr) + abs(lc - gc)) - (abs(db / Wb - gr) + abs(db % Wb - gc));
+                k = diff > 0 ? 1 : 2;
             }
-            const int db = cell_block(de);
-            const int diff = (abs(lr - gr) + abs(lc - gc)) - (abs(db / Wb - gr) + abs(db % Wb - gc));
-            if (diff > 0) ++forward; else ++backward;
+            kind[de] = (unsigned short)(k | (cut ? 4 : 0));
         }
+        __syncthreads();
+        if (tid == 0) {
+            for (int de = 0; de < cells; ++de) {
+                if (!is_dead_end_off(de)) continue;
+                const int kd = kind[de];
+                const bool cut = (kd & 4) != 0;
+                bool blocked = false;
+                int first_dp = -1;
+                for (int y = jup[de]; y != 0xffff && (cut ? !is_sol(y) : y != start_c); y = jup[y]) {
+                    if (ms.flags[y] & MF_DP) { blocked = true; break; }
+                    if (first_dp < 0) first_dp = y;
+                }
+                if (blocked) continue;
+                if (first_dp >= 0) ms.flags[first_dp] |= MF_DP;
+                if ((kd & 3) == 0) ++alcoves; else if ((kd & 3) == 1) ++forward; else ++backward;
+            }
+        }
+        __syncthreads();
+        for (int ci = tid; ci < cells; ci += nthr) { ms.minleaf[ci] = 0xffffu; ms.comp[ci] = 0xffffu; }   // scratch back to its initial state
+        __syncthreads();
     }
 
+    MET_TICK(4);
     // ---- 5. smallest dead-end rank below every off-solution node (adjacency order of the reference)
     for (int ci = tid; ci < cells; ci += nthr) {
         if (!is_dead_end_off(ci)) continue;
@@ -212,6 +255,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
             y = ms.pnode[y];
         }
     }
+    MET_TICK(5);
     // ---- 6. component root of every plain node
     for (int ci = tid; ci < cells; ci += nthr) {
         if (!(ms.flags[ci] & MF_NODE) || !is_plain(ci)) continue;
@@ -221,11 +265,12 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
     }
     __syncthreads();
 
+    MET_TICK(6);
     // ---- 7. every tree edge goes to at most one hallway (maze_complexity_evaluation.py:186-221)
     for (int n = tid; n < cells; n += nthr) {
         if (!(ms.flags[n] & MF_NODE) || n == start_c) continue;
         const int p = ms.pnode[n];
-        const unsigned d = ms.dpar[n];
+        const unsigned d = ms.dpar[n] & 0xffu;
         const double s = 1.0 / (double)(2 * d);
         if (is_sol(n)) {                       // solution chain = hallway 0
             atomicAdd(&s_D0, (double)d);
@@ -246,6 +291,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
     }
     __syncthreads();
 
+    MET_TICK(7);
     // ---- 8. hallway complexity -> branch (maze_complexity_evaluation.py:223-259,286-308)
     for (int r = tid; r < cells; r += nthr) {
         if (!(ms.flags[r] & MF_NODE) || ms.comp[r] != r) continue;
@@ -261,6 +307,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
     }
     __syncthreads();
 
+    MET_TICK(8);
     // ---- 9. reduce: sum and product over branches
     double tsum = 0.0, tprod = 1.0;
     for (int k = tid; k < cells; k += nthr) {
