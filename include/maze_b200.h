@@ -40,6 +40,10 @@ extern "C" {
 /* limits */
 #define MAZE_MAX_DIM      255  /* H, W <= 255 (positions are stored in one byte each)        */
 #define MAZE_GEN_MAX_DIM  131  /* generator / fields kernels stage one maze in shared memory */
+#define MAZE_GEN_MAX_CELLS 64  /* generators hold one 64-bit word per lattice row: bordered shapes up to
+                                  129 x 129 (64 x 64 cells), toroidal shapes up to 127 x 127 (generated at
+                                  shape + 2 = 129); a slot asking for more is left untouched and gets
+                                  MAZE_META_SOL_LEN = -1                                              */
 #define MAZE_WINDOW       15   /* simple_maze_env.py:130 WINDOW_DIM                          */
 
 /* generator ids: lib/maze_generation.py:24-30 */

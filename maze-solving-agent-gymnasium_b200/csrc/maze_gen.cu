@@ -476,6 +476,10 @@ maze_generate_warp_kernel(GenParams p) {
         if (flags & MAZE_FLAG_TOROIDAL) continue;   // done by the CTA kernel
         const int gen_count = mm[MAZE_META_SPARE];
         const int nr = (H - 1) / 2, nc = (W - 1) / 2;
+        if (nr > MAZE_GEN_MAX_CELLS || nc > MAZE_GEN_MAX_CELLS || nr < 1 || nc < 1) {
+            if (lane == 0) mm[MAZE_META_SOL_LEN] = -1;
+            continue;
+        }
 #ifdef MAZE_GEN_PROFILE
         long long _t = clock64();
 #endif
@@ -548,6 +552,10 @@ maze_generate_kernel(GenParams p) {
         const int gen_count = mm[MAZE_META_SPARE];
         const int Hb = tor ? H + 2 : H, Wb = tor ? W + 2 : W;   // :48 gen_maze(shape + 2)
         const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2;
+        if (nr > MAZE_GEN_MAX_CELLS || nc > MAZE_GEN_MAX_CELLS || nr < 1 || nc < 1 || Hb * Wb > p.smem_hw) {
+            if (tid == 0) mm[MAZE_META_SOL_LEN] = -1;
+            continue;
+        }
 
 #ifdef MAZE_GEN_PROFILE
         long long _t = clock64();

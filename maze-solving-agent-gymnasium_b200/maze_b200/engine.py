@@ -111,7 +111,7 @@ class MazePool:
             if shapes is None:
                 shapes = self.max_shape
             def record(shape, a, t):
-                H, W = check_shape(shape, cabi.GEN_MAX_DIM - 2)
+                H, W = check_shape(shape, cabi.GEN_MAX_DIM - 2 - (2 if t else 0))   # toroidal mazes are generated at shape + 2
                 if H * W > self.slot:
                     raise ValueError(f"shape {(H, W)} does not fit the pool slot")
                 if isinstance(a, str):

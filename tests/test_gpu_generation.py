@@ -122,6 +122,22 @@ def test_generator_distribution_matches_reference(algo, shape):
         assert ok, (algo, shape, name, info)
 
 
+@pytest.mark.parametrize("algo", ALGORITHMS)
+def test_largest_toroidal_shape(algo):
+    """127 x 127 border-less mazes are generated at 129 x 129 = 64 x 64 cells, the lattice limit."""
+    mb, pool = _gen(6, 127, algo, toroidal=True, seed=3)
+    meta = pool.meta_host()
+    for m in range(6):
+        grid = pool.grid_host(m)
+        assert grid.shape == (127, 127)
+        ok, why = check_perfect_maze(np.pad(grid, 1))
+        assert ok, (algo, m, why)
+        t = MazeTables(grid, _unpack(meta[m, mb.cabi.META_START]), _unpack(meta[m, mb.cabi.META_GOAL]), True)
+        np.testing.assert_array_equal(pool.table_host(m), t.table)
+    with pytest.raises(ValueError):
+        mb.MazePool(2, (129, 129)).generate(toroidal=True)
+
+
 def test_generate_argument_errors():
     import maze_b200 as mb
     pool = mb.MazePool(4, (21, 21))
