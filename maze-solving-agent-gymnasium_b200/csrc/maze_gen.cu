@@ -26,6 +26,7 @@
 // draws from Python's global `random` through set iteration order, which cannot be replayed, so
 // parity for generators is structural (spanning tree) + distributional (see tests).
 #include "maze_metrics.cuh"
+#include "maze_walls.cuh"
 
 #ifdef MAZE_GEN_PROFILE   // scratch instrumentation: cycles per phase, summed over mazes
 __device__ unsigned long long g_gen_prof[8];
@@ -42,10 +43,8 @@ extern "C" int maze_debug_gen_profile(unsigned long long* out, int reset) {
 
 namespace {
 
-typedef unsigned long long u64;
 constexpr int GEN_THREADS = FIELD_THREADS;   // CTA-per-maze kernel
 constexpr int WARP_GEN_THREADS = 256;        // warp-per-maze kernel: 8 mazes per CTA
-constexpr unsigned FULL = 0xffffffffu;
 
 struct GenParams {
     uint8_t* grids;          // [M, slot] out (may be NULL)
@@ -87,27 +86,6 @@ struct GenRng {
     }
     __device__ __forceinline__ unsigned below(unsigned n) { return __umulhi(next(), n); }   // bias < n / 2^32
 };
-
-// ---- row bit-planes in registers (warp-uniform i, j everywhere) -------------------------------
-
-struct RowSets {
-    u64 a0, a1;   // rows lane, lane + 32
-};
-struct Walls {
-    RowSets e, s;
-};
-
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-
-__device__ __forceinline__ u64 row_get(const RowSets& s, int i) {   // row i, broadcast to every lane
-    return __shfl_sync(FULL, (i >> 5) ? s.a1 : s.a0, i & 31);
-}
-__device__ __forceinline__ void row_or(RowSets& s, int i, u64 bits) {
-    if ((i & 31) == lane_id()) {
-        if (i >> 5) s.a1 |= bits; else s.a0 |= bits;
-    }
-}
-__device__ __forceinline__ int cell_bit(const RowSets& s, int i, int j) { return (int)((row_get(s, i) >> j) & 1ull); }
 
 __device__ __forceinline__ int warp_incl_scan(int v) {
     const int lane = lane_id();
@@ -297,25 +275,6 @@ __device__ __forceinline__ void generate_walls(Walls& w, int algo, int nr, int n
     if (algo == MAZE_ALGO_RPRIM) gen_random_prim(w, nr, nc, si, sj, rng);
     else if (algo == MAZE_ALGO_DFS) gen_depth_first(w, nr, nc, si, sj, rng);
     else gen_prim_and_kill(w, nr, nc, si, sj, rng);
-}
-
-// ---- bit-parallel breadth-first search over the cell lattice ----------------------------------
-
-struct Reach {   // cells adjacent to the frontier, by where their frontier neighbour sits
-    u64 l0, l1, r0, r1, a0, a1, b0, b1;   // left / right / above / below, rows lane / lane + 32
-};
-
-__device__ __forceinline__ void bfs_expand(const Walls& w, u64 f0, u64 f1, Reach& x) {
-    const int lane = lane_id();
-    x.l0 = (f0 & w.e.a0) << 1;  x.l1 = (f1 & w.e.a1) << 1;
-    x.r0 = (f0 >> 1) & w.e.a0;  x.r1 = (f1 >> 1) & w.e.a1;
-    const u64 d0 = f0 & w.s.a0, d1 = f1 & w.s.a1;          // frontier cells whose south wall is open
-    const u64 u0 = __shfl_up_sync(FULL, d0, 1), u1 = __shfl_up_sync(FULL, d1, 1), wrap_a = __shfl_sync(FULL, d0, 31);
-    x.a0 = lane == 0 ? 0ull : u0;
-    x.a1 = lane == 0 ? wrap_a : u1;
-    const u64 n0 = __shfl_down_sync(FULL, f0, 1), n1 = __shfl_down_sync(FULL, f1, 1), wrap_b = __shfl_sync(FULL, f1, 0);
-    x.b0 = (lane == 31 ? wrap_b : n0) & w.s.a0;
-    x.b1 = (lane == 31 ? 0ull : n1) & w.s.a1;
 }
 
 // goal = the leaf farthest from start, first in row-major order on ties
@@ -562,7 +521,10 @@ maze_generate_kernel(GenParams p) {
 #endif
         for (int cand = 0; cand < p.candidates; ++cand) {
             __syncthreads();   // previous item / candidate fully consumed before smem is reused
-            for (int i = tid; i < Hb * Wb; i += GEN_THREADS) f.grid[i] = 0;
+            for (int i = tid; i < Hb * Wb; i += GEN_THREADS) {
+                f.grid[i] = 0;
+                if (kScored) f.dist[i] = DIST_INF;
+            }
             __syncthreads();
             GEN_TICK(0);
 
@@ -579,6 +541,7 @@ maze_generate_kernel(GenParams p) {
                 }
                 __syncwarp();
                 if (tid == 0) f.grid[s_goal] = 2;   // :33
+                if (kScored) cell_bfs_distances(w, si, sj, f.dist, Wb);   // block distances from start for the metrics
             }
             __syncthreads();
             GEN_TICK(1);
@@ -586,7 +549,6 @@ maze_generate_kernel(GenParams p) {
             if constexpr (kScored) {
                 // McClendon difficulty of the bordered maze (base_maze_env.py:86-92; for border-less
                 // mazes lib/maze_generation.py:51), on block distances from start
-                block_bfs(f, Hb, Wb, false, s_start);
                 GEN_TICK(2);
                 maze_metrics(f, ms, Hb, Wb, s_start, s_goal, s_metrics, false);
                 if (tid == 0) {

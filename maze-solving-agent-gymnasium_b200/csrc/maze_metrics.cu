@@ -3,6 +3,7 @@
 // zero-padded grid, which is exactly the bordered maze gen_maze_no_border scored before stripping
 // (lib/maze_generation.py:48-56; trainers pad the same way, off_policy_trainer.py:63-64).
 #include "maze_metrics.cuh"
+#include "maze_walls.cuh"
 
 #ifdef MAZE_METRICS_PROFILE
 extern "C" int maze_debug_metrics_profile(unsigned long long* out, int reset) {
@@ -43,7 +44,21 @@ maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restr
 #ifdef MAZE_METRICS_PROFILE
         long long _mt = clock64();
 #endif
-        block_bfs(f, Hb, Wb, false, start_idx);
+        // block distances from start: bit-parallel BFS over the cell lattice by warp 0 (one level per
+        // cell distance, whatever the frontier size); lattices above 64 x 64 cells use the CTA-wide BFS
+        const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2;
+        if (nr <= MAZE_GEN_MAX_CELLS && nc <= MAZE_GEN_MAX_CELLS && (start_idx / Wb & 1) && (start_idx % Wb & 1)) {
+            for (int i = tid; i < Hb * Wb; i += FIELD_THREADS) f.dist[i] = DIST_INF;
+            __syncthreads();
+            if (tid < 32) {
+                Walls w;
+                walls_from_grid(f.grid, Wb, nr, nc, w);
+                cell_bfs_distances(w, (start_idx / Wb - 1) >> 1, (start_idx % Wb - 1) >> 1, f.dist, Wb);
+            }
+            __syncthreads();
+        } else {
+            block_bfs(f, Hb, Wb, false, start_idx);
+        }
         MET_TICK(0);
         maze_metrics(f, ms, Hb, Wb, start_idx, goal_idx, s_out);
         if (tid == 0) {
