@@ -8,24 +8,9 @@ maze_fields_kernel(const uint8_t* __restrict__ grids, int32_t* __restrict__ meta
                    const int32_t* __restrict__ ids, int slot) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int m = ids ? ids[blockIdx.x] : blockIdx.x;
-    int32_t* mm = meta + (size_t)m * MAZE_META_WORDS;
-    const int H = mm[MAZE_META_H], W = mm[MAZE_META_W];
-    const int start = mm[MAZE_META_START], goal = mm[MAZE_META_GOAL];
-    const bool tor = (mm[MAZE_META_FLAGS] & MAZE_FLAG_TOROIDAL) != 0;
-    const int hw = H * W;
-    FieldSmem f = field_smem_carve(smem, hw);
-    const uint8_t* g = grids + (size_t)m * slot;
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) f.grid[i] = g[i];
-    __syncthreads();
-    const int gr = goal & 0xffff, gc = goal >> 16;
-    block_bfs(f, H, W, tor, gr * W + gc);
-    encode_step_table(f, H, W, tor, gr, gc, table + (size_t)m * slot);
-    if (threadIdx.x == 0) {
-        const int d = f.dist[(start & 0xffff) * W + (start >> 16)];
-        const int sol_len = (d == DIST_INF) ? 0 : d + 1;
-        mm[MAZE_META_SOL_LEN] = sol_len;
-        mm[MAZE_META_MAX_STEPS] = max_steps_budget(H, W, sol_len);
-    }
+    const int32_t* mm = meta + (size_t)m * MAZE_META_WORDS;
+    FieldSmem f = field_smem_carve(smem, mm[MAZE_META_H] * mm[MAZE_META_W]);
+    fields_of_slot(f, grids, meta, table, m, slot);
 }
 
 }  // namespace

@@ -145,3 +145,26 @@ __device__ inline void encode_step_table(const FieldSmem& f, int H, int W, bool 
         out[i] = (uint8_t)((f.grid[i] != 0 ? MAZE_TAB_OPEN : 0) | (code << MAZE_TAB_CODE_SHIFT) | (d4 << MAZE_TAB_D4_SHIFT));
     }
 }
+
+// Fields of the maze in slot m whose block grid lies in global memory: BFS from the goal, step table,
+// step budget (the body of maze_fields; also the second half of toroidal generation).  One CTA.
+__device__ inline void fields_of_slot(const FieldSmem& f, const uint8_t* __restrict__ grids, int32_t* __restrict__ meta,
+                                      uint8_t* __restrict__ table, int m, int slot) {
+    int32_t* mm = meta + (size_t)m * MAZE_META_WORDS;
+    const int H = mm[MAZE_META_H], W = mm[MAZE_META_W];
+    const int start = mm[MAZE_META_START], goal = mm[MAZE_META_GOAL];
+    const bool tor = (mm[MAZE_META_FLAGS] & MAZE_FLAG_TOROIDAL) != 0;
+    const uint8_t* g = grids + (size_t)m * slot;
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) f.grid[i] = g[i];
+    __syncthreads();
+    const int gr = goal & 0xffff, gc = goal >> 16;
+    block_bfs(f, H, W, tor, gr * W + gc);
+    encode_step_table(f, H, W, tor, gr, gc, table + (size_t)m * slot);
+    if (threadIdx.x == 0) {
+        const int d = f.dist[(start & 0xffff) * W + (start >> 16)];
+        const int sol_len = (d == DIST_INF) ? 0 : d + 1;
+        mm[MAZE_META_SOL_LEN] = sol_len;
+        mm[MAZE_META_MAX_STEPS] = max_steps_budget(H, W, sol_len);
+    }
+}

@@ -417,7 +417,29 @@ __device__ __forceinline__ void encode_bordered(const Walls& w, const GoalField&
     }
 }
 
-// ---- warp-per-maze kernel (bordered mazes, unscored) ------------------------------------------
+// Border-less (toroidal) maze: the block grid of the bordered maze without its outer ring
+// (lib/maze_generation.py:53-55), written from the register planes; pitch W = Wb - 2.
+__device__ __forceinline__ void write_stripped_grid(const Walls& w, int Hb, int Wb, int gi, int gj, uint8_t* __restrict__ grid) {
+    const int lane = lane_id();
+    const int W = Wb - 2;
+    for (int r = 1; r < Hb - 1; ++r) {
+        const bool cell_row = (r & 1) != 0;
+        const int i = cell_row ? (r - 1) >> 1 : (r >> 1) - 1;
+        const u64 Ei = cell_row ? row_get(w.e, i) : 0ull, Si = cell_row ? 0ull : row_get(w.s, i);
+        for (int c = 1 + lane; c < Wb - 1; c += 32) {
+            int gv = 0;
+            if (cell_row) {
+                if (c & 1) gv = (i == gi && ((c - 1) >> 1) == gj) ? 2 : 1;
+                else gv = (int)((Ei >> ((c - 2) >> 1)) & 1ull);
+            } else if (c & 1) {
+                gv = (int)((Si >> ((c - 1) >> 1)) & 1ull);
+            }
+            grid[(r - 1) * W + (c - 1)] = (uint8_t)gv;
+        }
+    }
+}
+
+// ---- warp-per-maze kernel (unscored) ----------------------------------------------------------
 
 __global__ void __launch_bounds__(WARP_GEN_THREADS, 4)
 maze_generate_warp_kernel(GenParams p) {
@@ -432,9 +454,11 @@ maze_generate_warp_kernel(GenParams p) {
         int32_t* mm = p.meta + (size_t)m * MAZE_META_WORDS;
         const int H = mm[MAZE_META_H], W = mm[MAZE_META_W];
         const int flags = mm[MAZE_META_FLAGS];
-        if (flags & MAZE_FLAG_TOROIDAL) continue;   // done by the CTA kernel
+        const bool tor = (flags & MAZE_FLAG_TOROIDAL) != 0;
+        if (tor && !p.grids) continue;   // without a grid buffer the CTA kernel does the toroidal slots
         const int gen_count = mm[MAZE_META_SPARE];
-        const int nr = (H - 1) / 2, nc = (W - 1) / 2;
+        const int Hb = tor ? H + 2 : H, Wb = tor ? W + 2 : W;   // :48 gen_maze(shape + 2)
+        const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2;
         if (nr > MAZE_GEN_MAX_CELLS || nc > MAZE_GEN_MAX_CELLS || nr < 1 || nc < 1) {
             if (lane == 0) mm[MAZE_META_SOL_LEN] = -1;
             continue;
@@ -450,6 +474,17 @@ maze_generate_warp_kernel(GenParams p) {
         const int goal = select_goal(w, si, sj);
         const int gi = goal >> 8, gj = goal & 0xff;
         GEN_TICK(2);
+        if (tor) {   // grid + start / goal now, fields by maze_fields_toroidal_kernel (block-level BFS on the torus)
+            write_stripped_grid(w, Hb, Wb, gi, gj, p.grids + (size_t)m * p.slot);
+            __syncwarp();
+            if (lane == 0) {
+                mm[MAZE_META_START] = (2 * si) | ((2 * sj) << 16);
+                mm[MAZE_META_GOAL] = (2 * gi) | ((2 * gj) << 16);
+                mm[MAZE_META_SOL_LEN] = 0;   // pending: written by the fields kernel
+                mm[MAZE_META_SPARE] = gen_count + 1;
+            }
+            continue;
+        }
         GoalField g;
         goal_field(w, gi, gj, si, sj, 2 * (H < W ? H : W), g);
         GEN_TICK(5);
@@ -464,6 +499,20 @@ maze_generate_warp_kernel(GenParams p) {
             mm[MAZE_META_SPARE] = gen_count + 1;
         }
         GEN_TICK(6);
+    }
+}
+
+// second half of unscored toroidal generation: fields of the toroidal slots among the items
+__global__ void __launch_bounds__(FIELD_THREADS)
+maze_fields_toroidal_kernel(GenParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = p.count_dev ? min(*p.count_dev, p.n) : p.n;
+    FieldSmem f = field_smem_carve(smem, p.smem_hw);
+    for (int item = blockIdx.x; item < n; item += gridDim.x) {
+        const int m = p.ids ? p.ids[item] : item;
+        const int32_t* mm = p.meta + (size_t)m * MAZE_META_WORDS;
+        if (!(mm[MAZE_META_FLAGS] & MAZE_FLAG_TOROIDAL) || mm[MAZE_META_SOL_LEN] == -1) continue;
+        fields_of_slot(f, p.grids, p.meta, p.table, m, p.slot);
     }
 }
 
@@ -639,8 +688,17 @@ extern "C" int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8
         maze_generate_warp_kernel<<<grid, WARP_GEN_THREADS, 0, st>>>(p);
         MAZE_CHECK(cudaGetLastError());
     }
-    // toroidal slots (always) and scored generation: one CTA per maze.  When nothing in the batch is
-    // toroidal the CTAs of the unscored launch find no work and exit.
+    if (!scored && grids) {   // toroidal slots: their fields need a block-resolution BFS; CTAs find no work otherwise
+        const size_t fsmem = field_smem_bytes(p.smem_hw);
+        MAZE_CHECK(cudaFuncSetAttribute(maze_fields_toroidal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        int per = 0;
+        MAZE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, maze_fields_toroidal_kernel, FIELD_THREADS, fsmem));
+        if (per < 1) per = 1;
+        maze_fields_toroidal_kernel<<<n < per * sms ? n : per * sms, FIELD_THREADS, fsmem, st>>>(p);
+        MAZE_CHECK(cudaGetLastError());
+        return 0;
+    }
+    // scored generation (and toroidal slots when there is no grid buffer): one CTA per maze
     size_t smem = field_smem_bytes(p.smem_hw);
     if (scored) smem += (((size_t)p.smem_hw + 15) & ~(size_t)15) + metrics_smem_bytes(p.smem_cells);
     auto kernel = scored ? maze_generate_kernel<true> : maze_generate_kernel<false>;
