@@ -211,7 +211,17 @@ def measure_extras(mb, torch, device):
     t = timed(lambda: venv.step(acts), 100)
     out["v1_window_env_steps_per_s"] = Bv / t
     out["v1_window_write_GBps"] = Bv * 2700 / t / 1e9
-    del venv
+    # DQN data path: step + bit-packed observation + replay push (245 B per transition), and batch sampling
+    from maze_b200.dqn import DeviceReplay
+    memory = DeviceReplay(venv, 1 << 20, seed=1)
+    memory.observe()
+
+    def step_push():
+        venv.batch.step(acts, venv._mode)
+        memory.push(acts)
+    out["dqn_step_push_env_steps_per_s"] = Bv / timed(step_push, 100)
+    out["dqn_replay_samples_per_s"] = 65536 / timed(lambda: memory.sample(65536), 20)
+    del venv, memory
     # fused tabular Q-learning rollout (policy + step + update per env, 64 steps per launch)
     from maze_b200.agents import QAgent
     Bq = 1048576
