@@ -568,46 +568,52 @@ maze_generate_kernel(GenParams p) {
 #ifdef MAZE_GEN_PROFILE
         long long _t = clock64();
 #endif
-        for (int cand = 0; cand < p.candidates; ++cand) {
-            __syncthreads();   // previous item / candidate fully consumed before smem is reused
-            for (int i = tid; i < Hb * Wb; i += GEN_THREADS) {
-                f.grid[i] = 0;
-                if (kScored) f.dist[i] = DIST_INF;
-            }
-            __syncthreads();
-            GEN_TICK(0);
-
-            if (tid < 32) {
-                Walls w;
-                int si, sj;
+        // Candidates are DRAWN four at a time, one per warp (the carving loop is a dependent chain that
+        // leaves a lone warp mostly idle), and SCORED one after the other in candidate order by the CTA.
+        constexpr int NW = GEN_THREADS / 32;
+        const int wid = tid >> 5;
+        for (int base = 0; base < p.candidates; base += NW) {
+            Walls w;
+            int si = 0, sj = 0, goal = 0;
+            if (base + wid < p.candidates) {
                 generate_walls(w, algo, nr, nc, p.seed, (u64)(p.slot_id_base + m) | ((u64)(unsigned)gen_count << 40),
-                               (unsigned)cand, si, sj);
-                const int goal = select_goal(w, si, sj);
-                expand_walls(w, f.grid, Wb, nr, nc);
-                if (tid == 0) {
-                    s_start = (2 * si + 1) * Wb + 2 * sj + 1;
-                    s_goal = (2 * (goal >> 8) + 1) * Wb + 2 * (goal & 0xff) + 1;
-                }
-                __syncwarp();
-                if (tid == 0) f.grid[s_goal] = 2;   // :33
-                if (kScored) cell_bfs_distances(w, si, sj, f.dist, Wb);   // block distances from start for the metrics
+                               (unsigned)(base + wid), si, sj);
+                goal = select_goal(w, si, sj);
             }
-            __syncthreads();
             GEN_TICK(1);
-
-            if constexpr (kScored) {
-                // McClendon difficulty of the bordered maze (base_maze_env.py:86-92; for border-less
-                // mazes lib/maze_generation.py:51), on block distances from start
-                GEN_TICK(2);
-                maze_metrics(f, ms, Hb, Wb, s_start, s_goal, s_metrics, false);
-                if (tid == 0) {
-                    s_take = (cand == 0) || (s_metrics.difficulty < s_keep_diff);   // strict <, first wins ties
-                    if (s_take) { s_keep_diff = s_metrics.difficulty; s_keep_start = s_start; s_keep_goal = s_goal; }
+            for (int k = 0; k < NW && base + k < p.candidates; ++k) {
+                const int cand = base + k;
+                __syncthreads();   // previous item / candidate fully consumed before smem is reused
+                for (int i = tid; i < Hb * Wb; i += GEN_THREADS) {
+                    f.grid[i] = 0;
+                    if (kScored) f.dist[i] = DIST_INF;
                 }
                 __syncthreads();
-                if (p.candidates > 1 && s_take)
-                    for (int i = tid; i < Hb * Wb; i += GEN_THREADS) keep[i] = f.grid[i];
-                GEN_TICK(3);
+                if (wid == k) {
+                    expand_walls(w, f.grid, Wb, nr, nc);
+                    if ((tid & 31) == 0) {
+                        s_start = (2 * si + 1) * Wb + 2 * sj + 1;
+                        s_goal = (2 * (goal >> 8) + 1) * Wb + 2 * (goal & 0xff) + 1;
+                    }
+                    __syncwarp();
+                    if ((tid & 31) == 0) f.grid[s_goal] = 2;   // :33
+                    if (kScored) cell_bfs_distances(w, si, sj, f.dist, Wb);   // block distances from start for the metrics
+                }
+                __syncthreads();
+                GEN_TICK(2);
+                if constexpr (kScored) {
+                    // McClendon difficulty of the bordered maze (base_maze_env.py:86-92; for border-less
+                    // mazes lib/maze_generation.py:51), on block distances from start
+                    maze_metrics(f, ms, Hb, Wb, s_start, s_goal, s_metrics, false);
+                    if (tid == 0) {
+                        s_take = (cand == 0) || (s_metrics.difficulty < s_keep_diff);   // strict <, first wins ties
+                        if (s_take) { s_keep_diff = s_metrics.difficulty; s_keep_start = s_start; s_keep_goal = s_goal; }
+                    }
+                    __syncthreads();
+                    if (p.candidates > 1 && s_take)
+                        for (int i = tid; i < Hb * Wb; i += GEN_THREADS) keep[i] = f.grid[i];
+                    GEN_TICK(3);
+                }
             }
         }
         if (kScored && p.candidates > 1) {
