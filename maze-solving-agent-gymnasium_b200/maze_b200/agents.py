@@ -163,7 +163,15 @@ class _ReferenceNamedAgent:
     def update_hyperparameter(self, is_better=None):
         """Applied per agent on the device at episode end (see update); kept for API parity."""
 
-    def rollout(self, k_steps: int, mode: int = cabi.STEP_AUTORESET):
+    def rollout(self, k_steps: int, mode=None):
+        """k_steps fused {get_action, env.step, update} iterations per env in one launch.  `mode`
+        defaults to the vector env's own step mode (autoreset, pool cycling); regeneration on win
+        needs a generation launch between steps and is only available through get_action / update."""
+        if mode is None:
+            mode = getattr(self.env, "_mode", cabi.STEP_AUTORESET)
+            if mode & cabi.STEP_WIN_QUEUE:
+                raise cabi.MazeError("rollout() cannot regenerate mazes between its fused steps: use on_win='keep' / 'next', "
+                                     "or the unfused get_action() / env.step() / update() loop")
         self.core.rollout(k_steps, mode)
 
 

@@ -29,7 +29,7 @@ def _replay(meta, z, visit_layout, on_step):
         on_step(batch, pairs, t + 1)
 
 
-@pytest.mark.parametrize("visit_layout", ["env", "cell"])
+@pytest.mark.parametrize("visit_layout", ["env", "cell", "tile"])
 def test_window_matches_reference_traces(golden_steps, visit_layout):
     z, meta = golden_steps
     meta = [m for m in meta if m["enrich"]]

@@ -93,8 +93,9 @@ def test_step_matches_reference_traces(golden_steps):
         check(t + 1)
 
 
+@pytest.mark.parametrize("visit_layout", ["cell", "tile"])
 @pytest.mark.parametrize("win_next", [False, True])
-def test_step_autoreset_matches_oracle(win_next):
+def test_step_autoreset_matches_oracle(win_next, visit_layout):
     """Many envs over a mixed pool (euclid + torus, 11..81 blocks), autoreset on, 70 % greedy
     policy so that goals are reached; compared against the closed-form oracle every step."""
     from oracle.vector import OracleVector
@@ -106,7 +107,8 @@ def test_step_autoreset_matches_oracle(win_next):
     B = 3 * M
     rng = np.random.default_rng(5)
     env_maze = np.arange(B) % M
-    batch = mb.MazeBatch(pool, B, env_maze=torch.from_numpy(env_maze.astype(np.int32)).cuda(), stats=True, pool_stride=7)
+    batch = mb.MazeBatch(pool, B, env_maze=torch.from_numpy(env_maze.astype(np.int32)).cuda(), stats=True, pool_stride=7,
+                          visit_layout=visit_layout)
     ora = OracleVector(mazes, env_maze, autoreset=True, win_next=win_next, pool_stride=7)
     mode = mb.cabi.STEP_AUTORESET | (mb.cabi.STEP_WIN_NEXT if win_next else 0)
     batch.reset()
