@@ -225,7 +225,8 @@ def measure_extras(mb, torch, device):
     # fused tabular Q-learning rollout (policy + step + update per env, 64 steps per launch)
     from maze_b200.agents import QAgent
     Bq = 1048576
-    qenv = mb.MazeVectorEnv(Bq, shape=SHAPE, num_mazes=1000, seed=1234, on_win="next", stats=True, device=device)
+    qenv = mb.MazeVectorEnv(Bq, shape=SHAPE, num_mazes=1000, seed=1234, on_win="next", stats=True, device=device,
+                            visit_layout="tile")
     agent = QAgent(qenv, learning_rate=0.1, initial_epsilon=0.9, epsilon_decay=2000, final_epsilon=0.05,
                    discount_factor=0.7, eta=1e-3, envs_per_agent=Bq, capacity=1 << 24)
     qenv.reset()
@@ -233,6 +234,20 @@ def measure_extras(mb, torch, device):
     t = timed(lambda: agent.rollout(K), 3)
     agent.core.check_overflow()
     out["q_rollout_env_steps_per_s"] = Bq * K / t
+    del qenv, agent
+    # open-loop bursts: maze_step_many over a 64-step action tape, every per-step output written (bit-identical
+    # to 64 maze_step launches); tiled visit layout.  Reported beside the headline, which is one launch per step.
+    Bm = 4096000
+    menv = mb.MazeVectorEnv(Bm, shape=SHAPE, num_mazes=1000, seed=1234, on_win="next", stats=False, device=device,
+                            visit_layout="tile")
+    menv.reset()
+    tape = torch.randint(0, 4, (K, Bm), dtype=torch.uint8, device=device)
+    for _ in range(5):
+        menv.step_many(tape, trace=False)
+    t = timed(lambda: menv.step_many(tape, trace=True), 4)
+    out["step_many_env_steps_per_s"] = Bm * K / t
+    out["step_many"] = {"k_steps": K, "envs": Bm, "us_per_step_equivalent": t / K * 1e6, "trace": "agent, best_dir, reward, terminated, truncated for every step",
+                        "algorithmic_GBps": ALGO_BYTES_PER_STEP * Bm * K / t / 1e9, "frac_of_measured_hbm_peak": ALGO_BYTES_PER_STEP * Bm * K / t / 1e9 / measured_peak_gbs()[0]}
     return out
 
 

@@ -235,7 +235,101 @@ maze_reset_kernel(maze_env_batch b, const uint8_t* __restrict__ mask) {
     if (b.ep_return) b.ep_return[e] = 0.0;
 }
 
+// k_steps transitions per env, state in registers (see maze_step_many in the header).  Same rules as
+// maze_step_kernel step by step, including the next-step autoreset and the episode statistics.
+__global__ void __launch_bounds__(STEP_THREADS)
+maze_step_many_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, int k_steps, uint32_t mode, StepLuts luts,
+                      maze_step_trace tr, int e0, int e1) {
+    const int e = e0 + blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (e >= e1) return;
+    const size_t B = (size_t)b.num_envs;
+    EnvState st = unpack_state(b.state[e]);
+    int m = b.env_maze[e];
+    MazeView mz = load_maze(b, m);
+    double reward = 0.0, ep_return = b.ep_return ? b.ep_return[e] : 0.0;
+    int term = 0, trunc = 0;
+    bool target_changed = false;
+    unsigned long long n_episodes = 0, n_wins = 0;
+    double return_sum = 0.0;
+    for (int k = 0; k < k_steps; ++k) {
+        if ((mode & MAZE_STEP_AUTORESET) && (st.flags & MAZE_ST_NEEDS_RESET)) {
+            if ((mode & MAZE_STEP_WIN_NEXT) && (st.flags & MAZE_ST_WON)) {
+                m += b.pool_stride;
+                if (m >= b.num_mazes) m -= b.num_mazes;
+                mz = load_maze(b, m);
+            }
+            bool wrapped;
+            begin_episode(st, mz.start, __ldg(mz.tab + (mz.start & 0xffff) * mz.W + (mz.start >> 16)), wrapped);
+            if (wrapped)
+                for (int i = 0; i < b.visit_slot; ++i) *VISIT_AT(b, e, i) = 0;
+            reward = 0.0; term = 0; trunc = 0;
+            ep_return = 0.0;
+            target_changed = true;
+        } else {
+            const StepResult r = env_transition(b, e, st, mz, __ldcs(actions + (size_t)k * B + e) & 3, luts);
+            reward = r.reward; term = r.term; trunc = r.trunc;
+            ep_return += reward;
+            if (term | trunc) {
+                ++n_episodes;
+                n_wins += term;
+                return_sum += ep_return;
+            }
+        }
+        const size_t at = (size_t)k * B + e;
+        if (tr.agent) __stcs(reinterpret_cast<int2*>(tr.agent) + at, make_int2(st.r, st.c));
+        if (tr.best_dir)
+            __stcs(reinterpret_cast<int2*>(tr.best_dir) + at,
+                   best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, mz.H, mz.W, mz.tor));
+        if (tr.reward) __stcs(tr.reward + at, reward);
+        if (tr.terminated) __stcs(tr.terminated + at, (uint8_t)term);
+        if (tr.truncated) __stcs(tr.truncated + at, (uint8_t)trunc);
+    }
+    b.state[e] = pack_state(st);
+    b.env_maze[e] = m;
+    reinterpret_cast<int2*>(b.agent)[e] = make_int2(st.r, st.c);
+    if (target_changed) reinterpret_cast<int2*>(b.target)[e] = make_int2(mz.goal & 0xffff, mz.goal >> 16);
+    reinterpret_cast<int2*>(b.best_dir)[e] = best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, mz.H, mz.W, mz.tor);
+    b.reward[e] = reward;
+    b.terminated[e] = (uint8_t)term;
+    b.truncated[e] = (uint8_t)trunc;
+    if (b.ep_return) b.ep_return[e] = ep_return;
+    if (n_episodes) {
+        if (b.stats) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 0), n_episodes);
+            if (n_wins) atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 1), n_wins);
+            if (n_episodes - n_wins) atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 2), n_episodes - n_wins);
+        }
+        if (b.ep_return && b.stats_return) atomicAdd(b.stats_return, return_sum);
+    }
+}
+
 }  // namespace
+
+extern "C" int maze_step_many(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* actions, int k_steps, uint32_t mode,
+                              const maze_step_trace* trace, int chunk_envs, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = maze_check_batch(ctx, b)) return rc;
+    if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_step_many: actions");
+    if (k_steps < 1 || chunk_envs < 0) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_step_many: k_steps / chunk_envs");
+    if (mode & MAZE_STEP_WIN_QUEUE)
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_step_many: MAZE_STEP_WIN_QUEUE needs a generation launch between steps; use maze_step");
+    maze_step_trace tr = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (trace) tr = *trace;
+    if (((uintptr_t)tr.agent & 7) || ((uintptr_t)tr.best_dir & 7) || ((uintptr_t)tr.reward & 7))
+        return maze_fail_arg(ctx, MAZE_E_ALIGN, "maze_step_many: trace pointer alignment");
+    // measured on B200 (tools/perf_step_many.py): one launch over all envs beats L2-sized chunks (the
+    // locality that matters is each thread re-touching its own sectors within the burst), so chunking
+    // is opt-in
+    const int chunk = chunk_envs > 0 ? chunk_envs : b->num_envs;
+    const StepLuts luts = step_luts(ctx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int e0 = 0; e0 < b->num_envs; e0 += chunk) {
+        const int e1 = e0 + chunk < b->num_envs ? e0 + chunk : b->num_envs;
+        maze_step_many_kernel<<<(e1 - e0 + STEP_THREADS - 1) / STEP_THREADS, STEP_THREADS, 0, st>>>(*b, actions, k_steps, mode, luts, tr, e0, e1);
+    }
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* actions, uint32_t mode, void* stream) {
     if (!ctx) return MAZE_E_NULL;

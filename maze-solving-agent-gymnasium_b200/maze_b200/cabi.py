@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -59,6 +59,11 @@ Q_EMPTY = 0xffffffffffffffff
 Q_NO_SLOT = 0xffffffff
 
 
+class MazeStepTrace(C.Structure):
+    _fields_ = [("agent", C.c_void_p), ("best_dir", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
+                ("truncated", C.c_void_p)]
+
+
 class MazeError(RuntimeError):
     pass
 
@@ -74,6 +79,8 @@ SIGNATURES = {
     "maze_reward_lut": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "maze_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "maze_step": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_uint32, C.c_void_p]),
+    "maze_step_many": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_int, C.c_uint32, C.POINTER(MazeStepTrace),
+                                 C.c_int, C.c_void_p]),
     "maze_reset": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p]),
     "maze_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),

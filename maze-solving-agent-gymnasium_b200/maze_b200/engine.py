@@ -266,6 +266,26 @@ class MazeBatch:
                                   cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_step")
 
+    def step_many(self, actions: torch.Tensor, mode: int = 0, trace: bool = False, chunk_envs: int = 0):
+        """K consecutive transitions for action sequences known in advance: actions uint8 [K, B] on the
+        device.  Bit-identical to K step() calls; with trace=True returns the per-step outputs
+        dict(agent [K,B,2], best_dir [K,B,2], reward [K,B], terminated [K,B], truncated [K,B])."""
+        if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        K = actions.shape[0]
+        assert actions.shape == (K, self.num_envs)
+        out, tr = None, None
+        if trace:
+            d, B = self.device, self.num_envs
+            out = dict(agent=torch.empty((K, B, 2), dtype=torch.int32, device=d), best_dir=torch.empty((K, B, 2), dtype=torch.int32, device=d),
+                       reward=torch.empty((K, B), dtype=torch.float64, device=d), terminated=torch.empty((K, B), dtype=torch.uint8, device=d),
+                       truncated=torch.empty((K, B), dtype=torch.uint8, device=d))
+            tr = cabi.MazeStepTrace(**{k: v.data_ptr() for k, v in out.items()})
+        rc = cabi.lib().maze_step_many(self.ctx.handle, C.byref(self._c), cabi.ptr(actions), int(K), int(mode),
+                                       C.byref(tr) if tr is not None else None, int(chunk_envs), cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_step_many")
+        return out
+
     def compute_window(self):
         """Enriched observation of the current positions: fills self.window [B,3,15,15] float32 and
         self.agent_norm / self.target_norm [B,2] float64 (agent / maze_shape, target / maze_shape)."""

@@ -68,14 +68,16 @@ class MazeVectorEnv(_VectorBase):
                  num_mazes: Optional[int] = None, device="cuda", seed: int = 0, autoreset: bool = True,
                  on_win: str = "keep", reference_order: bool = False, stats: bool = True,
                  slot_id_base: int = 0, pool: Optional[MazePool] = None, env_maze=None, enrich: bool = False,
-                 candidates: int = 1, start_shape=None, grow: int = 0, algorithm_schedule=None):
+                 candidates: int = 1, start_shape=None, grow: int = 0, algorithm_schedule=None, visit_layout=None):
         """enrich=True gives the -v1 observation (normalised agent / target, 15x15 window);
         candidates=6 makes every generated maze the least difficult of six (generate_maze).
         Curriculum (on_win="regenerate"): `shape` is the maximum block shape; mazes start at
         `start_shape` (one shape or one per maze) and grow by `grow` blocks per win
         (variable-size envs: START_SHAPE and +(4, 4), simple_variable_maze_env.py:17,97);
         `algorithm_schedule` = ((wins, algorithm), ...) switches a slot's generator by its win count
-        (off_policy_trainer.py:302-310: ((5, "prim&kill"), (10, "dfs")))."""
+        (off_policy_trainer.py:302-310: ((5, "prim&kill"), (10, "dfs"))).
+        visit_layout: "cell" (default; best for one launch per step), "tile" (best for the fused
+        multi-step paths: step_many, the Q-learning rollout), "env" (default with enrich)."""
         if topology not in ("euclid", "toroidal"):
             raise ValueError("topology must be 'euclid' or 'toroidal'")
         if on_win not in ("keep", "next", "regenerate"):
@@ -117,7 +119,7 @@ class MazeVectorEnv(_VectorBase):
             per = max(1, self.num_envs // pool.num_mazes)
             env_maze = (torch.arange(self.num_envs, device=self.device, dtype=torch.int32) // per).clamp_(max=pool.num_mazes - 1)
         self.batch = MazeBatch(pool, self.num_envs, env_maze=env_maze, stats=stats, queue=(on_win == "regenerate"),
-                               visit_layout="env" if self.enrich else "cell")
+                               visit_layout=visit_layout or ("env" if self.enrich else "cell"))
         self._mode = ((cabi.STEP_AUTORESET if self.autoreset else 0)
                       | (cabi.STEP_WIN_NEXT if on_win == "next" else 0)
                       | (cabi.STEP_WIN_QUEUE if on_win == "regenerate" else 0))
@@ -145,6 +147,14 @@ class MazeVectorEnv(_VectorBase):
             b.compute_window()
             return {"agent": b.agent_norm, "target": b.target_norm, "best dir": b.best_dir, "window": b.window}
         return {"agent": b.agent, "target": b.target, "best dir": b.best_dir}
+
+    def step_many(self, actions, trace: bool = True):
+        """K consecutive steps for an action tape known in advance (uint8 [K, B] device tensor): the same
+        transitions as K step() calls, one launch.  Returns the per-step outputs (see MazeBatch.step_many).
+        Not available with on_win='regenerate'."""
+        if self.on_win == "regenerate":
+            raise cabi.MazeError("step_many cannot regenerate mazes between its fused steps")
+        return self.batch.step_many(actions, self._mode, trace=trace)
 
     def get_mask_direction(self, probs: bool = False):
         """float32 [B, 4] direction mask of every env (env.get_mask_direction of the reference)."""

@@ -170,3 +170,38 @@ def test_argument_errors_are_reported():
         mb.MazePool(2, (20, 21))
     with pytest.raises(mb.cabi.MazeError):
         mb.MazePool(2, (21, 21), device="cpu")
+
+
+@pytest.mark.parametrize("visit_layout", ["cell", "tile"])
+@pytest.mark.parametrize("chunk", [0, 100])
+def test_step_many_equals_repeated_steps(visit_layout, chunk):
+    """maze_step_many over a K-step action tape == K maze_step calls: per-step trace, final state,
+    visit counters, episode statistics (autoreset + pool cycling on)."""
+    mb = _engine()
+    mazes = _collect_golden_mazes()
+    M = len(mazes)
+    pool = mb.MazePool.from_grids([m["grid"] for m in mazes], [m["start"] for m in mazes],
+                                  [m["goal"] for m in mazes], [m["toroidal"] for m in mazes])
+    B, K = 5 * M + 3, 96
+    env_maze = torch.from_numpy((np.arange(B) % M).astype(np.int32)).cuda()
+    mode = mb.cabi.STEP_AUTORESET | mb.cabi.STEP_WIN_NEXT
+    rng = np.random.default_rng(3)
+    acts = torch.from_numpy(rng.integers(0, 4, (3 * K, B)).astype(np.uint8)).cuda()
+    one = mb.MazeBatch(pool, B, env_maze=env_maze.clone(), stats=True, pool_stride=5, visit_layout=visit_layout)
+    many = mb.MazeBatch(pool, B, env_maze=env_maze.clone(), stats=True, pool_stride=5, visit_layout=visit_layout)
+    one.reset(); many.reset()
+    for burst in range(3):
+        tape = acts[burst * K:(burst + 1) * K]
+        ref = {k: [] for k in ("agent", "best_dir", "reward", "terminated", "truncated")}
+        for t in range(K):
+            one.step(tape[t], mode)
+            for k in ref:
+                ref[k].append(getattr(one, k).clone())
+        tr = many.step_many(tape, mode, trace=True, chunk_envs=chunk)
+        for k in ref:
+            assert torch.equal(tr[k], torch.stack(ref[k])), (burst, k)
+        for k in ("state", "env_maze", "agent", "target", "best_dir", "reward", "terminated", "truncated", "visits", "ep_return", "stats"):
+            assert torch.equal(getattr(many, k), getattr(one, k)), (burst, k)
+        assert abs(float(many.stats_return.item()) - float(one.stats_return.item())) < 1e-6
+    assert int(one.stats[0].item()) > 0
+    assert many.step_many(acts[:4], mode) is None          # no trace: only the final outputs
