@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 8
+#define MAZE_ABI_VERSION 9
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -343,6 +343,54 @@ int maze_dqn_select(maze_ctx* ctx, const maze_env_batch* b, const float* q_value
 #define MAZE_METRIC_DE_COUNT   6  /* dead ends counted by calculate_DE                         */
 int maze_difficulty(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids,
                     int n, int slot, int max_h, int max_w, double* out, void* stream);
+
+/* maze_difficulty plus the Kim-Crawfis metrics MetricsCalculator defines but nothing in the
+ * reference calls (lib/maze_difficulty_evaluation/metrics_calculator.py): one extra record of
+ * MAZE_METRIC_EXT_WORDS doubles per processed slot in ext_out.  All are bit-identical to the
+ * reference (same divisions; the dead-end sums run in its row-major dead-end order).
+ *   density :18-20; T :28-37, J :39-53, CR :55-69 of the solution path;
+ *   AC, FDE, BDE = the three terms of DE (calculate_DE_sub :100-127);
+ *   L_DE :224-241; T_DE / D_sharp / L_sharp :175-222 for dead-end types AC, FDE, BDE (3 words each).
+ * find_decision (:243-255) iterates an empty range and always returns None; L_DE and L_sharp are
+ * therefore plain sums of len(de_path) / CE, which is what is computed here. */
+#define MAZE_METRIC_EXT_WORDS   20
+#define MAZE_METRIC_EXT_DENSITY 0
+#define MAZE_METRIC_EXT_T       1
+#define MAZE_METRIC_EXT_J       2
+#define MAZE_METRIC_EXT_CR      3
+#define MAZE_METRIC_EXT_AC      4
+#define MAZE_METRIC_EXT_FDE     5
+#define MAZE_METRIC_EXT_BDE     6
+#define MAZE_METRIC_EXT_L_DE    7
+#define MAZE_METRIC_EXT_T_DE    8   /* [3]: AC, FDE, BDE */
+#define MAZE_METRIC_EXT_D_SHARP 11  /* [3] */
+#define MAZE_METRIC_EXT_L_SHARP 14  /* [3] */
+int maze_difficulty_ext(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids,
+                        int n, int slot, int max_h, int max_w, double* out, double* ext_out, void* stream);
+
+/* ---- packed maze sets (wire / on-disk interchange) -------------------
+ * Record k of `packed` (packed_stride bytes) belongs to slot ids[k] (slot k when ids is NULL); H, W,
+ * goal and flags of a slot come from its meta record, which the caller fills before maze_unpack
+ * (then maze_fields rebuilds the step table).  The reference has no such format (its mazes are Python
+ * lists of lists, lib/maze_generation.py:17); the file layout built on it is documented in
+ * maze_b200/mazeset.py.
+ *   MAZE_PACK_BITMAP  1 bit per block (open != 0), row-major, LSB first, (H*W + 7) / 8 bytes:
+ *                     lossless for every grid, both topologies
+ *   MAZE_PACK_WALLS   4 wall bits per logical cell (N 1, E 2, S 4, W 8; set = wall), two cells per
+ *                     byte, low nibble first, (cells + 1) / 2 bytes: bordered (euclidean) mazes whose
+ *                     logical cells are all open, i.e. every generator output (800 B for 40 x 40) */
+#define MAZE_PACK_BITMAP 0
+#define MAZE_PACK_WALLS  1
+int maze_pack(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids, int n, int slot,
+              int format, uint8_t* packed, int packed_stride, void* stream);
+int maze_unpack(maze_ctx* ctx, const uint8_t* packed, int packed_stride, int format, uint8_t* grids,
+                const int32_t* meta, const int32_t* ids, int n, int slot, void* stream);
+
+/* generate_collection_of_mazes' tensor encode (lib/maze_generation.py:236-242): out int32 [n, 3, h, w]
+ * = [wall (== 0), tile (== 1, the goal is neither), non_visited (!= 0, start cleared)] of n slots of
+ * one shape. */
+int maze_collection_encode(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids, int n,
+                           int slot, int h, int w, int32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

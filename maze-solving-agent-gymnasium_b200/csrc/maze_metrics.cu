@@ -19,7 +19,7 @@ namespace {
 __global__ void __launch_bounds__(FIELD_THREADS)
 maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restrict__ meta,
                        const int32_t* __restrict__ ids, int n, int slot, int smem_hw, int smem_cells,
-                       double* __restrict__ out) {
+                       double* __restrict__ out, double* __restrict__ ext_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ MazeMetrics s_out;
     const int tid = threadIdx.x;
@@ -60,7 +60,8 @@ maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restr
             block_bfs(f, Hb, Wb, false, start_idx);
         }
         MET_TICK(0);
-        maze_metrics(f, ms, Hb, Wb, start_idx, goal_idx, s_out);
+        maze_metrics(f, ms, Hb, Wb, start_idx, goal_idx, s_out, true, ext_out != nullptr);
+        if (ext_out && tid < MAZE_METRIC_EXT_WORDS) ext_out[(size_t)item * MAZE_METRIC_EXT_WORDS + tid] = s_out.ext[tid];
         if (tid == 0) {
             double* o = out + (size_t)item * MAZE_METRIC_WORDS;
             o[MAZE_METRIC_DIFFICULTY] = s_out.difficulty;
@@ -77,9 +78,8 @@ maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restr
 
 }  // namespace
 
-extern "C" int maze_difficulty(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids,
-                               int n, int slot, int max_h, int max_w, double* out, void* stream) {
-    if (!ctx) return MAZE_E_NULL;
+static int launch_difficulty(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids,
+                             int n, int slot, int max_h, int max_w, double* out, double* ext_out, void* stream) {
     if (!grids || !meta || !out) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_difficulty pointer");
     if (n <= 0 || slot <= 0) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_difficulty n / slot");
     if (max_h < 5 || max_w < 5 || !(max_h & 1) || !(max_w & 1) || max_h + 2 > MAZE_GEN_MAX_DIM || max_w + 2 > MAZE_GEN_MAX_DIM)
@@ -94,7 +94,20 @@ extern "C" int maze_difficulty(maze_ctx* ctx, const uint8_t* grids, const int32_
     if (per_sm < 1) per_sm = 1;
     const int resident = per_sm * (ctx->num_sms > 0 ? ctx->num_sms : 148);
     maze_difficulty_kernel<<<n < resident ? n : resident, FIELD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-        grids, meta, ids, n, slot, smem_hw, smem_cells, out);
+        grids, meta, ids, n, slot, smem_hw, smem_cells, out, ext_out);
     MAZE_CHECK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int maze_difficulty(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids,
+                               int n, int slot, int max_h, int max_w, double* out, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    return launch_difficulty(ctx, grids, meta, ids, n, slot, max_h, max_w, out, nullptr, stream);
+}
+
+extern "C" int maze_difficulty_ext(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids,
+                                   int n, int slot, int max_h, int max_w, double* out, double* ext_out, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (!ext_out) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_difficulty_ext: ext_out");
+    return launch_difficulty(ctx, grids, meta, ids, n, slot, max_h, max_w, out, ext_out, stream);
 }

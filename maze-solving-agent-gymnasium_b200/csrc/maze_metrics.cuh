@@ -73,14 +73,17 @@ static __device__ unsigned long long g_met_prof[12];
 struct MazeMetrics {
     double difficulty, complexity, L, DE, D;
     int sol_len, de_count;
+    double ext[MAZE_METRIC_EXT_WORDS];   // filled when maze_metrics(..., ext = true); see include/maze_b200.h
 };
 
 // All threads of the CTA call this; the result is valid on thread 0.
 // with_kc = false skips the (sequential) Kim-Crawfis DE pass: DE / de_count are then 0.
+// ext = true (needs with_kc) also fills out.ext with the metrics the reference defines but never calls
+// (metrics_calculator.py:18-69,175-244), bit-identical: same divisions, sums in row-major dead-end order.
 __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, int Hb, int Wb,
-                                    int start_idx, int goal_idx, MazeMetrics& out, bool with_kc = true) {
+                                    int start_idx, int goal_idx, MazeMetrics& out, bool with_kc = true, bool ext = false) {
     __shared__ double s_D0, s_S0, s_red[2][FIELD_THREADS / 32];
-    __shared__ int s_dcount;
+    __shared__ int s_dcount, s_sol_counts[3], s_open;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2, cells = nr * nc;
     auto cell_block = [&](int ci) { return (2 * (ci / nc) + 1) * Wb + 2 * (ci % nc) + 1; };
@@ -92,6 +95,8 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
             out.difficulty = out.complexity = out.L = out.DE = out.D = nan("");
             out.sol_len = 0;
             out.de_count = 0;
+            if (ext)
+                for (int i = 0; i < MAZE_METRIC_EXT_WORDS; ++i) out.ext[i] = nan("");
         }
         __syncthreads();
         return;
@@ -117,26 +122,39 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
         ms.pnode[ci] = 0xffffu;
         ms.dpar[ci] = 0;
     }
-    if (tid == 0) { s_D0 = 0.0; s_S0 = 0.0; s_dcount = 0; }
+    if (tid == 0) { s_D0 = 0.0; s_S0 = 0.0; s_dcount = 0; s_open = 0; }
     __syncthreads();
+    if (ext) {   // calculate_density :18-20
+        int open = 0;
+        for (int i = tid; i < Hb * Wb; i += nthr) open += f.grid[i] != 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) open += __shfl_xor_sync(0xffffffffu, open, o);
+        if ((tid & 31) == 0) atomicAdd(&s_open, open);
+    }
 
     MET_TICK(1);
     // ---- 2. mark the solution (goal -> start along BFS parents); D = decision cells on it
     if (tid == 0) {
-        int b = goal_idx, dcount = 0;
+        int b = goal_idx, dcount = 0, junctions = 0, crossings = 0, turns = 0, arrived = 0;
         for (;;) {
             const int ci = block_cell(b);
             ms.flags[ci] |= MF_SOL;
-            if ((ms.flags[ci] & MF_NB) > 2) ++dcount;   // metrics_calculator.py:71-85 (only cells can have > 2)
+            const int nbc = ms.flags[ci] & MF_NB;
+            if (nbc > 2) ++dcount;   // metrics_calculator.py:71-85 (only cells can have > 2)
+            junctions += nbc == 3;   // calculate_J :39-53
+            crossings += nbc == 4;   // calculate_CR :55-69
             if (b == start_idx) break;
             const int d = f.dist[b];
             int step = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (f.grid[b + offs[k]] != 0 && (int)f.dist[b + offs[k]] == d - 1) step = offs[k];
+            if (arrived != 0 && arrived != step) ++turns;   // calculate_T :28-37 (interior blocks only; passages are straight)
+            arrived = step;
             b += 2 * step;   // passage block, then the next cell
         }
         s_dcount = dcount;
+        s_sol_counts[0] = turns; s_sol_counts[1] = junctions; s_sol_counts[2] = crossings;
     }
     __syncthreads();
 
@@ -177,6 +195,8 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
     //   4c  thread 0: walk only the chain of decision points above each dead end, stop at the first
     //       recorded one
     int alcoves = 0, forward = 0, backward = 0;
+    double x_lde = 0.0, x_t[3] = {0.0, 0.0, 0.0}, x_d[3] = {0.0, 0.0, 0.0}, x_l[3] = {0.0, 0.0, 0.0};
+    const double ce_d = (double)((Hb - 1) * ((Wb - 1) / 2) - 1);   // metrics_calculator.py:16
     if (with_kc) {
         unsigned short* jup = ms.minleaf;
         unsigned short* kind = ms.comp;
@@ -199,9 +219,10 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
             const bool cut = j <= sol_len - 2;
             // interior nodes: strictly above the dead end, up to (cut) the node below A or (uncut) the node below start
             bool has_turn = false;
-            int prev = de, below_a = de;
+            int prev = de, below_a = de, n_turns = 0, n_dp = 0;
             for (int y = ms.pnode[de]; cut ? (y != a) : (y != start_c); y = ms.pnode[y]) {
-                if (dcode(prev) != dcode(y)) has_turn = true;
+                if (dcode(prev) != dcode(y)) { has_turn = true; ++n_turns; }
+                n_dp += (ms.flags[y] & MF_NB) > 2;
                 if (!is_sol(y)) below_a = y;
                 prev = y;
             }
@@ -222,6 +243,12 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
                 k = diff > 0 ? 1 : 2;
             }
             kind[de] = (unsigned short)(k | (cut ? 4 : 0));
+            if (ext) {   // per dead end terms of T_DE :175-185, D_sharp :187-197, L_sharp / L_DE :199-241
+                if (!cut && (ms.flags[start_c] & MF_NB) > 2) ++n_dp;   // an uncut path ends on start itself
+                ms.dsum[de] = (unsigned)len;
+                ms.ssum[de] = __ddiv_rn(__ddiv_rn((double)n_turns, (double)sol_len), (double)len);
+                ms.bsum[de] = __ddiv_rn(__ddiv_rn((double)n_dp, (double)sol_len), (double)len);
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -229,6 +256,13 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
                 if (!is_dead_end_off(de)) continue;
                 const int kd = kind[de];
                 const bool cut = (kd & 4) != 0;
+                if (ext) {   // sums over ALL off-solution dead ends, in this (row-major) order
+                    const double l = __ddiv_rn((double)ms.dsum[de], ce_d);
+                    x_lde = __dadd_rn(x_lde, l);
+                    x_l[kd & 3] = __dadd_rn(x_l[kd & 3], l);
+                    x_t[kd & 3] = __dadd_rn(x_t[kd & 3], ms.ssum[de]);
+                    x_d[kd & 3] = __dadd_rn(x_d[kd & 3], ms.bsum[de]);
+                }
                 bool blocked = false;
                 int first_dp = -1;
                 for (int y = jup[de]; y != 0xffff && (cut ? !is_sol(y) : y != start_c); y = jup[y]) {
@@ -241,7 +275,10 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
             }
         }
         __syncthreads();
-        for (int ci = tid; ci < cells; ci += nthr) { ms.minleaf[ci] = 0xffffu; ms.comp[ci] = 0xffffu; }   // scratch back to its initial state
+        for (int ci = tid; ci < cells; ci += nthr) {   // scratch back to its initial state
+            ms.minleaf[ci] = 0xffffu; ms.comp[ci] = 0xffffu;
+            if (ext) { ms.dsum[ci] = 0u; ms.ssum[ci] = 0.0; ms.bsum[ci] = 0.0; }
+        }
         __syncthreads();
     }
 
@@ -335,6 +372,23 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
                            __ddiv_rn((double)backward, (double)sol_len));   // AC + FDE + BDE, :97-98
         out.sol_len = sol_len;
         out.de_count = alcoves + forward + backward;
+        if (ext) {
+            const double sl = (double)sol_len;
+            out.ext[MAZE_METRIC_EXT_DENSITY] = __ddiv_rn((double)s_open, (double)(Hb * Wb));
+            out.ext[MAZE_METRIC_EXT_T] = __ddiv_rn((double)s_sol_counts[0], sl);
+            out.ext[MAZE_METRIC_EXT_J] = __ddiv_rn((double)s_sol_counts[1], sl);
+            out.ext[MAZE_METRIC_EXT_CR] = __ddiv_rn((double)s_sol_counts[2], sl);
+            out.ext[MAZE_METRIC_EXT_AC] = __ddiv_rn((double)alcoves, sl);
+            out.ext[MAZE_METRIC_EXT_FDE] = __ddiv_rn((double)forward, sl);
+            out.ext[MAZE_METRIC_EXT_BDE] = __ddiv_rn((double)backward, sl);
+            out.ext[MAZE_METRIC_EXT_L_DE] = x_lde;
+            for (int k = 0; k < 3; ++k) {
+                out.ext[MAZE_METRIC_EXT_T_DE + k] = x_t[k];
+                out.ext[MAZE_METRIC_EXT_D_SHARP + k] = x_d[k];
+                out.ext[MAZE_METRIC_EXT_L_SHARP + k] = x_l[k];
+            }
+            for (int k = MAZE_METRIC_EXT_L_SHARP + 3; k < MAZE_METRIC_EXT_WORDS; ++k) out.ext[k] = 0.0;
+        }
     }
     __syncthreads();
 }

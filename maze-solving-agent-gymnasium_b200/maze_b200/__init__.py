@@ -4,6 +4,7 @@ loudly when the library has not been built, and every compute entry point needs 
 """
 from . import cabi, dist  # noqa: F401
 from .engine import ALGO_IDS, MazeBatch, MazePool  # noqa: F401
+from . import mazeset  # noqa: F401
 from .vector_env import MazeVectorEnv  # noqa: F401
 
-__all__ = ["cabi", "dist", "MazePool", "MazeBatch", "MazeVectorEnv", "ALGO_IDS"]
+__all__ = ["cabi", "dist", "mazeset", "MazePool", "MazeBatch", "MazeVectorEnv", "ALGO_IDS"]

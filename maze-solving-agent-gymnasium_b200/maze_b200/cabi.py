@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -19,6 +19,10 @@ ALGO_RPRIM, ALGO_DFS, ALGO_PRIMKILL = 0, 1, 2
 MAX_DIM, GEN_MAX_DIM, WINDOW = 255, 131, 15
 METRIC_WORDS = 8
 METRIC_NAMES = ("difficulty", "complexity", "L", "DE", "D", "sol_len", "de_count")
+PACK_BITMAP, PACK_WALLS = 0, 1
+METRIC_EXT_WORDS = 20
+METRIC_EXT_NAMES = ("density", "T", "J", "CR", "AC", "FDE", "BDE", "L_DE", "T_DE_AC", "T_DE_FDE", "T_DE_BDE",
+                    "D_sharp_AC", "D_sharp_FDE", "D_sharp_BDE", "L_sharp_AC", "L_sharp_FDE", "L_sharp_BDE")
 E_NULL, E_RANGE, E_SHAPE, E_ALGO, E_ALIGN = -1, -2, -3, -4, -5
 
 
@@ -98,6 +102,14 @@ SIGNATURES = {
                                   C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "maze_difficulty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
+    "maze_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                            C.c_void_p]),
+    "maze_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p]),
+    "maze_collection_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p]),
+    "maze_difficulty_ext": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

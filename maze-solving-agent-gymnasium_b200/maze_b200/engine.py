@@ -161,15 +161,25 @@ class MazePool:
                                         int(wb), code(ab), cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_curriculum")
 
-    def difficulty(self, ids=None) -> torch.Tensor:
+    def difficulty(self, ids=None, extended: bool = False):
         """float64 [n, 8] metric records (cabi.METRIC_NAMES) of the given slots (all if None):
-        McClendon difficulty / complexity, Kim-Crawfis L / DE / D, solution length, dead-end count."""
+        McClendon difficulty / complexity, Kim-Crawfis L / DE / D, solution length, dead-end count.
+        extended=True returns (records, ext) with ext float64 [n, 20] (cabi.METRIC_EXT_NAMES): the
+        Kim-Crawfis metrics nothing in the reference calls (density, T, J, CR, AC / FDE / BDE, L_DE and the
+        per-type T_DE / D_sharp / L_sharp sums)."""
         if ids is None:
             ids_t, n = None, self.num_mazes
         else:
             ids_t = torch.as_tensor(ids, dtype=torch.int32, device=self.device).contiguous()
             n = ids_t.numel()
         out = torch.empty((n, cabi.METRIC_WORDS), dtype=torch.float64, device=self.device)
+        if extended:
+            ext = torch.empty((n, cabi.METRIC_EXT_WORDS), dtype=torch.float64, device=self.device)
+            rc = cabi.lib().maze_difficulty_ext(self.ctx.handle, cabi.ptr(self.grids), cabi.ptr(self.meta), cabi.ptr(ids_t), n,
+                                                self.slot, self.max_shape[0], self.max_shape[1], cabi.ptr(out), cabi.ptr(ext),
+                                                cabi.current_stream(self.device))
+            self.ctx.check(rc, "maze_difficulty_ext")
+            return out, ext
         rc = cabi.lib().maze_difficulty(self.ctx.handle, cabi.ptr(self.grids), cabi.ptr(self.meta), cabi.ptr(ids_t), n,
                                         self.slot, self.max_shape[0], self.max_shape[1], cabi.ptr(out),
                                         cabi.current_stream(self.device))

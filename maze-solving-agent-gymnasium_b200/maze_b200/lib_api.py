@@ -67,13 +67,8 @@ def generate_collection_of_mazes(shape, num_mazes: int, algorithms=("dfs", "r-pr
         algos = [random.choice(list(algorithms)) for _ in range(need)]
         pool = MazePool(need, tuple(shape), _DEVICE)
         pool.generate(shapes=tuple(shape), algorithms=algos, seed=random.getrandbits(62))
-        H, W = int(shape[0]), int(shape[1])
-        grids = pool.grids[:, :H * W].reshape(need, H, W)
-        meta = pool.meta_host()
-        stack = torch.stack([(grids == 0), (grids == 1), (grids != 0)], dim=1).to(torch.int32)
-        for k in range(need):
-            sr, sc = _unpack(meta[k, cabi.META_START])
-            stack[k, 2, sr, sc] = 0
+        from .mazeset import collection_tensor
+        stack = collection_tensor(pool)     # maze_collection_encode kernel
         host = stack.cpu()
         for k in range(need):
             key = host[k].numpy().tobytes()
@@ -83,10 +78,11 @@ def generate_collection_of_mazes(shape, num_mazes: int, algorithms=("dfs", "r-pr
     return out
 
 
-def maze_metrics(mazes, starts, goals, toroidal=False, device=None) -> torch.Tensor:
-    """Batched metrics: float64 [n, 8] records (cabi.METRIC_NAMES) for host block grids."""
+def maze_metrics(mazes, starts, goals, toroidal=False, device=None, extended: bool = False):
+    """Batched metrics: float64 [n, 8] records (cabi.METRIC_NAMES) for host block grids; with
+    extended=True also the [n, 20] records of cabi.METRIC_EXT_NAMES (MazePool.difficulty)."""
     pool = MazePool.from_grids([np.asarray(m, dtype=np.uint8) for m in mazes], starts, goals, toroidal, device or _DEVICE)
-    return pool.difficulty()
+    return pool.difficulty(extended=extended)
 
 
 def _goal_of(maze):
@@ -112,8 +108,11 @@ class ComplexityEvaluation:
 
 
 class MetricsCalculator:
-    """Kim & Crawfis L / D / DE (metrics_calculator.py:3-173).  The path arguments keep the reference's
-    signatures; only their first block (the start) and the maze's goal are needed."""
+    """Kim & Crawfis metrics (metrics_calculator.py:3-255).  The path arguments keep the reference's
+    signatures and mean the solution path: only its first block (the start) and the maze's goal are
+    needed, the kernel walks the tree itself.  `type` is "AC", "FDE" or "BDE"."""
+
+    _TYPES = {"AC": 0, "FDE": 1, "BDE": 2}
 
     def __init__(self, maze, sol_path_length: int):
         self.maze = maze
@@ -121,13 +120,54 @@ class MetricsCalculator:
         self.maze_size = (len(maze), len(maze[0]))
         self.goal = _goal_of(maze)
         self.CE = (self.maze_size[0] - 1) * ((self.maze_size[1] - 1) // 2) - 1
-        self._rec = {}
+        self._rec, self._ext = {}, {}
 
     def _record(self, path):
         start = (int(path[0][0]), int(path[0][1]))
         if start not in self._rec:
-            self._rec[start] = maze_metrics([self.maze], [start], [self.goal])[0].cpu().numpy()
+            rec, ext = maze_metrics([self.maze], [start], [self.goal], extended=True)
+            self._rec[start] = rec[0].cpu().numpy()
+            self._ext[start] = ext[0].cpu().numpy()
         return self._rec[start]
+
+    def _extended(self, path):
+        self._record(path)
+        return self._ext[(int(path[0][0]), int(path[0][1]))]
+
+    def _typed(self, path, type, base):
+        if type not in self._TYPES:
+            return 0     # the reference compares strings: an unknown type matches no dead end
+        return float(self._extended(path)[base + self._TYPES[type]])
+
+    def calculate_density(self):
+        # needs no path: score from any open cell (the record's density does not depend on the start)
+        rc = np.argwhere(np.asarray(self.maze) == 1)
+        return float(self._extended([tuple(rc[0])])[0])
+
+    def calculate_T(self, path):
+        return float(self._extended(path)[1])
+
+    def calculate_J(self, path):
+        return float(self._extended(path)[2])
+
+    def calculate_CR(self, path):
+        return float(self._extended(path)[3])
+
+    def calculate_DE_sub(self, path):
+        e = self._extended(path)
+        return float(e[4]), float(e[5]), float(e[6])
+
+    def calculate_L_DE(self, path):
+        return float(self._extended(path)[7])
+
+    def calculate_T_DE(self, path, type):
+        return self._typed(path, type, 8)
+
+    def calculate_D_sharp(self, path, type):
+        return self._typed(path, type, 11)
+
+    def calculate_L_sharp(self, path, type):
+        return self._typed(path, type, 14)
 
     def calculate_L(self, path):
         return len(path) / self.CE

@@ -16,6 +16,8 @@ Modules
   env_port.py    PortEnv: step/reset exactly as the reference computes them (A* per step);
                  ClosedFormEnv: the O(1) table-driven restatement the kernels implement
   generation.py  r-prim / dfs / prim&kill generators + goal selection + validity checks
-  metrics.py     McClendon difficulty/complexity and Kim-Crawfis L / D / DE
+  metrics.py     McClendon difficulty/complexity, Kim-Crawfis L / D / DE and the unused
+                 Kim-Crawfis metrics (density, T, J, CR, AC/FDE/BDE, L_DE, *_sharp)
   qlearn.py      tabular Q / double-Q update rules
+  mazeset.py     packed maze-set records (.mzs files) and the auto-encoder channel encode
 """

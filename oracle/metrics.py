@@ -239,3 +239,58 @@ def kim_crawfis(grid, start, goal):
     DE = alcoves / sol_len + forward / sol_len + backward / sol_len      # :97-98, summed in this order
     return dict(L=L, D=D, DE=DE, sol_len=sol_len, dead_end_count=alcoves + forward + backward,
                 alcoves=alcoves, forward=forward, backward=backward)
+
+
+DE_TYPES = ("AC", "FDE", "BDE")
+
+
+def kim_crawfis_extended(grid, start, goal):
+    """The MetricsCalculator methods the reference defines but never calls
+    (metrics_calculator.py:18-69,175-244), restated on the spanning tree:
+
+      density :18-20   open blocks / (H * W)
+      T :28-37  J :39-53  CR :55-69   turns / 3-neighbour / 4-neighbour blocks of the solution over len(sol)
+      AC, FDE, BDE :100-127           the three terms of DE
+      L_DE :224-241                   sum over ALL off-solution dead ends of len(de_path) / CE
+      T_DE(type) :175-185             sum over dead ends of that type of (turns(de_path) / len(sol)) / len(de_path)
+      D_sharp(type) :187-197          same with the > 2-neighbour blocks of de_path (end points included)
+      L_sharp(type) :199-222          sum over dead ends of that type of len(de_path) / CE
+
+    `find_decision` (:243-255) iterates `range(1, len(path) - 1, -1)`, which is empty for every path
+    of two or more blocks, so it always returns None: L_DE and L_sharp never shorten a path and never
+    record a decision point.  Sums run in row-major dead-end order with the reference's operations,
+    so the values are bit-identical, not just close."""
+    t = _Tree(grid, start, goal)
+    sol, sol_len = t.sol, len(t.sol)
+    ce = (t.H - 1) * ((t.W - 1) // 2) - 1
+    gr, gc = t.goal
+
+    def turns(path):
+        return sum(1 for i in range(1, len(path) - 1)
+                   if path[i - 1][0] != path[i + 1][0] and path[i - 1][1] != path[i + 1][1])
+
+    out = dict(density=int((t.g != 0).sum()) / (t.H * t.W), T=turns(sol) / sol_len,
+               J=sum(1 for b in sol if t.nb[b] == 3) / sol_len, CR=sum(1 for b in sol if t.nb[b] == 4) / sol_len)
+    base = kim_crawfis(grid, start, goal)
+    out.update(AC=base["alcoves"] / sol_len, FDE=base["forward"] / sol_len, BDE=base["backward"] / sol_len)
+    L_DE = 0
+    T_DE, D_sharp, L_sharp = [0, 0, 0], [0, 0, 0], [0, 0, 0]
+    for de in t.dead_ends_off_solution():
+        path = t.path_to_start(de)
+        for i in range(1, sol_len - 1):            # calculate_path :140-151
+            if t.on_sol[path[i]]:
+                path = path[:i]
+                break
+        n_turns = turns(path)
+        interior_dp = any(t.nb[path[k]] > 2 for k in range(1, len(path) - 1))
+        if len(path) >= 3 and (interior_dp or n_turns > 0):           # type_of_DE :153-173
+            diff = (abs(path[-1][0] - gr) + abs(path[-1][1] - gc)) - (abs(path[0][0] - gr) + abs(path[0][1] - gc))
+            k = 1 if diff > 0 else 2
+        else:
+            k = 0
+        L_DE += len(path) / ce
+        L_sharp[k] += len(path) / ce
+        T_DE[k] += (n_turns / sol_len) / len(path)
+        D_sharp[k] += (sum(1 for b in path if t.nb[b] > 2) / sol_len) / len(path)
+    out.update(L_DE=L_DE, T_DE=T_DE, D_sharp=D_sharp, L_sharp=L_sharp)
+    return out

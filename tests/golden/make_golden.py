@@ -14,6 +14,8 @@ stubbed, nothing else).  Every array stored here is an output of reference code:
   metrics.npz   gen_maze outputs with ComplexityEvaluation difficulty/complexity and
                 MetricsCalculator L / DE / D, plus hallway/branch structure sizes
   qagent.npz    QAgent / DQAgent table contents after scripted transition sequences
+  metrics_ext.npz  the MetricsCalculator methods nobody calls (density, T, J, CR, AC/FDE/BDE, L_DE,
+                T_DE / D_sharp / L_sharp per dead-end type) on the mazes of metrics.npz
 """
 from __future__ import annotations
 
@@ -337,11 +339,40 @@ def make_metric_table(out_path, n=120):
     np.savez_compressed(out_path, **out)
 
 
+EXT_TYPES = ("AC", "FDE", "BDE")
+
+
+def make_metrics_ext(out_path):
+    """The Kim-Crawfis metrics the reference defines but never calls (metrics_calculator.py:18-69,
+    175-244): density, T, J, CR, the AC / FDE / BDE split of DE, L_DE and the per-type T_DE /
+    D_sharp / L_sharp sums, computed by the unmodified MetricsCalculator on the bordered mazes of
+    metrics.npz (shape <= 61)."""
+    z = np.load(os.path.join(HERE, "metrics.npz"))
+    meta = json.loads(str(z["meta"]))
+    rows = []
+    for m in meta:
+        if m["no_border"] or m["shape"] > 61:
+            continue
+        t0 = time.time()
+        maze = z[f"m{m['id']}_grid"].astype(int).tolist()
+        sol = astar_limited_partial(maze, tuple(m["start"]), tuple(m["goal"]))
+        mc = MetricsCalculator(maze, len(sol))
+        ac, fde, bde = mc.calculate_DE_sub(sol)
+        row = dict(id=m["id"], density=mc.calculate_density(), T=mc.calculate_T(sol), J=mc.calculate_J(sol),
+                   CR=mc.calculate_CR(sol), AC=ac, FDE=fde, BDE=bde, L_DE=mc.calculate_L_DE(sol),
+                   T_DE=[mc.calculate_T_DE(sol, t) for t in EXT_TYPES],
+                   D_sharp=[mc.calculate_D_sharp(sol, t) for t in EXT_TYPES],
+                   L_sharp=[mc.calculate_L_sharp(sol, t) for t in EXT_TYPES])
+        rows.append(row)
+        print(f"metrics_ext m{m['id']} {m['algo']} {m['shape']} {time.time()-t0:.1f}s", flush=True)
+    np.savez_compressed(out_path, meta=np.array(json.dumps(rows)))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["steps", "bestdir", "metrics", "qagent", "genstats", "metric_table"]
     for w in which:
         t0 = time.time()
         {"steps": make_steps, "bestdir": make_bestdir, "metrics": make_metrics, "qagent": make_qagent,
-         "genstats": make_genstats, "metric_table": make_metric_table}[w](
+         "genstats": make_genstats, "metric_table": make_metric_table, "metrics_ext": make_metrics_ext}[w](
             os.path.join(HERE, f"{w}.npz"))
         print(f"== {w}.npz written in {time.time()-t0:.0f}s", flush=True)

@@ -117,3 +117,70 @@ def test_best_of_k_selection(algo, toroidal):
     pool1.generate(algorithms=algo, toroidal=toroidal, seed=77)
     d1 = pool1.difficulty().cpu().numpy()[:, 0]
     assert (prev_d <= d1 * (1 + 1e-12)).all() and (prev_d < d1 * (1 - 1e-9)).mean() > 0.5
+
+
+def _ext_vector(d):
+    return np.array([d["density"], d["T"], d["J"], d["CR"], d["AC"], d["FDE"], d["BDE"], d["L_DE"],
+                     *d["T_DE"], *d["D_sharp"], *d["L_sharp"]], dtype=np.float64)
+
+
+def test_extended_metrics_match_reference_bit_exactly():
+    """maze_difficulty_ext against tests/golden/metrics_ext.npz (the unmodified MetricsCalculator's
+    density / T / J / CR / DE_sub / L_DE / T_DE / D_sharp / L_sharp): identical float64 bit patterns,
+    and the base record is the one maze_difficulty writes."""
+    import json
+    import os
+    z, meta = load_golden("metrics")
+    ext_rows = json.loads(str(np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_ext.npz"))["meta"]))
+    rows = [next(m for m in meta if m["id"] == r["id"]) for r in ext_rows]
+    mb, pool = _pool_from_rows(z, rows)
+    base, ext = pool.difficulty(extended=True)
+    base, ext = base.cpu().numpy(), ext.cpu().numpy()
+    plain = pool.difficulty().cpu().numpy()
+    assert np.array_equal(base[:, 2:7], plain[:, 2:7])
+    np.testing.assert_allclose(base[:, :2], plain[:, :2], rtol=1e-12)
+    for k, r in enumerate(ext_rows):
+        want = _ext_vector(r)
+        assert np.array_equal(ext[k, :17].view(np.uint64), want.view(np.uint64)), (rows[k]["algo"], rows[k]["shape"], ext[k, :17], want)
+        assert not ext[k, 17:].any()
+
+
+@pytest.mark.parametrize("shape,toroidal", [(81, False), (129, False), (41, True)])
+def test_extended_metrics_match_oracle_on_generated_mazes(shape, toroidal):
+    import maze_b200 as mb
+    from oracle.metrics import kim_crawfis_extended
+    n = 9
+    pool = mb.MazePool(n, (shape, shape))
+    pool.generate(algorithms=list(ALGORITHMS) * 3, toroidal=toroidal, seed=77 + shape)
+    _, ext = pool.difficulty(extended=True)
+    ext = ext.cpu().numpy()
+    meta = pool.meta_host()
+    for m in range(n):
+        grid = pool.grid_host(m)
+        start = (int(meta[m, 2]) & 0xffff, int(meta[m, 2]) >> 16)
+        goal = (int(meta[m, 3]) & 0xffff, int(meta[m, 3]) >> 16)
+        if toroidal:   # scored on the zero-padded (bordered) grid
+            grid, start, goal = np.pad(grid, 1), (start[0] + 1, start[1] + 1), (goal[0] + 1, goal[1] + 1)
+        want = _ext_vector(kim_crawfis_extended(grid, start, goal))
+        assert np.array_equal(ext[m, :17].view(np.uint64), want.view(np.uint64)), (m, ext[m, :17], want)
+
+
+def test_metrics_calculator_mirror_exposes_the_unused_methods():
+    """lib.maze_difficulty_evaluation.MetricsCalculator with the reference's method names."""
+    import json
+    import os
+    from lib.maze_difficulty_evaluation.metrics_calculator import MetricsCalculator
+    z, meta = load_golden("metrics")
+    r = json.loads(str(np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_ext.npz"))["meta"]))[5]
+    m = next(x for x in meta if x["id"] == r["id"])
+    maze = z[f"m{m['id']}_grid"].astype(int).tolist()
+    mc = MetricsCalculator(maze, m["sol_len"])
+    sol = [tuple(m["start"])]   # only the first block of the solution path is consulted
+    assert mc.calculate_density() == r["density"]
+    assert mc.calculate_T(sol) == r["T"] and mc.calculate_J(sol) == r["J"] and mc.calculate_CR(sol) == r["CR"]
+    assert mc.calculate_DE_sub(sol) == (r["AC"], r["FDE"], r["BDE"])
+    assert mc.calculate_L_DE(sol) == r["L_DE"]
+    for k, t in enumerate(("AC", "FDE", "BDE")):
+        assert mc.calculate_T_DE(sol, t) == r["T_DE"][k]
+        assert mc.calculate_D_sharp(sol, t) == r["D_sharp"][k]
+        assert mc.calculate_L_sharp(sol, t) == r["L_sharp"][k]

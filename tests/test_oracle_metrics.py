@@ -51,3 +51,24 @@ def test_no_border_difficulty_is_taken_on_the_bordered_maze(golden_metrics):
         bordered = np.pad(z[f"m{m['id']}_grid"], 1)
         d, _ = mcclendon(bordered, (m["start"][0] + 1, m["start"][1] + 1), (m["goal"][0] + 1, m["goal"][1] + 1))
         assert d == pytest.approx(m["difficulty"], rel=1e-11)
+
+
+def _ext_rows():
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_ext.npz"))
+    return json.loads(str(z["meta"]))
+
+
+@pytest.mark.parametrize("row", _ext_rows(), ids=lambda r: f"m{r['id']}")
+def test_extended_kim_crawfis_metrics_match_reference(golden_metrics, row):
+    """density, T, J, CR, AC / FDE / BDE, L_DE, T_DE / D_sharp / L_sharp (metrics_calculator.py:18-69,
+    175-244) as the unmodified MetricsCalculator computes them: bit-identical (same divisions, sums in
+    the same row-major dead-end order)."""
+    from oracle.metrics import kim_crawfis_extended
+    z, meta = golden_metrics
+    m = next(x for x in meta if x["id"] == row["id"])
+    got = kim_crawfis_extended(z[f"m{m['id']}_grid"], m["start"], m["goal"])
+    for k, v in row.items():
+        if k != "id":
+            assert got[k] == v, k
