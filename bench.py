@@ -122,19 +122,26 @@ def run_reference(args, rank):
     one worker process per host core, each 'step' a bounded sample."""
     if rank != 0:
         return None
-    from oracle.baseline import time_env_steps
+    from oracle.baseline import PersistentVector
     cores = os.cpu_count() or 1
     mazes = reference_mazes(min(cores, 8))
-    per = max(0.25, min(2.0, 150.0 / max(1, args.steps + args.warmup)))
+    vec = PersistentVector(mazes, cores, "port")
+    # Size a 'step' (every worker advances its env by n transitions) so that warm-up + timed steps take about
+    # BUDGET_S in total, whatever K and W are: calibrate the per-core rate on a one-second sample first.
+    BUDGET_S = 90.0
+    cal = vec.step(64)
+    rate = 64 / cal["seconds"]                                  # transitions per second per worker
+    n = max(1, int(BUDGET_S * rate / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        time_env_steps(mazes, per, cores, "port")
+        vec.step(n)
     steps, secs = 0, 0.0
     for _ in range(args.steps):
-        r = time_env_steps(mazes, per, cores, "port")
+        r = vec.step(n)
         steps += r["steps"]; secs += r["seconds"]
+    vec.close()
     value = steps / secs
-    sample = (f"{args.steps} samples x {per:.2f} s, {cores} worker processes each stepping the oracle port (A* per step) "
-              f"of the reference env on an 81x81 r-prim maze, random actions, reset on done")
+    sample = (f"{args.steps} steps x {n} transitions x {cores} worker processes ({steps} env-steps in {secs:.1f} s), each worker "
+              f"stepping the oracle port (A* per step) of the reference env on an 81x81 r-prim maze, random actions, reset on done")
     return ({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,

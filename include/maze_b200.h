@@ -207,7 +207,8 @@ int maze_curriculum(maze_ctx* ctx, int32_t* meta, int32_t* wins, const int32_t* 
  *               15 x 15 crop around the agent: lib/maze_handler.py:4-54 (euclid: clamped into the
  *               grid, so not centred near the border), :56-80 (torus: centred, wraps), :82-99
  *   agent_norm  [B, 2] float64 = agent / maze_shape, target_norm likewise (either may be NULL)
- * Needs H, W >= 15.  Reads the step table, so the goal block must be the pool's goal (value 2). */
+ * Needs H, W >= 15.  Reads the step table, so the goal block must be the pool's goal (value 2).
+ * `window` must be 16-byte aligned (it is written with 16-byte stores). */
 int maze_window(maze_ctx* ctx, const maze_env_batch* b, float* window, double* agent_norm, double* target_norm,
                 void* stream);
 
@@ -367,6 +368,17 @@ int maze_difficulty(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, co
 #define MAZE_METRIC_EXT_L_SHARP 14  /* [3] */
 int maze_difficulty_ext(maze_ctx* ctx, const uint8_t* grids, const int32_t* meta, const int32_t* ids,
                         int n, int slot, int max_h, int max_w, double* out, double* ext_out, void* stream);
+
+/* The frame MazeViewTemplate draws (lib/maze_view.py:12-14,88-104,148-152; render_mode "rgb_array",
+ * base_maze_env.py:15,212-222) for n envs (env_ids NULL = envs 0..n-1): out uint8 [n, out_h, out_w, 3],
+ * out_h / out_w = 16 x the pool's maximum shape; 16 x 16 tiles in CELL_COLORS with a one-pixel
+ * outline, orange on blocks the agent has left in the current episode, the agent as an 8 x 8 square;
+ * pixels beyond a (smaller) maze and the window's last row / column are black.  The reference never
+ * repaints outlines on reset, so its trails accumulate over episodes on one maze; here a frame shows
+ * the current episode only (state lives in the visit counters, not in a surface). */
+#define MAZE_RENDER_TILE 16
+int maze_render(maze_ctx* ctx, const maze_env_batch* b, const int32_t* env_ids, int n, uint8_t* out,
+                int out_h, int out_w, void* stream);
 
 /* ---- packed maze sets (wire / on-disk interchange) -------------------
  * Record k of `packed` (packed_stride bytes) belongs to slot ids[k] (slot k when ids is NULL); H, W,

@@ -14,55 +14,101 @@ constexpr int OBS_THREADS = 256;
 constexpr int WIN = MAZE_WINDOW;
 constexpr int WIN_CELLS = WIN * WIN;
 
-__global__ void __launch_bounds__(OBS_THREADS)
+// A CTA of 8 warps serves 8 consecutive envs.  Each warp gathers its env's 225 window blocks and writes
+// one byte (0 / 1) per output float into shared memory, laid out exactly like the output; then all 256
+// threads stream the 8 x 2 700 bytes out as 16-byte stores, four shared bytes -> one float4 (8 envs x
+// 675 floats start on a 16-byte boundary; one env's 2 700 bytes do not).  ncu of the first version
+// (one 4-byte store per value, div / mod per block): 1 080 warp instructions per env, 77 % issue-slot
+// busy, table rows missing L2 behind the streamed output -- hence the incremental indexing, the byte
+// staging and the evict_last policy on the table loads below.
+constexpr int WIN_ENVS = OBS_THREADS / 32;
+constexpr int WIN_FLOATS = 3 * WIN_CELLS;
+
+#ifndef MAZE_WIN_MINB
+#define MAZE_WIN_MINB 5
+#endif
+// kTiled: 4 x 4-tiled visit index; kUnit: visit_cell_stride == 1 (env-major array, the -v1 default)
+template <bool kTiled, bool kUnit>
+__global__ void __launch_bounds__(OBS_THREADS, MAZE_WIN_MINB)
 maze_window_kernel(maze_env_batch b, float* __restrict__ window, double* __restrict__ agent_norm,
                    double* __restrict__ target_norm) {
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (OBS_THREADS / 32) + (threadIdx.x >> 5);
-    if (e >= b.num_envs) return;
-    const EnvState st = unpack_state(b.state[e]);
-    const int m = b.env_maze[e];
-    const int4 m0 = __ldg(reinterpret_cast<const int4*>(b.meta + (size_t)m * MAZE_META_WORDS));
-    const int H = m0.x, W = m0.y;
-    const bool tor = (__ldg(b.meta + (size_t)m * MAZE_META_WORDS + MAZE_META_FLAGS) & MAZE_FLAG_TOROIDAL) != 0;
-    const int start_idx = (m0.z & 0xffff) * W + (m0.z >> 16);
-    const int goal_idx = (m0.w & 0xffff) * W + (m0.w >> 16);
-    float* out = window + (size_t)e * (3 * WIN_CELLS);
-    if (H < WIN || W < WIN) {   // no 15 x 15 crop exists (the reference cannot build one either)
-        for (int i = lane; i < 3 * WIN_CELLS; i += 32) out[i] = 0.0f;
-        return;
-    }
-    int r0 = st.r - WIN / 2, c0 = st.c - WIN / 2;
-    if (!tor) {   // extract_submaze: clamped, and the reference uses len(maze) for both axes
-        r0 = min(max(r0, 0), H - WIN);
-        c0 = min(max(c0, 0), H - WIN);
-    }
-    const uint8_t* tab = b.table + (size_t)m * b.slot;
+    __shared__ __align__(16) uint8_t s_out[WIN_ENVS * WIN_FLOATS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int e0 = blockIdx.x * WIN_ENVS, e = e0 + w;
+    uint8_t* so = s_out + w * WIN_FLOATS;
+    if (e < b.num_envs) {
+        const EnvState st = unpack_state(b.state[e]);
+        const int m = b.env_maze[e];
+        const int4 m0 = __ldg(reinterpret_cast<const int4*>(b.meta + (size_t)m * MAZE_META_WORDS));
+        const int H = m0.x, W = m0.y;
+        const bool tor = (__ldg(b.meta + (size_t)m * MAZE_META_WORDS + MAZE_META_FLAGS) & MAZE_FLAG_TOROIDAL) != 0;
+        const int start_idx = (m0.z & 0xffff) * W + (m0.z >> 16);
+        const int goal_idx = (m0.w & 0xffff) * W + (m0.w >> 16);
+        if (H < WIN || W < WIN) {   // no 15 x 15 crop exists (the reference cannot build one either)
+            for (int i = lane; i < WIN_FLOATS; i += 32) so[i] = 0;
+        } else {
+            int r0 = st.r - WIN / 2, c0 = st.c - WIN / 2;
+            if (!tor) {   // extract_submaze: clamped, and the reference uses len(maze) for both axes
+                r0 = min(max(r0, 0), H - WIN);
+                c0 = min(max(c0, 0), H - WIN);
+            }
+            const uint8_t* tab = b.table + (size_t)m * b.slot;
+            const uint64_t pol_table = l2_policy<MAZE_TABLE_POLICY>();
+            const uint16_t* vbase = b.visits + (size_t)e * b.visit_env_stride;
+            const int wt = (W + 3) >> 2;
+            // Table byte and visit word of all (up to eight) blocks of a lane are requested together.  The visit
+            // word is fetched whether or not the block is open: a window row is 30 contiguous bytes of the
+            // env-major visit array, so the sectors are the same and one dependent round trip disappears.
+            constexpr int K = (WIN_CELLS + 31) / 32;
+            int idxs[K], tb[K];
+            unsigned vis[K];
+            int wr = lane / WIN, wc = lane - wr * WIN;   // window row / column of block i = 32 k + lane
 #pragma unroll
-    for (int k = 0; k < (WIN_CELLS + 31) / 32; ++k) {
-        const int i = k * 32 + lane;
-        if (i >= WIN_CELLS) break;
-        int rr = r0 + i / WIN, cc = c0 + i % WIN;
-        if (tor) {   // extract_submaze_toroid: (position + i - k) % maze_shape
-            rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
-            cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
+            for (int k = 0; k < K; ++k) {
+                int rr = r0 + min(wr, WIN - 1), cc = c0 + wc;   // (lanes past block 224 re-read the last row)
+                if (tor) {   // extract_submaze_toroid: (position + i - k) % maze_shape
+                    rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
+                    cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
+                }
+                idxs[k] = rr * W + cc;
+                tb[k] = pol_load_nc<MAZE_TABLE_POLICY>(tab + idxs[k], pol_table);
+                const int vi = kTiled ? ((((rr >> 2) * wt + (cc >> 2)) << 4) | ((rr & 3) << 2) | (cc & 3)) : idxs[k];
+                vis[k] = __ldcs(kUnit ? vbase + vi : vbase + (size_t)vi * b.visit_cell_stride);
+                wr += 2; wc += 2;                                // 32 = 2 * 15 + 2
+                if (wc >= WIN) { wc -= WIN; wr += 1; }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = k * 32 + lane;
+                if (i >= WIN_CELLS) break;
+                const bool open = (tb[k] & MAZE_TAB_OPEN) != 0;
+                // non_visited (base_maze_env.py:148-149,183-184): open, not the start, no visit in this episode
+                const bool fresh = open && idxs[k] != start_idx && !((int)(vis[k] >> 8) == st.epoch && (vis[k] & 0xffu) != 0);
+                so[i] = open ? 0 : 1;                                        // maze == 0
+                so[WIN_CELLS + i] = (open && idxs[k] != goal_idx) ? 1 : 0;   // maze == 1
+                so[2 * WIN_CELLS + i] = fresh ? 1 : 0;
+            }
         }
-        const int idx = rr * W + cc;
-        const bool open = (__ldg(tab + idx) & MAZE_TAB_OPEN) != 0;
-        bool fresh = false;   // non_visited (base_maze_env.py:148-149,183-184)
-        if (open && idx != start_idx) {
-            const unsigned v = *VISIT_AT(b, e, visit_index(b, rr, cc, W));
-            fresh = !((int)(v >> 8) == st.epoch && (v & 0xffu) != 0);
+        if (lane < 2) {
+            const int goal = m0.w;
+            const double shape = (double)(lane == 0 ? H : W);
+            if (agent_norm) agent_norm[(size_t)e * 2 + lane] = __ddiv_rn((double)(lane == 0 ? st.r : st.c), shape);
+            if (target_norm) target_norm[(size_t)e * 2 + lane] = __ddiv_rn((double)(lane == 0 ? (goal & 0xffff) : (goal >> 16)), shape);
         }
-        __stcs(out + i, open ? 0.0f : 1.0f);                                    // maze == 0
-        __stcs(out + WIN_CELLS + i, (open && idx != goal_idx) ? 1.0f : 0.0f);   // maze == 1
-        __stcs(out + 2 * WIN_CELLS + i, fresh ? 1.0f : 0.0f);
     }
-    if (lane < 2) {
-        const int goal = m0.w;
-        const double shape = (double)(lane == 0 ? H : W);
-        if (agent_norm) agent_norm[(size_t)e * 2 + lane] = __ddiv_rn((double)(lane == 0 ? st.r : st.c), shape);
-        if (target_norm) target_norm[(size_t)e * 2 + lane] = __ddiv_rn((double)(lane == 0 ? (goal & 0xffff) : (goal >> 16)), shape);
+    __syncthreads();
+    const int n_float = min(WIN_ENVS, b.num_envs - e0) * WIN_FLOATS;
+    float* out = window + (size_t)e0 * WIN_FLOATS;   // 16-byte aligned: e0 is a multiple of 8
+    for (int q = threadIdx.x; 4 * q < n_float; q += OBS_THREADS) {
+        const int f = 4 * q;
+        const unsigned v = *reinterpret_cast<const unsigned*>(s_out + f);   // four values, one byte each
+        if (f + 3 < n_float) {
+            __stcs(reinterpret_cast<float4*>(out) + q,
+                   make_float4(__uint_as_float((v & 1u) * 0x3f800000u), __uint_as_float((v >> 8 & 1u) * 0x3f800000u),
+                               __uint_as_float((v >> 16 & 1u) * 0x3f800000u), __uint_as_float((v >> 24 & 1u) * 0x3f800000u)));
+        } else {
+            for (int i = f; i < n_float; ++i) __stcs(out + i, (float)s_out[i]);
+        }
     }
 }
 
@@ -102,18 +148,111 @@ maze_direction_mask_kernel(maze_env_batch b, int probs, float4* __restrict__ mas
     mask[e] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// maze_render: the frame MazeViewTemplate keeps on its pygame surface (lib/maze_view.py:12-14,88-104,
+// 148-152), as uint8 [n, out_h, out_w, 3] for n selected envs.  One CTA per (env, tile row); a thread
+// produces four pixels (12 bytes) at a time.
+//   tile (r, c) = 16 x 16 pixels at (16 c, 16 r): CELL_COLORS[maze[r][c]] with a one-pixel outline,
+//   (59, 66, 82) as drawn by __draw_maze, (208, 135, 112) once the agent has left the block
+//   (_draw_cell, called by move_agent / _reset_agent on the block the agent leaves);
+//   agent = 8 x 8 square at offset (4, 4) of its tile; the layers are one pixel smaller than the
+//   window (:41-44), so the last pixel row / column stay black, like everything beyond the maze.
+// "Left" is derived from the episode's visit counters: start once the episode has a legal move, the
+// agent's own block when it is there for at least the second time, any other block with a visit.
+__global__ void __launch_bounds__(OBS_THREADS)
+maze_render_kernel(maze_env_batch b, const int32_t* __restrict__ env_ids, int out_h, int out_w, uint8_t* __restrict__ out) {
+    constexpr int T = MAZE_RENDER_TILE;
+    const int k = blockIdx.x, r = blockIdx.y;
+    const int e = env_ids ? env_ids[k] : k;
+    const EnvState st = unpack_state(b.state[e]);
+    const int m = b.env_maze[e];
+    const int4 m0 = __ldg(reinterpret_cast<const int4*>(b.meta + (size_t)m * MAZE_META_WORDS));
+    const int H = m0.x, W = m0.y;
+    const int start_r = m0.z & 0xffff, start_c = m0.z >> 16, goal_r = m0.w & 0xffff, goal_c = m0.w >> 16;
+    const uint8_t* tab = b.table + (size_t)m * b.slot;
+    const bool has_moved = ((st.flags >> MAZE_ST_NMOVES_SHIFT) & 3) >= 1;
+    __shared__ uint8_t s_tile[MAZE_GEN_MAX_DIM];   // per tile of this row: value (0 / 1 / 2) | trail << 2
+    for (int c = threadIdx.x; c < out_w / T; c += OBS_THREADS) {
+        int code = 0;
+        if (r < H && c < W) {
+            const bool open = (__ldg(tab + r * W + c) & MAZE_TAB_OPEN) != 0;
+            const int v = open ? ((r == goal_r && c == goal_c) ? 2 : 1) : 0;
+            bool trail = false;
+            if (open) {
+                const unsigned vis = *VISIT_AT(b, e, visit_index(b, r, c, W));
+                const int cnt = ((int)(vis >> 8) == st.epoch) ? (int)(vis & 0xff) : 0;
+                if (r == start_r && c == start_c) trail = has_moved;
+                else if (r == st.r && c == st.c) trail = cnt >= 2;
+                else trail = cnt >= 1;
+            }
+            code = v | (trail ? 4 : 0) | 8;
+        }
+        s_tile[c] = (uint8_t)code;
+    }
+    __syncthreads();
+    const int groups = out_w / 4;   // four pixels per thread and iteration
+    for (int p = threadIdx.x; p < T * groups; p += OBS_THREADS) {
+        const int ly = p / groups, x0 = (p % groups) * 4, y = r * T + ly;
+        if (y >= out_h) break;
+        unsigned char px[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = x0 + i, c = x / T, lx = x % T;
+            const int code = s_tile[c];
+            int cr = 0, cg = 0, cb = 0;
+            if ((code & 8) && x != W * T - 1 && y != H * T - 1) {
+                const int v = code & 3;
+                if (lx == 0 || lx == T - 1 || ly == 0 || ly == T - 1) {
+                    if (code & 4) { cr = 208; cg = 135; cb = 112; } else { cr = 59; cg = 66; cb = 82; }
+                } else if (r == st.r && c == st.c && lx >= T / 4 && lx < T / 4 + T / 2 && ly >= T / 4 && ly < T / 4 + T / 2) {
+                    cr = 94; cg = 129; cb = 172;                                     // AGENT_COLOR
+                } else if (v == 0) { cr = 46; cg = 52; cb = 64; }                    // CELL_COLORS: wall, floor, goal
+                else if (v == 1) { cr = 236; cg = 239; cb = 244; }
+                else { cr = 163; cg = 190; cb = 140; }
+            }
+            px[3 * i] = (unsigned char)cr; px[3 * i + 1] = (unsigned char)cg; px[3 * i + 2] = (unsigned char)cb;
+        }
+        unsigned* o = reinterpret_cast<unsigned*>(out + (((size_t)k * out_h + y) * out_w + x0) * 3);
+#pragma unroll
+        for (int w = 0; w < 3; ++w)
+            __stcs(o + w, (unsigned)px[4 * w] | ((unsigned)px[4 * w + 1] << 8) | ((unsigned)px[4 * w + 2] << 16) | ((unsigned)px[4 * w + 3] << 24));
+    }
+}
+
 }  // namespace
+
+extern "C" int maze_render(maze_ctx* ctx, const maze_env_batch* b, const int32_t* env_ids, int n, uint8_t* out,
+                           int out_h, int out_w, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = maze_check_batch(ctx, b)) return rc;
+    if (!out) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_render: out");
+    if (n <= 0 || out_h <= 0 || out_w <= 0 || out_h % MAZE_RENDER_TILE || out_w % MAZE_RENDER_TILE ||
+        out_h / MAZE_RENDER_TILE > MAZE_GEN_MAX_DIM || out_w / MAZE_RENDER_TILE > MAZE_GEN_MAX_DIM)
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_render: n / out_h / out_w (multiples of MAZE_RENDER_TILE, at most MAZE_GEN_MAX_DIM tiles)");
+    if ((uintptr_t)out & 3) return maze_fail_arg(ctx, MAZE_E_ALIGN, "maze_render: out must be 4-byte aligned");
+    if (env_ids == nullptr && n > b->num_envs) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_render: n exceeds num_envs");
+    maze_render_kernel<<<dim3(n, out_h / MAZE_RENDER_TILE), OBS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, env_ids, out_h, out_w, out);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int maze_window(maze_ctx* ctx, const maze_env_batch* b, float* window, double* agent_norm,
                            double* target_norm, void* stream) {
     if (!ctx) return MAZE_E_NULL;
     if (int rc = maze_check_batch(ctx, b)) return rc;
     if (!window) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_window: window");
-    if (((uintptr_t)window & 3) || ((uintptr_t)agent_norm & 7) || ((uintptr_t)target_norm & 7))
+    if (((uintptr_t)window & 15) || ((uintptr_t)agent_norm & 7) || ((uintptr_t)target_norm & 7))
         return maze_fail_arg(ctx, MAZE_E_ALIGN, "maze_window pointer alignment");
     const int per_cta = OBS_THREADS / 32;
     const int grid = (b->num_envs + per_cta - 1) / per_cta;
-    maze_window_kernel<<<grid, OBS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, window, agent_norm, target_norm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool unit = b->visit_cell_stride == 1;
+    if (b->visit_tiled) {
+        if (unit) maze_window_kernel<true, true><<<grid, OBS_THREADS, 0, st>>>(*b, window, agent_norm, target_norm);
+        else maze_window_kernel<true, false><<<grid, OBS_THREADS, 0, st>>>(*b, window, agent_norm, target_norm);
+    } else {
+        if (unit) maze_window_kernel<false, true><<<grid, OBS_THREADS, 0, st>>>(*b, window, agent_norm, target_norm);
+        else maze_window_kernel<false, false><<<grid, OBS_THREADS, 0, st>>>(*b, window, agent_norm, target_norm);
+    }
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

@@ -20,6 +20,7 @@ MAX_DIM, GEN_MAX_DIM, WINDOW = 255, 131, 15
 METRIC_WORDS = 8
 METRIC_NAMES = ("difficulty", "complexity", "L", "DE", "D", "sol_len", "de_count")
 PACK_BITMAP, PACK_WALLS = 0, 1
+RENDER_TILE = 16
 METRIC_EXT_WORDS = 20
 METRIC_EXT_NAMES = ("density", "T", "J", "CR", "AC", "FDE", "BDE", "L_DE", "T_DE_AC", "T_DE_FDE", "T_DE_BDE",
                     "D_sharp_AC", "D_sharp_FDE", "D_sharp_BDE", "L_sharp_AC", "L_sharp_FDE", "L_sharp_BDE")
@@ -102,6 +103,7 @@ SIGNATURES = {
                                   C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "maze_difficulty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
+    "maze_render": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "maze_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                             C.c_void_p]),
     "maze_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

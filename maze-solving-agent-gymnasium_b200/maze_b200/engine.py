@@ -309,6 +309,18 @@ class MazeBatch:
         self.ctx.check(rc, "maze_window")
         return self.window
 
+    def render(self, env_ids=None) -> torch.Tensor:
+        """uint8 [n, 16 H, 16 W, 3] frames of the given envs (all if None -- 5 MB per 81 x 81 env): the
+        picture MazeViewTemplate keeps on its surface (lib/maze_view.py:88-104,148-152)."""
+        ids_t = None if env_ids is None else torch.as_tensor(list(env_ids), dtype=torch.int32, device=self.device)
+        n = self.num_envs if ids_t is None else ids_t.numel()
+        H, W = self.pool.max_shape
+        out = torch.empty((n, H * cabi.RENDER_TILE, W * cabi.RENDER_TILE, 3), dtype=torch.uint8, device=self.device)
+        rc = cabi.lib().maze_render(self.ctx.handle, C.byref(self._c), cabi.ptr(ids_t), n, cabi.ptr(out), out.shape[1], out.shape[2],
+                                    cabi.current_stream(self.device))
+        self.ctx.check(rc, "maze_render")
+        return out
+
     def direction_mask(self, probs: bool = False):
         """float32 [B, 4] get_mask_direction of every env (action order down, up, right, left)."""
         if self.dir_mask is None:

@@ -206,8 +206,13 @@ class BaseMazeEnv(Env):
             return m.astype(np.float32)
         return m.astype(np.int32)
 
-    def render(self):
-        return None
+    def render(self, mode="human", close=False):
+        """rgb frame uint8 [16 H, 16 W, 3] of the current maze (base_maze_env.py:212-222 returns
+        maze_view.update(mode), the surface as an array); there is no window to update here."""
+        if close:
+            return None
+        H, W = self.maze_shape
+        return self._batch.render([0])[0, :H * 16, :W * 16].cpu().numpy()
 
     def close(self):
         pass

@@ -76,8 +76,9 @@ class MazeVectorEnv(_VectorBase):
         (variable-size envs: START_SHAPE and +(4, 4), simple_variable_maze_env.py:17,97);
         `algorithm_schedule` = ((wins, algorithm), ...) switches a slot's generator by its win count
         (off_policy_trainer.py:302-310: ((5, "prim&kill"), (10, "dfs"))).
-        visit_layout: "cell" (default; best for one launch per step), "tile" (best for the fused
-        multi-step paths: step_many, the Q-learning rollout), "env" (default with enrich)."""
+        visit_layout: "cell" (default; best for one launch per step), "tile" (env-major in 4 x 4 block tiles:
+        best for the fused multi-step paths -- step_many, the Q-learning rollout -- and the default with
+        enrich, where the 15 x 15 window then reads <= 25 whole sectors per env), "env" (env-major rows)."""
         if topology not in ("euclid", "toroidal"):
             raise ValueError("topology must be 'euclid' or 'toroidal'")
         if on_win not in ("keep", "next", "regenerate"):
@@ -119,7 +120,7 @@ class MazeVectorEnv(_VectorBase):
             per = max(1, self.num_envs // pool.num_mazes)
             env_maze = (torch.arange(self.num_envs, device=self.device, dtype=torch.int32) // per).clamp_(max=pool.num_mazes - 1)
         self.batch = MazeBatch(pool, self.num_envs, env_maze=env_maze, stats=stats, queue=(on_win == "regenerate"),
-                               visit_layout=visit_layout or ("env" if self.enrich else "cell"))
+                               visit_layout=visit_layout or ("tile" if self.enrich else "cell"))
         self._mode = ((cabi.STEP_AUTORESET if self.autoreset else 0)
                       | (cabi.STEP_WIN_NEXT if on_win == "next" else 0)
                       | (cabi.STEP_WIN_QUEUE if on_win == "regenerate" else 0))

@@ -53,3 +53,52 @@ def time_env_steps(mazes, seconds=10.0, workers=None, kind="port"):
     steps = sum(r[0] for r in res)
     longest = max(r[1] for r in res)
     return dict(value=steps / longest, steps=steps, seconds=longest, wall=wall, cores=workers, kind=kind)
+
+
+def _persistent_worker(conn, kind, grid, start, goal, toroidal, seed):
+    from .env_port import ClosedFormEnv, PortEnv
+    env = (PortEnv if kind == "port" else ClosedFormEnv)(grid, start, goal, toroidal)
+    rng = np.random.default_rng(seed)
+    env.reset()
+    while True:
+        n = conn.recv()
+        if n is None:
+            break
+        t0 = time.perf_counter()
+        for a in rng.integers(0, 4, n):
+            _, _, trunc, term, _ = env.step(int(a))
+            if trunc or term:
+                env.reset()
+        conn.send(time.perf_counter() - t0)
+
+
+class PersistentVector:
+    """One long-lived worker process per core, each owning one env (the AsyncVectorEnv shape): `step(n)`
+    advances every env by n transitions and returns the slowest worker's time, so a bench 'step' can be
+    a small bounded sample without paying a process spawn each time."""
+
+    def __init__(self, mazes, workers=None, kind="port"):
+        self.workers = workers or os.cpu_count() or 1
+        ctx = mp.get_context("fork")
+        self.conns, self.procs = [], []
+        for w in range(self.workers):
+            m = mazes[w % len(mazes)]
+            parent, child = ctx.Pipe()
+            p = ctx.Process(target=_persistent_worker, daemon=True,
+                            args=(child, kind, np.asarray(m["grid"]), tuple(m["start"]), tuple(m["goal"]), bool(m["toroidal"]), 1000 + w))
+            p.start()
+            self.conns.append(parent)
+            self.procs.append(p)
+
+    def step(self, n):
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send(int(n))
+        worker_s = max(c.recv() for c in self.conns)
+        return dict(steps=int(n) * self.workers, seconds=time.perf_counter() - t0, slowest_worker_seconds=worker_s)
+
+    def close(self):
+        for c in self.conns:
+            c.send(None)
+        for p in self.procs:
+            p.join(timeout=5)

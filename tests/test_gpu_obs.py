@@ -101,3 +101,40 @@ def test_window_against_oracle_with_autoreset():
                 o, _, tr, te, _ = env.step(int(acts[i]))
                 pending[i] = bool(tr or te)
             np.testing.assert_array_equal(win[i], o["window"], err_msg=f"env {i} step {t}")
+
+
+@pytest.mark.parametrize("toroidal", [False, True])
+def test_render_matches_the_replayed_drawing_calls(toroidal):
+    """maze_render against oracle/render.py (lib/maze_view.py's draw calls replayed on a numpy canvas)
+    along one episode: fresh frame, trail outlines on every block the agent has left, agent square."""
+    import maze_b200 as mb
+    from oracle.render import Canvas
+    pool = mb.MazePool(2, (21, 21))
+    pool.generate(algorithms=["r-prim", "dfs"], toroidal=toroidal, seed=3)
+    batch = mb.MazeBatch(pool, 2, env_maze=torch.tensor([0, 1], dtype=torch.int32, device="cuda"))
+    batch.reset()
+    meta = pool.meta_host()
+    canv = [Canvas(pool.grid_host(m), (int(meta[m, 2]) & 0xffff, int(meta[m, 2]) >> 16)) for m in range(2)]
+    frames = batch.render().cpu().numpy()
+    assert frames.shape == (2, 21 * 16, 21 * 16, 3) and frames.dtype == np.uint8
+    for m in range(2):
+        assert np.array_equal(frames[m], canv[m].frame())
+    rng = np.random.default_rng(5)
+    moved_any = False
+    for t in range(120):
+        before = batch.agent.cpu().numpy().copy()
+        batch.step(torch.from_numpy(rng.integers(0, 4, 2).astype(np.uint8)).cuda(), 0)
+        after = batch.agent.cpu().numpy()
+        if batch.terminated.any() or batch.truncated.any():
+            break
+        for m in range(2):
+            if (before[m] != after[m]).any():
+                canv[m].move_to(after[m])
+                moved_any = True
+        if t % 10 == 9:
+            frames = batch.render().cpu().numpy()
+            for m in range(2):
+                assert np.array_equal(frames[m], canv[m].frame()), (t, m)
+    assert moved_any
+    one = batch.render([1]).cpu().numpy()
+    assert np.array_equal(one[0], batch.render().cpu().numpy()[1])
