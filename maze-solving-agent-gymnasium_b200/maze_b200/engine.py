@@ -186,6 +186,17 @@ class MazePool:
         self.ctx.check(rc, "maze_difficulty")
         return out
 
+    # -- checkpoint / resume (the reference keeps no checkpoints; env state here is a
+    #    handful of SoA tensors, so a state dict of them is a complete checkpoint)
+    def state_dict(self):
+        return {"max_shape": tuple(self.max_shape), "grids": self.grids, "table": self.table, "meta": self.meta}
+
+    def load_state_dict(self, sd):
+        if tuple(sd["max_shape"]) != tuple(self.max_shape) or sd["grids"].shape != self.grids.shape:
+            raise ValueError("checkpoint was taken from a pool of another size / shape")
+        for k in ("grids", "table", "meta"):
+            getattr(self, k).copy_(sd[k])
+
     # -- host views (tests, facade)
     def meta_host(self):
         return self.meta.cpu().numpy()
@@ -243,6 +254,23 @@ class MazeBatch:
         self.queue_count = torch.zeros(1, dtype=torch.int32, device=d) if queue else None
         self.pool_stride = int(pool_stride)
         self._c = self._make_struct()
+
+    _CKPT = ("env_maze", "state", "visits", "agent", "target", "best_dir", "reward", "terminated", "truncated",
+             "ep_return", "stats", "stats_return", "queue", "queue_count")
+
+    def state_dict(self):
+        """Everything a later step depends on (the visit counters included: [slot, B] int16, by far the largest
+        entry).  Tensors are references, not copies: clone or torch.save them before stepping on."""
+        sd = {k: getattr(self, k) for k in self._CKPT if getattr(self, k) is not None}
+        sd["visit_layout"] = self.visit_layout
+        return sd
+
+    def load_state_dict(self, sd):
+        if sd["visit_layout"] != self.visit_layout or sd["state"].shape != self.state.shape:
+            raise ValueError("checkpoint was taken from a batch of another size / visit layout")
+        for k in self._CKPT:
+            if getattr(self, k) is not None:
+                getattr(self, k).copy_(sd[k])
 
     def _make_struct(self) -> cabi.MazeEnvBatch:
         p = self.pool

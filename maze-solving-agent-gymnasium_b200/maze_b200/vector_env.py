@@ -237,6 +237,17 @@ class MazeVectorEnv(_VectorBase):
             return obs, h["reward"].numpy(), trunc, term, info
         return obs, h["reward"].numpy(), term, trunc, info
 
+    def state_dict(self):
+        """Checkpoint of the whole env (pool, batch, curriculum win counts): load it into an env built with the
+        same arguments and the following steps are bit-identical.  Values are references to the live tensors --
+        `torch.save(env.state_dict(), path)` serialises them, `{k: v.clone()}` snapshots them in memory."""
+        return {"pool": self.pool.state_dict(), "batch": self.batch.state_dict(), "wins": self.wins}
+
+    def load_state_dict(self, sd):
+        self.pool.load_state_dict(sd["pool"])
+        self.batch.load_state_dict(sd["batch"])
+        self.wins.copy_(sd["wins"])
+
     def episode_statistics(self, reduce: bool = False):
         """Episodes / wins / truncations / return sum since construction (one small D2H); with
         reduce=True summed over all ranks of the torch.distributed job (the only collective of

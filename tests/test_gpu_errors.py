@@ -95,3 +95,63 @@ def test_single_env_and_odd_batch_sizes():
             ref = ora.step(acts)
             np.testing.assert_array_equal(batch.agent.cpu().numpy(), ref["agent"])
             np.testing.assert_array_equal(batch.reward.cpu().numpy().view(np.uint64), ref["reward"].view(np.uint64))
+
+
+def test_errors_of_the_abi_9_entry_points():
+    """maze_step_many, maze_difficulty_ext, maze_pack / maze_unpack, maze_collection_encode, maze_render,
+    maze_window alignment: bad arguments come back as MAZE_E_* codes with a message."""
+    mb, pool, batch, lib, ctx = _raw()
+    st = mb.cabi.current_stream(pool.device)
+    E, ptr = mb.cabi, mb.cabi.ptr
+    acts = torch.zeros((4, 8), dtype=torch.uint8, device="cuda")
+    assert lib.maze_step_many(ctx, C.byref(batch._c), None, 4, 0, None, 0, st) == E.E_NULL
+    assert lib.maze_step_many(ctx, C.byref(batch._c), ptr(acts), 0, 0, None, 0, st) == E.E_RANGE
+    assert lib.maze_step_many(ctx, C.byref(batch._c), ptr(acts), 4, E.STEP_WIN_QUEUE, None, 0, st) == E.E_RANGE
+    assert b"maze_step" in lib.maze_last_error(ctx)
+    tr = E.MazeStepTrace(agent=batch.agent.data_ptr() + 4)
+    assert lib.maze_step_many(ctx, C.byref(batch._c), ptr(acts), 4, 0, C.byref(tr), 0, st) == E.E_ALIGN
+    out = torch.empty((4, E.METRIC_WORDS), dtype=torch.float64, device="cuda")
+    assert lib.maze_difficulty_ext(ctx, ptr(pool.grids), ptr(pool.meta), None, 4, pool.slot, 21, 21, ptr(out), None, st) == E.E_NULL
+    assert lib.maze_difficulty_ext(ctx, ptr(pool.grids), ptr(pool.meta), None, 4, pool.slot, 20, 21, ptr(out), ptr(out), st) == E.E_SHAPE
+    packed = torch.empty((4, 56), dtype=torch.uint8, device="cuda")
+    assert lib.maze_pack(ctx, ptr(pool.grids), ptr(pool.meta), None, 4, pool.slot, 7, ptr(packed), 56, st) == E.E_RANGE        # format
+    assert lib.maze_pack(ctx, ptr(pool.grids), ptr(pool.meta), None, 4, pool.slot, E.PACK_BITMAP, ptr(packed), pool.slot, st) == E.E_RANGE   # stride > slot / 8
+    assert lib.maze_pack(ctx, ptr(pool.grids), ptr(pool.meta), None, 4, pool.slot, E.PACK_BITMAP, None, 56, st) == E.E_NULL
+    assert lib.maze_unpack(ctx, ptr(packed), 56, E.PACK_BITMAP, ptr(pool.grids), ptr(pool.meta), None, 0, pool.slot, st) == E.E_RANGE
+    assert lib.maze_unpack(ctx, ptr(packed), 56, E.PACK_BITMAP, ptr(pool.grids), ptr(pool.meta), None, 4, pool.slot + 1, st) == E.E_RANGE   # slot % 16
+    coll = torch.empty((4, 3, 21, 21), dtype=torch.int32, device="cuda")
+    assert lib.maze_collection_encode(ctx, ptr(pool.grids), ptr(pool.meta), None, 4, pool.slot, 41, 41, ptr(coll), st) == E.E_RANGE
+    assert lib.maze_collection_encode(ctx, ptr(pool.grids), ptr(pool.meta), None, 4, pool.slot, 21, 21, None, st) == E.E_NULL
+    img = torch.empty((1, 21 * 16, 21 * 16, 3), dtype=torch.uint8, device="cuda")
+    assert lib.maze_render(ctx, C.byref(batch._c), None, 1, ptr(img), 21 * 16 + 1, 21 * 16, st) == E.E_RANGE
+    assert lib.maze_render(ctx, C.byref(batch._c), None, 9, ptr(img), 21 * 16, 21 * 16, st) == E.E_RANGE    # n > num_envs
+    assert lib.maze_render(ctx, C.byref(batch._c), None, 1, None, 21 * 16, 21 * 16, st) == E.E_NULL
+    win = torch.empty(8 * 675 + 4, dtype=torch.float32, device="cuda")
+    assert lib.maze_window(ctx, C.byref(batch._c), win.data_ptr() + 4, None, None, st) == E.E_ALIGN
+    torch.cuda.synchronize()
+    # nothing was launched or damaged: the pool still scores and steps
+    assert torch.isfinite(pool.difficulty()).all()
+    batch.reset()
+    batch.step_many(acts, 0)
+    assert batch.state_host()["steps"].tolist() == [4] * 8
+
+
+def test_windows_of_odd_batch_sizes_are_complete():
+    """maze_window serves 8 envs per CTA with 16-byte stores: batch sizes that are not multiples of 8
+    (tail CTA, scalar tail stores) must produce the same windows as the same envs in a larger batch."""
+    import maze_b200 as mb
+    pool = mb.MazePool(3, (21, 21))
+    pool.generate(algorithms=["r-prim", "dfs", "prim&kill"], seed=4)
+    rng = np.random.default_rng(1)
+    tape = torch.from_numpy(rng.integers(0, 4, (30, 16)).astype(np.uint8)).cuda()
+    ref = None
+    for B in (16, 13, 9, 1):
+        batch = mb.MazeBatch(pool, B, env_maze=torch.arange(B, dtype=torch.int32, device="cuda") % 3, visit_layout="tile")
+        batch.reset()
+        for t in range(30):
+            batch.step(tape[t, :B].contiguous(), 0)
+        w = batch.compute_window().cpu().numpy()
+        if ref is None:
+            ref = w
+            assert ref.sum() > 0
+        assert np.array_equal(w, ref[:B]), B

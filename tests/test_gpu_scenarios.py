@@ -130,3 +130,53 @@ def test_config4_variable_size_curriculum_with_double_q():
             grid = env.pool.grid_host(e)
             assert grid.shape == (H, W) and check_perfect_maze(grid)[0]
     assert len(agent.core.table_host("a")) > B
+
+
+@pytest.mark.parametrize("on_win", ["next", "regenerate"])
+def test_checkpoint_resume_is_bit_identical(tmp_path, on_win):
+    """state_dict -> torch.save -> fresh env -> load_state_dict: the continued run equals the uninterrupted one
+    (positions, rewards, flags, regenerated mazes, statistics), also with regeneration on win."""
+    import maze_b200 as mb
+    kw = dict(shape=(21, 21), algorithms=["r-prim", "dfs", "prim&kill"], seed=11, on_win=on_win, stats=True)
+    B = 96
+    if on_win == "next":
+        kw["num_mazes"] = 12
+    env = mb.MazeVectorEnv(B, **kw)
+    env.reset()
+    rng = np.random.default_rng(2)
+
+    def actions(e):
+        # follow the best direction most of the time so that episodes are won and mazes change
+        best = e.batch.best_dir.cpu().numpy()
+        a = np.full(B, 0, dtype=np.uint8)
+        a[best[:, 0] == 1] = 1      # best dir = agent - next: (1, 0) means next is the row above -> action up
+        a[best[:, 0] == -1] = 0
+        a[best[:, 1] == 1] = 3
+        a[best[:, 1] == -1] = 2
+        rnd = rng.random(B) < 0.2
+        a[rnd] = rng.integers(0, 4, int(rnd.sum()))
+        return torch.from_numpy(a).cuda()
+
+    for _ in range(120):
+        env.step(actions(env))
+    path = str(tmp_path / "env.pt")
+    torch.save(env.state_dict(), path)
+    rng_state = rng.bit_generator.state
+    trace = []
+    for _ in range(150):
+        obs, rew, term, trunc, _ = env.step(actions(env))
+        trace.append((obs["agent"].clone(), obs["target"].clone(), obs["best dir"].clone(), rew.clone(), term.clone(), trunc.clone()))
+    assert int(env.batch.stats[1].item()) > 0          # some wins, so mazes did change
+    final_meta = env.pool.meta.clone()
+
+    other = mb.MazeVectorEnv(B, **kw)
+    other.reset()
+    other.load_state_dict(torch.load(path))
+    rng.bit_generator.state = rng_state
+    for t in range(150):
+        obs, rew, term, trunc, _ = other.step(actions(other))
+        got = (obs["agent"], obs["target"], obs["best dir"], rew, term, trunc)
+        for a, b in zip(got, trace[t]):
+            assert torch.equal(a, b), t
+    assert torch.equal(other.pool.meta, final_meta)
+    assert other.episode_statistics() == env.episode_statistics()
