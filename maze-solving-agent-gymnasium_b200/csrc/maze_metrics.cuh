@@ -83,7 +83,7 @@ struct MazeMetrics {
 __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, int Hb, int Wb,
                                     int start_idx, int goal_idx, MazeMetrics& out, bool with_kc = true, bool ext = false) {
     __shared__ double s_D0, s_S0, s_red[2][FIELD_THREADS / 32];
-    __shared__ int s_dcount, s_sol_counts[3], s_open;
+    __shared__ int s_dcount, s_sol_counts[3], s_open, s_de_counts[3];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2, cells = nr * nc;
     auto cell_block = [&](int ci) { return (2 * (ci / nc) + 1) * Wb + 2 * (ci % nc) + 1; };
@@ -122,7 +122,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
         ms.pnode[ci] = 0xffffu;
         ms.dpar[ci] = 0;
     }
-    if (tid == 0) { s_D0 = 0.0; s_S0 = 0.0; s_dcount = 0; s_open = 0; }
+    if (tid == 0) { s_D0 = 0.0; s_S0 = 0.0; s_dcount = 0; s_open = 0; s_de_counts[0] = s_de_counts[1] = s_de_counts[2] = 0; }
     __syncthreads();
     if (ext) {   // calculate_density :18-20
         int open = 0;
@@ -208,6 +208,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
             jup[ci] = (unsigned short)y;
         }
         __syncthreads();
+        MET_TICK(9);
         const int gr = goal_idx / Wb, gc = goal_idx % Wb;
         for (int de = tid; de < cells; de += nthr) {
             if (!is_dead_end_off(de)) continue;
@@ -251,33 +252,80 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            for (int de = 0; de < cells; ++de) {
+        MET_TICK(10);
+        // 4c.  The reference walks the dead ends in row-major order: dead end d counts unless a decision point of
+        // its chain was recorded by an earlier counted dead end, and a counted dead end records the first decision
+        // point of its chain.  With rec[P] = smallest index of a counted dead end whose first decision point is P,
+        //     counted(d)  <=>  no P in chain(d) has rec[P] < d,
+        // and this system has exactly one solution (by induction on d, which only looks at smaller indices).  It is
+        // reached by iterating from "everything counts": after k rounds the k smallest dead ends are final, in
+        // practice a handful of rounds; a round without a change is the fixpoint.  (The sequential pass this
+        // replaces was 66 % of the kernel's time on r-prim mazes.)  rec lives in ms.dsum at decision-point cells;
+        // the ext sums keep their terms in ms.dsum / ssum / bsum at dead-end cells, which are different cells.
+        constexpr unsigned NOT_RECORDED = 0xffffffffu;
+        constexpr int COUNTED = 8;
+        auto in_range = [&](int y, bool cut) { return y != 0xffff && (cut ? !is_sol(y) : y != start_c); };
+        for (int ci = tid; ci < cells; ci += nthr)
+            if (is_dead_end_off(ci)) kind[ci] |= COUNTED;
+        // (bounded on purpose: at most one round per dead end is ever needed, and an unbounded `for (;;)` around
+        // the barrier-with-reduction died with "illegal instruction" on 41 x 41 mazes on sm_100a, CUDA 12.9)
+        for (int round = 0; round <= cells; ++round) {
+            for (int ci = tid; ci < cells; ci += nthr)
+                if ((ms.flags[ci] & MF_NODE) && nbof(ci) > 2) ms.dsum[ci] = NOT_RECORDED;
+            __syncthreads();
+            for (int de = tid; de < cells; de += nthr) {
+                if (!is_dead_end_off(de) || !(kind[de] & COUNTED)) continue;
+                const int f = jup[de];
+                if (in_range(f, (kind[de] & 4) != 0)) atomicMin(&ms.dsum[f], (unsigned)de);
+            }
+            __syncthreads();
+            int changed = 0;
+            for (int de = tid; de < cells; de += nthr) {
                 if (!is_dead_end_off(de)) continue;
                 const int kd = kind[de];
                 const bool cut = (kd & 4) != 0;
-                if (ext) {   // sums over ALL off-solution dead ends, in this (row-major) order
-                    const double l = __ddiv_rn((double)ms.dsum[de], ce_d);
-                    x_lde = __dadd_rn(x_lde, l);
-                    x_l[kd & 3] = __dadd_rn(x_l[kd & 3], l);
-                    x_t[kd & 3] = __dadd_rn(x_t[kd & 3], ms.ssum[de]);
-                    x_d[kd & 3] = __dadd_rn(x_d[kd & 3], ms.bsum[de]);
-                }
                 bool blocked = false;
-                int first_dp = -1;
-                for (int y = jup[de]; y != 0xffff && (cut ? !is_sol(y) : y != start_c); y = jup[y]) {
-                    if (ms.flags[y] & MF_DP) { blocked = true; break; }
-                    if (first_dp < 0) first_dp = y;
+                for (int y = jup[de]; in_range(y, cut); y = jup[y])
+                    if (ms.dsum[y] < (unsigned)de) { blocked = true; break; }
+                if (blocked == ((kd & COUNTED) != 0)) {
+                    kind[de] = (unsigned short)(kd ^ COUNTED);
+                    changed = 1;
                 }
-                if (blocked) continue;
-                if (first_dp >= 0) ms.flags[first_dp] |= MF_DP;
-                if ((kd & 3) == 0) ++alcoves; else if ((kd & 3) == 1) ++forward; else ++backward;
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        {
+            int na = 0, nf = 0, nb_ = 0;
+            for (int de = tid; de < cells; de += nthr) {
+                if (!is_dead_end_off(de) || !(kind[de] & COUNTED)) continue;
+                const int k = kind[de] & 3;
+                na += k == 0; nf += k == 1; nb_ += k == 2;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                na += __shfl_xor_sync(0xffffffffu, na, o);
+                nf += __shfl_xor_sync(0xffffffffu, nf, o);
+                nb_ += __shfl_xor_sync(0xffffffffu, nb_, o);
+            }
+            if ((tid & 31) == 0) { atomicAdd(&s_de_counts[0], na); atomicAdd(&s_de_counts[1], nf); atomicAdd(&s_de_counts[2], nb_); }
+        }
+        if (ext && tid == 0) {   // sums over ALL off-solution dead ends, in row-major order (float sums: order matters)
+            for (int de = 0; de < cells; ++de) {
+                if (!is_dead_end_off(de)) continue;
+                const int k = kind[de] & 3;
+                const double l = __ddiv_rn((double)ms.dsum[de], ce_d);
+                x_lde = __dadd_rn(x_lde, l);
+                x_l[k] = __dadd_rn(x_l[k], l);
+                x_t[k] = __dadd_rn(x_t[k], ms.ssum[de]);
+                x_d[k] = __dadd_rn(x_d[k], ms.bsum[de]);
             }
         }
         __syncthreads();
+        alcoves = s_de_counts[0]; forward = s_de_counts[1]; backward = s_de_counts[2];
         for (int ci = tid; ci < cells; ci += nthr) {   // scratch back to its initial state
             ms.minleaf[ci] = 0xffffu; ms.comp[ci] = 0xffffu;
-            if (ext) { ms.dsum[ci] = 0u; ms.ssum[ci] = 0.0; ms.bsum[ci] = 0.0; }
+            ms.dsum[ci] = 0u;   // held rec[] at decision points (and the ext terms at dead ends)
+            if (ext) { ms.ssum[ci] = 0.0; ms.bsum[ci] = 0.0; }
         }
         __syncthreads();
     }

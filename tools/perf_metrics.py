@@ -18,6 +18,6 @@ for algo in ("r-prim", "dfs", "prim&kill"):
     line = f"{algo:10s} M={M}: {ms:.2f} ms  {M/ms*1e3:.3e} mazes/s"
     if prof:
         prof(buf, 1); tot = sum(buf) or 1
-        line += "  phases% bfs/init/sol/parents/DE/minleaf/comp/edges/branch: " + " ".join(f"{100*x/tot:.0f}" for x in list(buf)[:9]) + f"  kcyc/maze {tot/2/M/1e3:.0f}"
+        line += "  phases% bfs/init/sol/parents/DE/minleaf/comp/edges/branch: " + " ".join(f"{100*x/tot:.0f}" for x in list(buf)[:9]) + "  DE split 4a/4b/4c: " + " ".join(f"{100*x/tot:.0f}" for x in (buf[9], buf[10], buf[4])) + f"  kcyc/maze {tot/2/M/1e3:.0f}"
     print(line, flush=True)
     del pool
