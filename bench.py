@@ -319,6 +319,7 @@ def run_ours(args, rank, local_rank, world):
         env.step_host(host_tape[t % 4])
     barrier()
     torch.cuda.synchronize()
+    env.reset_host_counters()      # d2h_bytes_per_step() = bytes actually copied in the timed region / steps
     t0 = time.perf_counter()
     for t in range(e2e_steps):
         obs, rew, term, trunc, _ = env.step_host(host_tape[t % 4])
@@ -372,7 +373,10 @@ def run_ours(args, rank, local_rank, world):
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "maze_step_kernel"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step(),
-                    "d2h_bytes_per_step": env.d2h_bytes_per_step(), "steps": e2e_steps},
+                    "d2h_bytes_per_step": env.d2h_bytes_per_step(), "steps": e2e_steps,
+                    "note": "every output of every env is copied to pinned host memory each step (agent, best dir, reward, "
+                            "terminated, truncated); the target array is copied again only on steps whose launch rewrote it "
+                            "(an env restarting after a win), which the kernel reports through maze_env_batch.target_dirty"},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "extra": extra,

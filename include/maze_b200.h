@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 9
+#define MAZE_ABI_VERSION 10
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -117,7 +117,15 @@ typedef struct maze_env_batch {
                               idx = ((r >> 2) * ((W + 3) >> 2) + (c >> 2)) * 16 + (r & 3) * 4 + (c & 3),
                               so an agent walking a corridor keeps hitting the same sector      */
     int32_t   visit_slot;  /* visit entries per env (>= slot; tiled: >= 16 * ceil(H/4) * ceil(W/4)) */
+    int32_t*  target_dirty;/* optional [1] (may be NULL): set to 1 by every launch that writes `target`.  An env's
+                              target only changes when its maze does -- maze_reset, or the restart after a win --
+                              so maze_step rewrites `target` only then, and a host mirror of the outputs can skip
+                              the device-to-host copy of `target` on all other steps                       */
 } maze_env_batch;
+
+/* sizeof of the ABI structs as this library was compiled (a binding checks its own layout against it):
+ * which = 0 maze_env_batch, 1 maze_q_agent, 2 maze_replay, 3 maze_step_trace; -1 for anything else. */
+int  maze_sizeof(int which);
 
 int  maze_abi_version(void);
 int  maze_ctx_create(maze_ctx** out, int device);

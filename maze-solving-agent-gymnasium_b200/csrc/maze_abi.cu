@@ -38,6 +38,16 @@ int maze_check_batch(maze_ctx* ctx, const maze_env_batch* b) {
 
 extern "C" int maze_abi_version(void) { return MAZE_ABI_VERSION; }
 
+extern "C" int maze_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(maze_env_batch);
+        case 1: return (int)sizeof(maze_q_agent);
+        case 2: return (int)sizeof(maze_replay);
+        case 3: return (int)sizeof(maze_step_trace);
+        default: return -1;
+    }
+}
+
 extern "C" int maze_ctx_create(maze_ctx** out, int device) {
     if (!out) return MAZE_E_NULL;
     *out = nullptr;

@@ -249,6 +249,7 @@ maze_q_rollout_kernel(maze_env_batch b, maze_q_agent ag, int k_steps, uint32_t m
     store_cursor(ag, B, e, cur);
     reinterpret_cast<int2*>(b.agent)[e] = make_int2(st.r, st.c);
     reinterpret_cast<int2*>(b.target)[e] = make_int2(mz.goal & 0xffff, mz.goal >> 16);
+    if (b.target_dirty && threadIdx.x == 0) *b.target_dirty = 1;
     reinterpret_cast<int2*>(b.best_dir)[e] = best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, mz.H, mz.W, mz.tor);
     b.reward[e] = reward;
     b.terminated[e] = (uint8_t)term;

@@ -168,10 +168,13 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
 
         pol_store<MAZE_STATE_POLICY>(reinterpret_cast<unsigned long long*>(b.state) + e, (unsigned long long)pack_state(st), pol_state);
         st_cs(reinterpret_cast<int2*>(b.agent) + e, make_int2(st.r, st.c));
-        // `target` only changes when the env (re)starts on a possibly different maze; the buffer
-        // persists between steps, so it is rewritten on reset only
-        if (do_reset[k])
+        // `target` only changes when the env's maze does: the restart after a win (next pool maze, or the
+        // regenerated slot).  The buffer persists between steps, so it is rewritten only then, and
+        // target_dirty tells a host mirror that this launch touched it.
+        if (do_reset[k] && (raw[k] >> 24 & MAZE_ST_WON)) {
             st_cs(reinterpret_cast<int2*>(b.target) + e, make_int2(goal & 0xffff, goal >> 16));
+            if (b.target_dirty) *b.target_dirty = 1;
+        }
         st_cs(reinterpret_cast<int2*>(b.best_dir) + e,
               best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, H, W, tor[k] != 0));
         st_cs(b.reward + e, reward);
@@ -227,6 +230,7 @@ maze_reset_kernel(maze_env_batch b, const uint8_t* __restrict__ mask) {
     b.state[e] = pack_state(s);
     reinterpret_cast<int2*>(b.agent)[e] = make_int2(s.r, s.c);
     reinterpret_cast<int2*>(b.target)[e] = make_int2(goal & 0xffff, goal >> 16);
+    if (b.target_dirty && threadIdx.x == 0) *b.target_dirty = 1;
     reinterpret_cast<int2*>(b.best_dir)[e] =
         best_dir_from_code((s.tab >> MAZE_TAB_CODE_SHIFT) & 7, s.r, s.c, H, W, tor);
     b.reward[e] = 0.0;
@@ -287,7 +291,10 @@ maze_step_many_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, int
     b.state[e] = pack_state(st);
     b.env_maze[e] = m;
     reinterpret_cast<int2*>(b.agent)[e] = make_int2(st.r, st.c);
-    if (target_changed) reinterpret_cast<int2*>(b.target)[e] = make_int2(mz.goal & 0xffff, mz.goal >> 16);
+    if (target_changed) {
+        reinterpret_cast<int2*>(b.target)[e] = make_int2(mz.goal & 0xffff, mz.goal >> 16);
+        if (b.target_dirty) *b.target_dirty = 1;
+    }
     reinterpret_cast<int2*>(b.best_dir)[e] = best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, mz.H, mz.W, mz.tor);
     b.reward[e] = reward;
     b.terminated[e] = (uint8_t)term;

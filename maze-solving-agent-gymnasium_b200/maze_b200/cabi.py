@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -37,6 +37,7 @@ class MazeEnvBatch(C.Structure):
         ("queue", C.c_void_p), ("queue_count", C.c_void_p),
         ("visit_cell_stride", C.c_int64), ("visit_env_stride", C.c_int64),
         ("visit_tiled", C.c_int32), ("visit_slot", C.c_int32),
+        ("target_dirty", C.c_void_p),
     ]
 
 
@@ -103,6 +104,7 @@ SIGNATURES = {
                                   C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "maze_difficulty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
+    "maze_sizeof": (C.c_int, [C.c_int]),
     "maze_render": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "maze_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                             C.c_void_p]),

@@ -252,11 +252,12 @@ class MazeBatch:
         self.stats_return = torch.zeros(1, dtype=torch.float64, device=d) if stats else None
         self.queue = torch.zeros(B, dtype=torch.int32, device=d) if queue else None
         self.queue_count = torch.zeros(1, dtype=torch.int32, device=d) if queue else None
+        self.target_dirty = torch.zeros(1, dtype=torch.int32, device=d)   # set by launches that write `target`
         self.pool_stride = int(pool_stride)
         self._c = self._make_struct()
 
     _CKPT = ("env_maze", "state", "visits", "agent", "target", "best_dir", "reward", "terminated", "truncated",
-             "ep_return", "stats", "stats_return", "queue", "queue_count")
+             "ep_return", "stats", "stats_return", "queue", "queue_count", "target_dirty")
 
     def state_dict(self):
         """Everything a later step depends on (the visit counters included: [slot, B] int16, by far the largest
@@ -287,7 +288,8 @@ class MazeBatch:
             queue_count=None if self.queue_count is None else self.queue_count.data_ptr(),
             visit_cell_stride=self.num_envs if self.visit_layout == "cell" else 1,
             visit_env_stride=1 if self.visit_layout == "cell" else self.visit_slot,
-            visit_tiled=1 if self.visit_layout == "tile" else 0, visit_slot=self.visit_slot)
+            visit_tiled=1 if self.visit_layout == "tile" else 0, visit_slot=self.visit_slot,
+            target_dirty=self.target_dirty.data_ptr())
 
     def reset(self, mask: Optional[torch.Tensor] = None):
         if mask is not None:

@@ -140,6 +140,8 @@ class MazeVectorEnv(_VectorBase):
         self._h_actions = None
         self._d_actions = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
         self._h_out = None
+        self._h_flag = None
+        self._h_bytes, self._h_calls = 0, 0
 
     # ------------------------------------------------------------------------------------------
     def _obs(self):
@@ -213,7 +215,14 @@ class MazeVectorEnv(_VectorBase):
     def h2d_bytes_per_step(self):
         return self.num_envs
 
+    def reset_host_counters(self):
+        self._h_bytes, self._h_calls = 0, 0
+
     def d2h_bytes_per_step(self):
+        """Average bytes step_host() has copied back per call so far (the target array travels only on the steps
+        whose launch rewrote it); before the first call, the worst case."""
+        if self._h_calls:
+            return self._h_bytes / self._h_calls
         per = 3 * 8 + 8 + 1 + 1
         if self.enrich:
             per += 3 * cabi.WINDOW * cabi.WINDOW * 4 + 2 * 16
@@ -225,9 +234,25 @@ class MazeVectorEnv(_VectorBase):
         b = self.batch
         self.step(actions)
         h = self._host_out()
+        if self._h_flag is None:
+            self._h_flag = torch.ones(1, dtype=torch.int32, pin_memory=True)
+        # `target` changes only when an env's maze does (reset, restart after a win): the kernels raise
+        # batch.target_dirty when they write it, and only then is it copied again
+        self._h_flag.copy_(b.target_dirty, non_blocking=True)
+        nbytes = 4
         for k in h:
-            h[k].copy_(getattr(b, k), non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+            if k != "target":
+                h[k].copy_(getattr(b, k), non_blocking=True)
+                nbytes += h[k].numel() * h[k].element_size()
+        stream = torch.cuda.current_stream(self.device)
+        stream.synchronize()
+        if int(self._h_flag[0]) != 0:
+            b.target_dirty.zero_()
+            h["target"].copy_(b.target, non_blocking=True)
+            nbytes += h["target"].numel() * h["target"].element_size()
+            stream.synchronize()
+        self._h_bytes += nbytes
+        self._h_calls += 1
         obs = {"agent": h["agent"].numpy(), "target": h["target"].numpy(), "best dir": h["best_dir"].numpy()}
         if self.enrich:
             obs.update(agent=h["agent_norm"].numpy(), target=h["target_norm"].numpy(), window=h["window"].numpy())

@@ -194,3 +194,29 @@ def test_vector_env_enrich_and_registry():
     assert h_obs["window"].shape == (64, 3, 15, 15) and h_rew.dtype == np.float64
     mask = venv.get_mask_direction(probs=True)
     assert tuple(mask.shape) == (64, 4)
+
+
+def test_step_host_refreshes_target_only_when_a_maze_changed():
+    """step_host() skips the D2H copy of `target` unless the launch rewrote it (maze_env_batch.target_dirty):
+    the host arrays must still equal the device arrays after every step, through wins and pool cycling."""
+    import maze_b200 as mb
+    B = 64
+    env = mb.MazeVectorEnv(B, shape=(11, 11), num_mazes=16, algorithms=["r-prim", "dfs"], seed=3, on_win="next", stats=True)
+    env.reset()
+    rng = np.random.default_rng(0)
+    copies_with_target = 0
+    for t in range(400):
+        best = env.batch.best_dir.cpu().numpy()
+        a = np.zeros(B, dtype=np.uint8)
+        a[best[:, 0] == 1] = 1; a[best[:, 0] == -1] = 0; a[best[:, 1] == 1] = 3; a[best[:, 1] == -1] = 2
+        rnd = rng.random(B) < 0.1
+        a[rnd] = rng.integers(0, 4, int(rnd.sum()))
+        before = env._h_bytes
+        obs, rew, term, trunc, _ = env.step_host(a)
+        copies_with_target += (env._h_bytes - before) > B * 26 + 4
+        assert np.array_equal(obs["target"], env.batch.target.cpu().numpy()), t
+        assert np.array_equal(obs["agent"], env.batch.agent.cpu().numpy())
+        assert np.array_equal(rew, env.batch.reward.cpu().numpy())
+    wins = env.episode_statistics()["wins"]
+    assert wins > 0 and 0 < copies_with_target < 400     # targets did change, and most steps skipped the copy
+    assert env.d2h_bytes_per_step() < B * 34
