@@ -65,16 +65,11 @@ __device__ __forceinline__ PackedObs encode_obs(const maze_env_batch& b, int e) 
     }
     // float32 of the float64 quotient, like torch.tensor(np.concatenate([...]), dtype=float32)
     const int2 bd = best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, H, W, mz.tor);
-    double v = 0.0;
-    switch (lane) {
-        case 0: v = __ddiv_rn((double)st.r, (double)H); break;
-        case 1: v = __ddiv_rn((double)st.c, (double)W); break;
-        case 2: v = __ddiv_rn((double)(mz.goal & 0xffff), (double)H); break;
-        case 3: v = __ddiv_rn((double)(mz.goal >> 16), (double)W); break;
-        case 4: v = (double)bd.x; break;
-        case 5: v = (double)bd.y; break;
-        default: break;
-    }
+    // one division for the whole warp (lanes 0-3 hold the four quotients): a switch with a __ddiv_rn per case made
+    // the warp run the division subroutine four times
+    const double num = (double)(lane == 0 ? st.r : (lane == 1 ? st.c : (lane == 2 ? (mz.goal & 0xffff) : (mz.goal >> 16))));
+    const double q = __ddiv_rn(num, (double)((lane & 1) ? W : H));
+    const double v = lane < 4 ? q : (lane == 4 ? (double)bd.x : (lane == 5 ? (double)bd.y : 0.0));
     o.vec = (float)v;
     return o;
 }
