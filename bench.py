@@ -128,10 +128,12 @@ def run_reference(args, rank):
     vec = PersistentVector(mazes, cores, "port")
     # Size a 'step' (every worker advances its env by n transitions) so that warm-up + timed steps take about
     # BUDGET_S in total, whatever K and W are: calibrate the per-core rate on a one-second sample first.
-    BUDGET_S = 90.0
+    # Workers advance in lock step like gymnasium's AsyncVectorEnv (a step waits for the slowest env); at least four
+    # transitions per step so that the spread of A* costs between positions does not dominate the sample.
+    BUDGET_S = 120.0
     cal = vec.step(64)
     rate = 64 / cal["seconds"]                                  # transitions per second per worker
-    n = max(1, int(BUDGET_S * rate / max(1, args.steps + args.warmup)))
+    n = max(4, min(256, int(BUDGET_S * rate / max(1, args.steps + args.warmup))))
     for _ in range(args.warmup):
         vec.step(n)
     steps, secs = 0, 0.0
