@@ -108,6 +108,7 @@ extern "C" void maze_ctx_destroy(maze_ctx* ctx) {
     cudaFree(ctx->d_lut_revisit);
     cudaFree(ctx->d_lut_invalid);
     cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_scratch);
     delete ctx;
 }
 

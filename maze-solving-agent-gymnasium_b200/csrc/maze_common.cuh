@@ -20,6 +20,8 @@ struct maze_ctx {
     double h_shaping[4];     // index = (D[prev]-D[cur]) & 3 : 0 -> 0, 1 -> +1, 3 -> -1
     int    num_sms;
     int    step_ept;        // envs per thread of maze_step (tunable: MAZE_STEP_EPT)
+    void*  d_scratch;       // library-owned scratch (candidate wall planes of scored generation), grown on demand
+    size_t scratch_bytes;
     char   err[512];
 };
 

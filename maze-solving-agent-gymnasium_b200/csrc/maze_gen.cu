@@ -62,7 +62,13 @@ struct GenParams {
     double* difficulty;      // [n] optional out: difficulty of the maze kept for item k
     unsigned long long seed;
     long long slot_id_base;
+    // scored bulk generation in two kernels: candidate wall planes drawn by the warp kernel into scratch
+    unsigned long long* planes;   // [n * candidates, PLANE_WORDS] or NULL
+    int item_base;                // first item of this chunk when ids is NULL
 };
+
+// one candidate in scratch: E plane (64 rows), S plane (64 rows), then start / goal cell
+constexpr int PLANE_WORDS = 2 * MAZE_GEN_MAX_CELLS + 2;
 
 // Per-maze random stream: PCG-XSH-RR 64/32 whose state and increment come from one Philox4x32-10
 // block keyed by (seed, global slot id | generation count, candidate).  The key makes streams
@@ -502,6 +508,41 @@ maze_generate_warp_kernel(GenParams p) {
     }
 }
 
+// ---- scored bulk generation, first half: every (slot, candidate) pair is one work item of the warp generator
+// (32 warps per SM hide the dependent-issue latency of carving, which a 4-warp CTA cannot); the walls go to
+// scratch as bit-planes (1 KB per candidate), the CTA kernel then only scores and keeps.
+__global__ void __launch_bounds__(WARP_GEN_THREADS, 4)
+maze_generate_planes_kernel(GenParams p) {
+    const int lane = lane_id();
+    const int total = p.n * p.candidates;
+    for (;;) {
+        int work = 0;
+        if (lane == 0) work = atomicAdd(p.work_counter, 1);
+        work = __shfl_sync(FULL, work, 0);
+        if (work >= total) break;
+        const int item = work / p.candidates, cand = work - item * p.candidates;
+        const int m = p.ids ? p.ids[item] : p.item_base + item;
+        const int32_t* mm = p.meta + (size_t)m * MAZE_META_WORDS;
+        const int H = mm[MAZE_META_H], W = mm[MAZE_META_W], flags = mm[MAZE_META_FLAGS];
+        const bool tor = (flags & MAZE_FLAG_TOROIDAL) != 0;
+        const int Hb = tor ? H + 2 : H, Wb = tor ? W + 2 : W;
+        const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2;
+        if (nr > MAZE_GEN_MAX_CELLS || nc > MAZE_GEN_MAX_CELLS || nr < 1 || nc < 1) continue;   // the CTA kernel reports it
+        Walls w;
+        int si, sj;
+        generate_walls(w, (flags >> 8) & 0xff, nr, nc, p.seed,
+                       (u64)(p.slot_id_base + m) | ((u64)(unsigned)mm[MAZE_META_SPARE] << 40), (unsigned)cand, si, sj);
+        const int goal = select_goal(w, si, sj);
+        unsigned long long* out = p.planes + (size_t)work * PLANE_WORDS;
+        out[lane] = w.e.a0; out[32 + lane] = w.e.a1;
+        out[MAZE_GEN_MAX_CELLS + lane] = w.s.a0; out[MAZE_GEN_MAX_CELLS + 32 + lane] = w.s.a1;
+        if (lane == 0) {
+            out[2 * MAZE_GEN_MAX_CELLS] = (unsigned long long)(unsigned)((si << 8) | sj);
+            out[2 * MAZE_GEN_MAX_CELLS + 1] = (unsigned long long)(unsigned)goal;
+        }
+    }
+}
+
 // second half of unscored toroidal generation: fields of the toroidal slots among the items
 __global__ void __launch_bounds__(FIELD_THREADS)
 maze_fields_toroidal_kernel(GenParams p) {
@@ -550,7 +591,7 @@ maze_generate_kernel(GenParams p) {
     MetricsSmem ms = metrics_smem_carve(keep + keep_bytes, p.smem_cells, f.queue);
 
     for (int item = blockIdx.x; item < n; item += gridDim.x) {
-        const int m = p.ids ? p.ids[item] : item;
+        const int m = p.ids ? p.ids[item] : p.item_base + item;
         int32_t* mm = p.meta + (size_t)m * MAZE_META_WORDS;
         const int H = mm[MAZE_META_H], W = mm[MAZE_META_W];
         const int flags = mm[MAZE_META_FLAGS];
@@ -576,9 +617,19 @@ maze_generate_kernel(GenParams p) {
             Walls w;
             int si = 0, sj = 0, goal = 0;
             if (base + wid < p.candidates) {
-                generate_walls(w, algo, nr, nc, p.seed, (u64)(p.slot_id_base + m) | ((u64)(unsigned)gen_count << 40),
-                               (unsigned)(base + wid), si, sj);
-                goal = select_goal(w, si, sj);
+                if (p.planes) {   // drawn by maze_generate_planes_kernel
+                    const unsigned long long* in = p.planes + ((size_t)item * p.candidates + base + wid) * PLANE_WORDS;
+                    const int lane = tid & 31;
+                    w.e.a0 = in[lane]; w.e.a1 = in[32 + lane];
+                    w.s.a0 = in[MAZE_GEN_MAX_CELLS + lane]; w.s.a1 = in[MAZE_GEN_MAX_CELLS + 32 + lane];
+                    const int sij = (int)in[2 * MAZE_GEN_MAX_CELLS];
+                    si = sij >> 8; sj = sij & 0xff;
+                    goal = (int)in[2 * MAZE_GEN_MAX_CELLS + 1];
+                } else {
+                    generate_walls(w, algo, nr, nc, p.seed, (u64)(p.slot_id_base + m) | ((u64)(unsigned)gen_count << 40),
+                                   (unsigned)(base + wid), si, sj);
+                    goal = select_goal(w, si, sj);
+                }
             }
             GEN_TICK(1);
             for (int k = 0; k < NW && base + k < p.candidates; ++k) {
@@ -681,6 +732,7 @@ extern "C" int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8
     p.difficulty = difficulty;
     p.work_counter = nullptr;
     p.seed = seed; p.slot_id_base = slot_id_base;
+    p.planes = nullptr; p.item_base = 0;
 
     if (!scored) {   // bordered slots: one warp per maze, persistent over the items
         int per_sm = 0;
@@ -713,6 +765,39 @@ extern "C" int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8
     MAZE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GEN_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const int resident = per_sm * sms;
+    // Bulk best-of-k (host-side n, more than a handful of slots): the candidates are drawn by the warp generator
+    // into library-owned scratch, chunk by chunk, and the CTA kernel only scores and keeps.  Regeneration queues
+    // (device-side count, a few slots per step) stay on the single-kernel path.
+    constexpr int CHUNK = 8192;
+    if (scored && candidates > 1 && !count_dev && n >= 16 && !getenv("MAZE_GEN_SINGLE_KERNEL")) {
+        const int chunk = n < CHUNK ? n : CHUNK;
+        const size_t need = (size_t)chunk * candidates * PLANE_WORDS * sizeof(unsigned long long);
+        if (ctx->scratch_bytes < need) {
+            MAZE_CHECK(cudaStreamSynchronize(st));
+            cudaFree(ctx->d_scratch);
+            ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+            MAZE_CHECK(cudaMalloc(&ctx->d_scratch, need));
+            ctx->scratch_bytes = need;
+        }
+        int wper = 0;
+        MAZE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wper, maze_generate_planes_kernel, WARP_GEN_THREADS, 0));
+        if (wper < 1) wper = 1;
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+            GenParams q = p;
+            q.n = n - c0 < chunk ? n - c0 : chunk;
+            q.ids = ids ? ids + c0 : nullptr;
+            q.item_base = c0;
+            q.difficulty = difficulty ? difficulty + c0 : nullptr;
+            q.planes = static_cast<unsigned long long*>(ctx->d_scratch);
+            q.work_counter = ctx->d_counter;
+            MAZE_CHECK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
+            const int want = (q.n * candidates + WARP_GEN_THREADS / 32 - 1) / (WARP_GEN_THREADS / 32);
+            maze_generate_planes_kernel<<<want < wper * sms ? want : wper * sms, WARP_GEN_THREADS, 0, st>>>(q);
+            kernel<<<q.n < resident ? q.n : resident, GEN_THREADS, smem, st>>>(q);
+        }
+        MAZE_CHECK(cudaGetLastError());
+        return 0;
+    }
     kernel<<<n < resident ? n : resident, GEN_THREADS, smem, st>>>(p);
     MAZE_CHECK(cudaGetLastError());
     return 0;
