@@ -194,7 +194,10 @@ int maze_reset(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* mask, void
  *   difficulty optional [n] out: difficulty of the maze kept for ids[k] (NULL with candidates 1
  *             skips the evaluation)
  *   RNG       Philox4x32-10, key = seed, counter = (slot_id_base + slot, generation count,
- *             candidate): results do not depend on how slots are sharded over GPUs. */
+ *             candidate): results do not depend on how slots are sharded over GPUs. *
+ * Bulk best-of-k (candidates > 1, count_dev NULL, n >= 16) runs as two kernels and keeps the candidates'
+ * wall planes in a ctx-owned scratch buffer (<= 8 192 x candidates x 1 KB, allocated on first use, freed by
+ * maze_ctx_destroy); the result is identical to the single-kernel path used for regeneration queues. */
 int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8_t* table, const int32_t* ids,
                   const int32_t* count_dev, int n, int slot, int max_h, int max_w,
                   uint64_t seed, int64_t slot_id_base, int candidates, double* difficulty, void* stream);
