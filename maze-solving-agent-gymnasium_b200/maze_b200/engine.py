@@ -270,8 +270,9 @@ class MazeBatch:
         if sd["visit_layout"] != self.visit_layout or sd["state"].shape != self.state.shape:
             raise ValueError("checkpoint was taken from a batch of another size / visit layout")
         for k in self._CKPT:
-            if getattr(self, k) is not None:
+            if getattr(self, k) is not None and k in sd:
                 getattr(self, k).copy_(sd[k])
+        self.target_dirty.fill_(1)   # host mirrors of `target` must be refreshed after a restore
 
     def _make_struct(self) -> cabi.MazeEnvBatch:
         p = self.pool
