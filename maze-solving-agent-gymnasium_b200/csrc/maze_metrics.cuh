@@ -24,7 +24,7 @@ struct MetricsSmem {
     double* bsum;             // [cells] branch complexity by branch key
 };
 
-constexpr int MF_NB = 0x07, MF_TURN = 0x08, MF_SOL = 0x10, MF_NODE = 0x20, MF_DP = 0x40;
+constexpr int MF_NB = 0x07, MF_TURN = 0x08, MF_SOL = 0x10, MF_NODE = 0x20, MF_PDIR_SHIFT = 6;   // bits 6-7: parent direction
 
 // The four u16 arrays (8 bytes per cell) live in the BFS queue of FieldSmem, which is dead once
 // the distances from start exist (2 * H * W bytes > 8 * cells); the rest is carved from `base`.
@@ -48,17 +48,18 @@ __device__ inline MetricsSmem metrics_smem_carve(unsigned char* base, int cells,
     return m;
 }
 
-// 16-bit atomic min on shared memory (two cells share a 32-bit word)
-__device__ __forceinline__ void atomic_min_u16(unsigned short* p, unsigned short v) {
+// 16-bit atomic min on shared memory (two cells share a 32-bit word); true if v was stored, false if the
+// cell already held something <= v
+__device__ __forceinline__ bool atomic_min_u16(unsigned short* p, unsigned short v) {
     unsigned int* w = reinterpret_cast<unsigned int*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
     const bool hi = (reinterpret_cast<uintptr_t>(p) & 2) != 0;
     unsigned int old = *w;
     for (;;) {
         const unsigned short cur = hi ? (unsigned short)(old >> 16) : (unsigned short)(old & 0xffffu);
-        if (cur <= v) return;
+        if (cur <= v) return false;
         const unsigned int repl = hi ? ((old & 0x0000ffffu) | ((unsigned int)v << 16)) : ((old & 0xffff0000u) | v);
         const unsigned int seen = atomicCAS(w, old, repl);
-        if (seen == old) return;
+        if (seen == old) return true;
         old = seen;
     }
 }
@@ -112,8 +113,16 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
         const int up = f.grid[b - Wb] != 0, dn = f.grid[b + Wb] != 0, lf = f.grid[b - 1] != 0, rt = f.grid[b + 1] != 0;
         const int nb = up + dn + lf + rt;
         const int turn = (nb == 2) && !((up && dn) || (lf && rt));
-        const int node = ((nb != 2) || turn || ci == start_c) && f.dist[b] != DIST_INF;   // unreachable cells play no part
-        ms.flags[ci] = (uint8_t)(nb | (turn ? MF_TURN : 0) | (node ? MF_NODE : 0));
+        const int d = f.dist[b];
+        const int node = ((nb != 2) || turn || ci == start_c) && d != DIST_INF;   // unreachable cells play no part
+        // direction of the tree parent (the open neighbour one block closer to start; the last match in the
+        // order up, down, left, right, as the sequential walks used to pick it), kept in the two top flag bits
+        int pdir = 0;
+        if (up && (int)f.dist[b - Wb] == d - 1) pdir = 0;
+        if (dn && (int)f.dist[b + Wb] == d - 1) pdir = 1;
+        if (lf && (int)f.dist[b - 1] == d - 1) pdir = 2;
+        if (rt && (int)f.dist[b + 1] == d - 1) pdir = 3;
+        ms.flags[ci] = (uint8_t)(nb | (turn ? MF_TURN : 0) | (node ? MF_NODE : 0) | (pdir << MF_PDIR_SHIFT));
         ms.dsum[ci] = 0u;
         ms.ssum[ci] = 0.0;
         ms.bsum[ci] = 0.0;
@@ -144,11 +153,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
             junctions += nbc == 3;   // calculate_J :39-53
             crossings += nbc == 4;   // calculate_CR :55-69
             if (b == start_idx) break;
-            const int d = f.dist[b];
-            int step = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (f.grid[b + offs[k]] != 0 && (int)f.dist[b + offs[k]] == d - 1) step = offs[k];
+            const int step = offs[ms.flags[ci] >> MF_PDIR_SHIFT];
             if (arrived != 0 && arrived != step) ++turns;   // calculate_T :28-37 (interior blocks only; passages are straight)
             arrived = step;
             b += 2 * step;   // passage block, then the next cell
@@ -163,11 +168,7 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
     for (int ci = tid; ci < cells; ci += nthr) {
         if (!(ms.flags[ci] & MF_NODE) || ci == start_c) continue;
         int b = cell_block(ci);
-        const int d = f.dist[b];
-        int step = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (f.grid[b + offs[k]] != 0 && (int)f.dist[b + offs[k]] == d - 1) step = offs[k];
+        const int step = offs[ms.flags[ci] >> MF_PDIR_SHIFT];
         int hops = 0, pc;
         do {
             b += 2 * step;
@@ -334,9 +335,13 @@ __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, i
     // ---- 5. smallest dead-end rank below every off-solution node (adjacency order of the reference)
     for (int ci = tid; ci < cells; ci += nthr) {
         if (!is_dead_end_off(ci)) continue;
+        // A walk stops at the first node that already holds a smaller rank: the dead end that put it there is
+        // on its own way up and covers every ancestor (the smallest rank of a subtree never meets a smaller one
+        // inside it, so it always reaches the subtree's root).  Without the early exit every walk hammered the
+        // same few nodes next to the solution with CAS loops (22 % of the kernel on r-prim mazes).
         int y = ci;
         while (!is_sol(y)) {
-            atomic_min_u16(ms.minleaf + y, (unsigned short)ci);
+            if (!atomic_min_u16(ms.minleaf + y, (unsigned short)ci)) break;
             y = ms.pnode[y];
         }
     }
