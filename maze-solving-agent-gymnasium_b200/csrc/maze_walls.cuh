@@ -71,16 +71,21 @@ __device__ __forceinline__ void walls_from_grid(const uint8_t* grid, int Wb, int
 // Block distances from cell (si, sj) written into dist[] (pitch Wb) for every cell reached and for
 // the passage block it was reached through; everything else must hold DIST_INF already.  One
 // bit-parallel level per cell distance: 2 * level for cells, 2 * level - 1 for the passage.
+// (Tried: a corridor fast path that follows a singleton frontier in the shared-memory grid without shuffles. The
+// frontier of a dfs maze is rarely exactly one cell -- side branches keep it at two to four -- so it lost 5 %.)
 __device__ __forceinline__ void cell_bfs_distances(const Walls& w, int si, int sj, unsigned short* dist, int Wb) {
     const int lane = lane_id();
     u64 f0 = 0ull, f1 = 0ull;
     if ((si & 31) == lane) { if (si >> 5) f1 = 1ull << sj; else f0 = 1ull << sj; }
     u64 v0 = f0, v1 = f1;
     if (lane == 0) dist[(2 * si + 1) * Wb + 2 * sj + 1] = 0;
-    auto scatter = [&](u64 bits, int row, int off, int level) {   // off: block offset from the cell to its parent-side passage
+    // one pass over the newly reached cells of a row; a cell reached from several sides at once (mazes with
+    // cycles) keeps the first source in the order left, right, above, below
+    auto scatter = [&](u64 bits, u64 l, u64 r, u64 a, int row, int level) {
         while (bits) {
             const int j = __ffsll((long long)bits) - 1;
             bits &= bits - 1;
+            const int off = ((l >> j) & 1ull) ? -1 : (((r >> j) & 1ull) ? 1 : (((a >> j) & 1ull) ? -Wb : Wb));
             const int b = (2 * row + 1) * Wb + 2 * j + 1;
             dist[b] = (unsigned short)(2 * level);
             dist[b + off] = (unsigned short)(2 * level - 1);
@@ -91,16 +96,8 @@ __device__ __forceinline__ void cell_bfs_distances(const Walls& w, int si, int s
         bfs_expand(w, f0, f1, x);
         const u64 n0 = (x.l0 | x.r0 | x.a0 | x.b0) & ~v0, n1 = (x.l1 | x.r1 | x.a1 | x.b1) & ~v1;
         if (!__ballot_sync(FULL, (n0 | n1) != 0ull)) break;
-        // a cell reached from several sides at once (mazes with cycles) keeps the first source listed
-        u64 t0 = n0, t1 = n1;
-        scatter(t0 & x.l0, lane, -1, level);       t0 &= ~x.l0;
-        scatter(t0 & x.r0, lane, 1, level);        t0 &= ~x.r0;
-        scatter(t0 & x.a0, lane, -Wb, level);      t0 &= ~x.a0;
-        scatter(t0 & x.b0, lane, Wb, level);
-        scatter(t1 & x.l1, lane + 32, -1, level);  t1 &= ~x.l1;
-        scatter(t1 & x.r1, lane + 32, 1, level);   t1 &= ~x.r1;
-        scatter(t1 & x.a1, lane + 32, -Wb, level); t1 &= ~x.a1;
-        scatter(t1 & x.b1, lane + 32, Wb, level);
+        scatter(n0, x.l0, x.r0, x.a0, lane, level);
+        scatter(n1, x.l1, x.r1, x.a1, lane + 32, level);
         v0 |= n0; v1 |= n1; f0 = n0; f1 = n1;
     }
     __syncwarp();
