@@ -43,7 +43,7 @@ extern "C" int maze_debug_gen_profile(unsigned long long* out, int reset) {
 
 namespace {
 
-constexpr int GEN_THREADS = FIELD_THREADS;   // CTA-per-maze kernel
+constexpr int GEN_THREADS = METRIC_THREADS;   // CTA-per-maze kernel (scores with maze_metrics)
 constexpr int WARP_GEN_THREADS = 256;        // warp-per-maze kernel: 8 mazes per CTA
 
 struct GenParams {

@@ -16,7 +16,7 @@ extern "C" int maze_debug_metrics_profile(unsigned long long* out, int reset) {
 
 namespace {
 
-__global__ void __launch_bounds__(FIELD_THREADS)
+__global__ void __launch_bounds__(METRIC_THREADS)
 maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restrict__ meta,
                        const int32_t* __restrict__ ids, int n, int slot, int smem_hw, int smem_cells,
                        double* __restrict__ out, double* __restrict__ ext_out) {
@@ -34,7 +34,7 @@ maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restr
         const int Hb = H + 2 * pad, Wb = W + 2 * pad;
         const uint8_t* g = grids + (size_t)m * slot;
         __syncthreads();
-        for (int i = tid; i < Hb * Wb; i += FIELD_THREADS) {
+        for (int i = tid; i < Hb * Wb; i += METRIC_THREADS) {
             const int r = i / Wb - pad, c = i % Wb - pad;
             f.grid[i] = (r >= 0 && r < H && c >= 0 && c < W) ? g[r * W + c] : 0;
         }
@@ -48,7 +48,7 @@ maze_difficulty_kernel(const uint8_t* __restrict__ grids, const int32_t* __restr
         // cell distance, whatever the frontier size); lattices above 64 x 64 cells use the CTA-wide BFS
         const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2;
         if (nr <= MAZE_GEN_MAX_CELLS && nc <= MAZE_GEN_MAX_CELLS && (start_idx / Wb & 1) && (start_idx % Wb & 1)) {
-            for (int i = tid; i < Hb * Wb; i += FIELD_THREADS) f.dist[i] = DIST_INF;
+            for (int i = tid; i < Hb * Wb; i += METRIC_THREADS) f.dist[i] = DIST_INF;
             __syncthreads();
             if (tid < 32) {
                 Walls w;
@@ -90,10 +90,10 @@ static int launch_difficulty(maze_ctx* ctx, const uint8_t* grids, const int32_t*
     const size_t smem = field_smem_bytes(smem_hw) + metrics_smem_bytes(smem_cells);
     MAZE_CHECK(cudaFuncSetAttribute(maze_difficulty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MAZE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, maze_difficulty_kernel, FIELD_THREADS, smem));
+    MAZE_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, maze_difficulty_kernel, METRIC_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const int resident = per_sm * (ctx->num_sms > 0 ? ctx->num_sms : 148);
-    maze_difficulty_kernel<<<n < resident ? n : resident, FIELD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+    maze_difficulty_kernel<<<n < resident ? n : resident, METRIC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
         grids, meta, ids, n, slot, smem_hw, smem_cells, out, ext_out);
     MAZE_CHECK(cudaGetLastError());
     return 0;

@@ -83,7 +83,7 @@ struct MazeMetrics {
 // (metrics_calculator.py:18-69,175-244), bit-identical: same divisions, sums in row-major dead-end order.
 __device__ inline void maze_metrics(const FieldSmem& f, const MetricsSmem& ms, int Hb, int Wb,
                                     int start_idx, int goal_idx, MazeMetrics& out, bool with_kc = true, bool ext = false) {
-    __shared__ double s_D0, s_S0, s_red[2][FIELD_THREADS / 32];
+    __shared__ double s_D0, s_S0, s_red[2][METRIC_THREADS / 32];
     __shared__ int s_dcount, s_sol_counts[3], s_open, s_de_counts[3];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int nr = (Hb - 1) / 2, nc = (Wb - 1) / 2, cells = nr * nc;
