@@ -130,7 +130,7 @@ def run_reference(args, rank):
     # BUDGET_S in total, whatever K and W are: calibrate the per-core rate on a one-second sample first.
     # Workers advance in lock step like gymnasium's AsyncVectorEnv (a step waits for the slowest env); at least four
     # transitions per step so that the spread of A* costs between positions does not dominate the sample.
-    BUDGET_S = 120.0
+    BUDGET_S = float(os.environ.get("MAZE_REF_BUDGET_S", "120"))   # (tests shrink it)
     cal = vec.step(64)
     rate = 64 / cal["seconds"]                                  # transitions per second per worker
     n = max(4, min(256, int(BUDGET_S * rate / max(1, args.steps + args.warmup))))

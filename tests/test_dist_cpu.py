@@ -63,3 +63,27 @@ def test_reduce_is_identity_without_a_process_group():
     assert torch.equal(mdist.reduce_statistics(v), v)
     with pytest.raises(ValueError):
         mdist.reduce_statistics(torch.zeros(4, dtype=torch.float64))
+
+
+def test_reference_arm_of_the_bench_runs_without_a_gpu():
+    """`bench.py --impl reference` is the CPU arm the driver runs beside ours: it must work on a box
+    without a GPU, print exactly one JSON line with the contract keys, and honour its time budget."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MAZE_REF_BUDGET_S="2")
+    t0 = time.time()
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["steps"] == 3 and d["warmup"] == 1 and d["gpu_launches"] == 0
+    assert time.time() - t0 < 120
