@@ -56,37 +56,39 @@ maze_window_kernel(maze_env_batch b, float* __restrict__ window, double* __restr
             const uint64_t pol_table = l2_policy<MAZE_TABLE_POLICY>();
             const uint16_t* vbase = b.visits + (size_t)e * b.visit_env_stride;
             const int wt = (W + 3) >> 2;
-            // Table byte and visit word of all (up to eight) blocks of a lane are requested together.  The visit
-            // word is fetched whether or not the block is open: a window row is 30 contiguous bytes of the
-            // env-major visit array, so the sectors are the same and one dependent round trip disappears.
-            constexpr int K = (WIN_CELLS + 31) / 32;
+            // Lane -> window block mapping: lanes 0-14 take the columns of an even window row, lanes 16-30 those of
+            // the odd row below it, eight row pairs per lane (lanes 15 / 31 and row 15 are idle: 225 of 256 slots).
+            // The column part of every index is then fixed per lane and the row part is a compile-time step, so the
+            // loop body is a handful of integer instructions around its two loads (the kernel is issue-bound).
+            // Table byte and visit word of all eight blocks are requested before any is used; the visit word is
+            // fetched whether or not the block is open (same sectors, one dependent round trip less).
+            constexpr int K = (WIN + 1) / 2;
+            const int half = lane >> 4, col = min(lane & 15, WIN - 1);
+            const bool col_ok = (lane & 15) < WIN;
+            int cc = c0 + col;
+            if (tor) cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);   // extract_submaze_toroid: (position + i - k) % maze_shape
+            const int cpart = kTiled ? (((cc >> 2) << 4) | (cc & 3)) : cc;
             int idxs[K], tb[K];
             unsigned vis[K];
-            int wr = lane / WIN, wc = lane - wr * WIN;   // window row / column of block i = 32 k + lane
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                int rr = r0 + min(wr, WIN - 1), cc = c0 + wc;   // (lanes past block 224 re-read the last row)
-                if (tor) {   // extract_submaze_toroid: (position + i - k) % maze_shape
-                    rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
-                    cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
-                }
+                int rr = r0 + min(2 * k + half, WIN - 1);
+                if (tor) rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
                 idxs[k] = rr * W + cc;
                 tb[k] = pol_load_nc<MAZE_TABLE_POLICY>(tab + idxs[k], pol_table);
-                const int vi = kTiled ? ((((rr >> 2) * wt + (cc >> 2)) << 4) | ((rr & 3) << 2) | (cc & 3)) : idxs[k];
+                const int vi = kTiled ? ((((rr >> 2) * wt) << 4) | ((rr & 3) << 2)) + cpart : idxs[k];
                 vis[k] = __ldcs(kUnit ? vbase + vi : vbase + (size_t)vi * b.visit_cell_stride);
-                wr += 2; wc += 2;                                // 32 = 2 * 15 + 2
-                if (wc >= WIN) { wc -= WIN; wr += 1; }
             }
+            uint8_t* sl = so + half * WIN + col;   // block (row 2 k + half, col) is output index 30 k + half * 15 + col
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const int i = k * 32 + lane;
-                if (i >= WIN_CELLS) break;
+                if (!col_ok || 2 * k + half >= WIN) continue;
                 const bool open = (tb[k] & MAZE_TAB_OPEN) != 0;
                 // non_visited (base_maze_env.py:148-149,183-184): open, not the start, no visit in this episode
                 const bool fresh = open && idxs[k] != start_idx && !((int)(vis[k] >> 8) == st.epoch && (vis[k] & 0xffu) != 0);
-                so[i] = open ? 0 : 1;                                        // maze == 0
-                so[WIN_CELLS + i] = (open && idxs[k] != goal_idx) ? 1 : 0;   // maze == 1
-                so[2 * WIN_CELLS + i] = fresh ? 1 : 0;
+                sl[2 * WIN * k] = open ? 0 : 1;                                          // maze == 0
+                sl[WIN_CELLS + 2 * WIN * k] = (open && idxs[k] != goal_idx) ? 1 : 0;     // maze == 1
+                sl[2 * WIN_CELLS + 2 * WIN * k] = fresh ? 1 : 0;
             }
         }
         if (lane < 2) {
