@@ -72,3 +72,54 @@ def test_extended_kim_crawfis_metrics_match_reference(golden_metrics, row):
     for k, v in row.items():
         if k != "id":
             assert got[k] == v, k
+
+
+def _dead_end_fixpoint(grid, start, goal):
+    """The parallel formulation maze_difficulty uses for the order-dependent part of calculate_DE
+    (csrc/maze_metrics.cuh, step 4c), in plain Python: iterate `counted` from all-true until nothing changes."""
+    from oracle.metrics import _Tree
+    t = _Tree(grid, start, goal)
+    sol_len = len(t.sol)
+    chains = []
+    for de in t.dead_ends_off_solution():
+        path = t.path_to_start(de)
+        for i in range(1, sol_len - 1):
+            if t.on_sol[path[i]]:
+                path = path[:i]
+                break
+        chains.append([p for p in path[1:-1] if t.nb[p] > 2])
+    n, counted, rounds = len(chains), [True] * len(chains), 0
+    while True:
+        rounds += 1
+        rec = {}
+        for i in range(n):
+            if counted[i] and chains[i]:
+                rec[chains[i][0]] = min(rec.get(chains[i][0], n), i)
+        new = [not any(rec.get(p, n) < i for p in chains[i]) for i in range(n)]
+        if new == counted:
+            return sum(counted), rounds
+        counted = new
+
+
+def test_dead_end_count_as_a_fixpoint_equals_the_sequential_rule():
+    """The reference decides dead end by dead end, in row-major order, whether it counts (metrics_calculator.py:
+    100-127).  The kernel solves the same rule as a fixpoint; both must agree on every maze, and the number of
+    rounds stays small."""
+    import random
+    from oracle.generation import gen_maze
+    rng = random.Random(5)
+    worst = 0
+    for k in range(45):
+        S = rng.choice([11, 21, 41])
+        algo = rng.choice(["r-prim", "dfs", "prim&kill"])
+        start, goal, grid = gen_maze((S, S), algo, rng)
+        got, rounds = _dead_end_fixpoint(grid, start, goal)
+        assert got == kim_crawfis(grid, start, goal)["dead_end_count"], (S, algo)
+        worst = max(worst, rounds)
+    z, meta = load_golden("metrics")
+    for m in meta:
+        if not m["no_border"] and m["shape"] <= 61:
+            got, rounds = _dead_end_fixpoint(z[f"m{m['id']}_grid"], m["start"], m["goal"])
+            assert got / m["sol_len"] == pytest.approx(m["DE"], rel=1e-12), m["id"]
+            worst = max(worst, rounds)
+    assert worst <= 6
