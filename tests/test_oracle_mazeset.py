@@ -50,3 +50,28 @@ def test_file_round_trip(tmp_path, fmt):
     assert fmt2 == fmt and np.array_equal(metas2, metas)
     for (g, _), back in zip(rows, grids):
         assert np.array_equal(back, g)
+
+
+def test_product_loader_rejects_bad_files_before_touching_the_gpu(tmp_path):
+    """maze_b200.mazeset.load validates magic / version / format / length on the host (ValueError), and
+    packed_stride knows both record sizes; none of this needs a device."""
+    import struct
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "maze-solving-agent-gymnasium_b200"))
+    from maze_b200 import mazeset
+    assert mazeset.packed_stride((81, 81), "bitmap") == 821 and mazeset.packed_stride((81, 81), "walls") == 800
+    with pytest.raises(ValueError):
+        mazeset.packed_stride((81, 81), "rle")
+    good_header = struct.pack("<8s6I", b"MAZEB200", 1, 0, 1, 11, 11, 16)
+    cases = {
+        "magic": struct.pack("<8s6I", b"NOTAMAZE", 1, 0, 1, 11, 11, 16) + bytes(32 + 16),
+        "version": struct.pack("<8s6I", b"MAZEB200", 9, 0, 1, 11, 11, 16) + bytes(32 + 16),
+        "format": struct.pack("<8s6I", b"MAZEB200", 1, 5, 1, 11, 11, 16) + bytes(32 + 16),
+        "length": good_header + bytes(10),
+    }
+    for name, blob in cases.items():
+        path = tmp_path / f"{name}.mzs"
+        path.write_bytes(blob)
+        with pytest.raises(ValueError):
+            mazeset.load(str(path))
