@@ -61,21 +61,33 @@ def _persistent_worker(conn, kind, grid, start, goal, toroidal, seed):
     rng = np.random.default_rng(seed)
     env.reset()
     while True:
-        n = conn.recv()
-        if n is None:
+        cmd = conn.recv()
+        if cmd is None:
             break
+        kind_, arg = cmd
         t0 = time.perf_counter()
-        for a in rng.integers(0, 4, n):
-            _, _, trunc, term, _ = env.step(int(a))
-            if trunc or term:
-                env.reset()
-        conn.send(time.perf_counter() - t0)
+        n = 0
+        if kind_ == "count":          # exactly `arg` transitions
+            for a in rng.integers(0, 4, arg):
+                _, _, trunc, term, _ = env.step(int(a))
+                if trunc or term:
+                    env.reset()
+            n = int(arg)
+        else:                         # "time": as many transitions as fit into `arg` seconds
+            deadline = t0 + arg
+            while True:
+                _, _, trunc, term, _ = env.step(int(rng.integers(0, 4)))
+                n += 1
+                if trunc or term:
+                    env.reset()
+                if time.perf_counter() >= deadline:
+                    break
+        conn.send((n, time.perf_counter() - t0))
 
 
 class PersistentVector:
-    """One long-lived worker process per core, each owning one env (the AsyncVectorEnv shape): `step(n)`
-    advances every env by n transitions and returns the slowest worker's time, so a bench 'step' can be
-    a small bounded sample without paying a process spawn each time."""
+    """One long-lived worker process per core, each owning one env, so that a bench 'step' can be a small
+    bounded sample without paying a process spawn each time."""
 
     def __init__(self, mazes, workers=None, kind="port"):
         self.workers = workers or os.cpu_count() or 1
@@ -91,11 +103,19 @@ class PersistentVector:
             self.procs.append(p)
 
     def step(self, n):
+        """Lock step (the AsyncVectorEnv shape): every env advances by exactly n transitions."""
+        return self._run(("count", int(n)))
+
+    def run_for(self, seconds):
+        """Free running: every worker steps its env for `seconds` of wall time (no waiting for the slowest env)."""
+        return self._run(("time", float(seconds)))
+
+    def _run(self, cmd):
         t0 = time.perf_counter()
         for c in self.conns:
-            c.send(int(n))
-        worker_s = max(c.recv() for c in self.conns)
-        return dict(steps=int(n) * self.workers, seconds=time.perf_counter() - t0, slowest_worker_seconds=worker_s)
+            c.send(cmd)
+        res = [c.recv() for c in self.conns]
+        return dict(steps=sum(r[0] for r in res), seconds=time.perf_counter() - t0, slowest_worker_seconds=max(r[1] for r in res))
 
     def close(self):
         for c in self.conns:
