@@ -96,7 +96,8 @@ typedef struct maze_env_batch {
     uint16_t* visits;      /* epoch << 8 | saturating visit count of (block idx, env e) at
                               idx * visit_cell_stride + e * visit_env_stride: cell-major
                               [slot, B] (strides B, 1) for the -v0 step; env-major [B, slot]
-                              (strides 1, slot) when the 15x15 window is read every step      */
+                              (strides 1, slot), best with visit_tiled = 1, when the 15x15
+                              window is read every step or several steps fuse into a launch   */
     /* outputs of step / reset (reference obs dict of base_maze_env.py:116-122) */
     int32_t*  agent;       /* [B, 2] int32                                                   */
     int32_t*  target;      /* [B, 2]                                                         */
