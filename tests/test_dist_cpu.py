@@ -87,3 +87,23 @@ def test_reference_arm_of_the_bench_runs_without_a_gpu():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["steps"] == 3 and d["warmup"] == 1 and d["gpu_launches"] == 0
     assert time.time() - t0 < 120
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """The driver launches the reference arm like ours (torchrun, N ranks): rank 0 alone measures and prints,
+    the other ranks exit 0 without work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MAZE_REF_BUDGET_S="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(root, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
