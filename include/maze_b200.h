@@ -297,8 +297,9 @@ int maze_q_rollout(maze_ctx* ctx, const maze_env_batch* b, const maze_q_agent* a
  * (epsilon-greedy whose exploration draws from get_mask_direction(probs=True)), and the state the
  * trainer builds from the -v1 observation (lib/trainers/off_policy_trainer.py:153-171):
  * state = (float32[6] = agent / shape, target / shape, best dir ; float32[3, 15, 15] window).
- * The ring keeps windows BIT-PACKED (3 channels x 8 words of 32 blocks = 96 B instead of 2 700 B)
- * and unpacks them when a batch is sampled. */
+ * The ring keeps windows BIT-PACKED (3 channels x 8 words = 96 B instead of 2 700 B; word k of a
+ * channel holds window rows 2 k in bits 0-14 and 2 k + 1 in bits 16-30) and unpacks them when a
+ * batch is sampled. */
 #define MAZE_WINDOW_WORDS 24   /* 3 channels x 8 uint32 (225 of 256 bits used per channel)        */
 typedef struct maze_replay {
     int64_t   capacity;     /* transitions in the ring                                            */

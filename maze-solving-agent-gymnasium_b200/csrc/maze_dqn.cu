@@ -4,7 +4,7 @@
 // lib/trainers/off_policy_trainer.py:153-171.
 //
 // A -v1 observation is 6 floats + a 3 x 15 x 15 window of {0, 1}: the window is kept as 24 words
-// (one ballot per 32 blocks and channel), so a transition costs 2 x (24 + 96) + 5 = 245 B of HBM
+// (one ballot per two window rows and channel), so a transition costs 2 x (24 + 96) + 5 = 245 B of HBM
 // instead of 5.5 KB, and a 1 M-transition ring fits in 245 MB.
 #include "maze_env.cuh"
 
@@ -39,16 +39,19 @@ __device__ __forceinline__ PackedObs encode_obs(const maze_env_batch& b, int e) 
     }
     PackedObs o;
     o.word = 0;
+    // Lane -> window block: lanes 0-14 take the columns of window row 2 k, lanes 16-30 those of row 2 k + 1 (lanes
+    // 15 / 31 and row 15 are idle), so word k of a channel holds two window rows and the column part of every index
+    // is fixed per lane (the kernel is issue-bound: per-block div / mod and index arithmetic were half of it).
+    const int half = lane >> 4, col = lane & 15;
+    const bool col_ok = ok && col < WIN;
+    int cc = c0 + min(col, WIN - 1);
+    if (mz.tor) cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
 #pragma unroll
-    for (int k = 0; k < (WIN_CELLS + 31) / 32; ++k) {
-        const int i = k * 32 + lane;
+    for (int k = 0; k < (WIN + 1) / 2; ++k) {
         bool wall = false, floor = false, fresh = false;
-        if (ok && i < WIN_CELLS) {
-            int rr = r0 + i / WIN, cc = c0 + i % WIN;
-            if (mz.tor) {
-                rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
-                cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
-            }
+        if (col_ok && 2 * k + half < WIN) {
+            int rr = r0 + 2 * k + half;
+            if (mz.tor) rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
             const int idx = rr * W + cc;
             const bool open = (__ldg(mz.tab + idx) & MAZE_TAB_OPEN) != 0;
             wall = !open;
@@ -122,8 +125,8 @@ __device__ __forceinline__ void unpack_window(const uint32_t* __restrict__ words
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const unsigned word = __shfl_sync(FULL, w, ch * 8 + k);
-            const int i = k * 32 + lane;
-            if (i < WIN_CELLS) __stcs(out + ch * WIN_CELLS + i, (float)((word >> lane) & 1u));
+            const int row = 2 * k + (lane >> 4), col = lane & 15;   // word k = window rows 2 k (bits 0-14) and 2 k + 1 (bits 16-30)
+            if (row < WIN && col < WIN) __stcs(out + ch * WIN_CELLS + row * WIN + col, (float)((word >> lane) & 1u));
         }
     }
 }

@@ -90,7 +90,9 @@ def unpack_windows(words: torch.Tensor) -> torch.Tensor:
     n = words.shape[0]
     w = words.view(n, 3, 8, 1).to(torch.int64) & 0xffffffff
     bits = (w >> torch.arange(32, device=words.device).view(1, 1, 1, 32)) & 1
-    return bits.reshape(n, 3, 256)[:, :, :cabi.WINDOW * cabi.WINDOW].reshape(n, 3, cabi.WINDOW, cabi.WINDOW).to(torch.float32)
+    # word k of a channel = window rows 2 k (bits 0-14) and 2 k + 1 (bits 16-30)
+    rows = bits.reshape(n, 3, 16, 16)[:, :, :cabi.WINDOW, :cabi.WINDOW]
+    return rows.to(torch.float32).contiguous()
 
 
 class MaskedEpsilonGreedy:
