@@ -6,14 +6,13 @@ from oracle.env_port import ClosedFormEnv, MazeTables, PortEnv
 from oracle.grid import ACTIONS, astar_len, bfs_dist, best_dir_vector
 
 
-def _replay(env_cls, z, m, max_shape=10**9):
+def _replay(env_cls, z, m, one_tape_above=10**9):
     i = m["id"]
-    if m["shape"] > max_shape:
-        pytest.skip("too slow for the A* port")
     toroidal = m["topology"] == "torus"
     env = env_cls(z[f"m{i}_grid"], m["start"], m["goal"], toroidal=toroidal, enrich=m["enrich"])
     assert env.max_steps == m["max_steps"]
-    for j in m["tapes"]:
+    tapes = m["tapes"] if m["shape"] <= one_tape_above else m["tapes"][:1]   # A* per step: keep the large mazes short
+    for j in tapes:
         pre = f"m{i}_t{j}_"
         obs, info = env.reset()
         T = len(z[pre + "action"])
@@ -51,7 +50,8 @@ def test_closed_form_env_matches_reference(golden_steps, m):
 
 @pytest.mark.parametrize("m", _metas(), ids=lambda m: f"{m['topology']}-{m['algo']}-{m['shape']}{'-v1' if m['enrich'] else ''}")
 def test_port_env_matches_reference(golden_steps, m):
-    _replay(PortEnv, golden_steps[0], m, max_shape=21)
+    # every shape, 81 x 81 included: this port is what bench.py times as the reference arm / cpu_baseline
+    _replay(PortEnv, golden_steps[0], m, one_tape_above=21)
 
 
 def test_best_dir_table_matches_reference(golden_bestdir):
