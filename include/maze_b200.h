@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 10
+#define MAZE_ABI_VERSION 11
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -80,6 +80,31 @@ extern "C" {
 #define MAZE_STEP_AUTORESET   0x01 /* gymnasium next-step autoreset                          */
 #define MAZE_STEP_WIN_NEXT    0x02 /* on autoreset after a win move to maze (m + stride) % M */
 #define MAZE_STEP_WIN_QUEUE   0x04 /* on a win append the env's maze slot to the regen queue */
+#define MAZE_STEP_PACKED      0x08 /* also write one packed uint32 record per env to batch.packed   */
+#define MAZE_STEP_NO_WIDE     0x10 /* with MAZE_STEP_PACKED: skip agent / best_dir / reward / terminated /
+                                      truncated (the record holds the same information in 4 bytes
+                                      instead of 26; `target` is still written when it changes)  */
+
+/* Packed step record (MAZE_STEP_PACKED): everything base_maze_env.py:116-122,210 returns for one env except
+ * `target` (which changes only with the maze), bit-exactly recoverable on the host:
+ *   bits 0-7 row | 8-15 col | 16-18 best-next code (0..3 = action towards the best neighbour, 4 = none;
+ *   best dir = agent - wrapped neighbour) | 19 terminated | 20 truncated | 21-22 reward kind | 23-30 reward index
+ * reward = maze_reward_lut(kind)[index] for kind 0 (revisit), 1 (invalid move), 2 (shaping: index 0 farther,
+ * 1 same, 2 closer); kind 3: index 0 -> 0.0 (reset step), 1 -> 1.0 (goal), 2 -> -1.0 (truncation).
+ * maze_step_decode_host turns records back into the wide arrays. */
+#define MAZE_REC_CODE_SHIFT   16
+#define MAZE_REC_TERM_SHIFT   19
+#define MAZE_REC_TRUNC_SHIFT  20
+#define MAZE_REC_KIND_SHIFT   21
+#define MAZE_REC_INDEX_SHIFT  23
+#define MAZE_REC_KIND_REVISIT 0
+#define MAZE_REC_KIND_INVALID 1
+#define MAZE_REC_KIND_SHAPING 2
+#define MAZE_REC_KIND_CONST   3
+#define MAZE_REC_CONST_ZERO      0
+#define MAZE_REC_CONST_ONE       1
+#define MAZE_REC_CONST_MINUS_ONE 2
+#define MAZE_REC_REWARD(kind, index) (((uint32_t)(kind) << MAZE_REC_KIND_SHIFT) | ((uint32_t)(index) << MAZE_REC_INDEX_SHIFT))
 
 typedef struct maze_ctx maze_ctx;
 
@@ -122,10 +147,11 @@ typedef struct maze_env_batch {
                               target only changes when its maze does -- maze_reset, or the restart after a win --
                               so maze_step rewrites `target` only then, and a host mirror of the outputs can skip
                               the device-to-host copy of `target` on all other steps                       */
+    uint32_t* packed;      /* optional [B] (may be NULL): packed step records, written under MAZE_STEP_PACKED        */
 } maze_env_batch;
 
 /* sizeof of the ABI structs as this library was compiled (a binding checks its own layout against it):
- * which = 0 maze_env_batch, 1 maze_q_agent, 2 maze_replay, 3 maze_step_trace; -1 for anything else. */
+ * which = 0 maze_env_batch, 1 maze_q_agent, 2 maze_replay, 3 maze_step_trace, 4 maze_dqn_net; -1 for anything else. */
 int  maze_sizeof(int which);
 
 int  maze_abi_version(void);
@@ -153,6 +179,20 @@ int maze_fields(maze_ctx* ctx, const uint8_t* grids, int32_t* meta, uint8_t* tab
  * of lib/maze_view.py:167-180 / :184-197, plus the observation of :116-122.
  * actions [B] uint8 in 0..3. */
 int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* actions, uint32_t mode, void* stream);
+
+/* HOST-side decode of n packed step records (plain C loop, no GPU): fills the wide arrays maze_step writes --
+ * agent [n, 2] int32, best_dir [n, 2] int32, reward [n] float64, terminated / truncated [n] uint8 (any may be NULL).
+ * shape [n, 2] int32 holds each env's (H, W) and toroidal [n] uint8 its topology; both may be NULL for bordered
+ * (euclidean) mazes, where best dir never wraps.  Bit-identical to the wide outputs of the same step. */
+int maze_step_decode_host(const uint32_t* records, int64_t n, const int32_t* shape, const uint8_t* toroidal, int32_t* agent,
+                          int32_t* best_dir, double* reward, uint8_t* terminated, uint8_t* truncated);
+
+/* Measurement aid, not part of the env path (tools/perf_scatter_rmw.py): one launch that
+ * streams maze_step's coalesced words for every env of `b` (streams != 0) and lets rmw_per_1024 of every 1024 envs do
+ * one 2-byte read-modify-write in arr (uint16 [n_elems]) -- pattern 0: uniform random element; 1: cell-major
+ * cell * B + env with a random cell per env; 2: as 1 with one cell per warp.  Overwrites b's outputs and state. */
+int maze_bench_scatter_rmw(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* actions, uint16_t* arr, int64_t n_elems, int pattern,
+                           int rmw_per_1024, uint32_t launch, int streams, void* stream);
 
 /* k_steps consecutive transitions per env in one call, for action sequences known in advance
  * (scripted / random exploration, replaying tapes): exactly the result of k_steps maze_step calls
@@ -336,6 +376,95 @@ int maze_dqn_sample(maze_ctx* ctx, const maze_replay* r, int n, uint64_t seed, u
  * that makes a decision (not for envs waiting for an autoreset). */
 int maze_dqn_select(maze_ctx* ctx, const maze_env_batch* b, const float* q_values, const double* eps_lut, int eps_len,
                     uint32_t* steps_done, uint64_t seed, int64_t env_id_base, uint8_t* actions, void* stream);
+
+/* ---- DQN / DDQN network on the tensor cores (north star item 4; BASELINE.json configs[4]) ------------
+ * The net of agents/ddqn_agent.py:18-52 (dqn_agent.py:19-57 is the same without Dropout):
+ *   Conv2d(3, 32, 3, padding 1) + LeakyReLU + MaxPool2d(2, 2) on the 3 x 15 x 15 window -> 32 x 7 x 7 = 1568
+ *   cat(conv features, 6 state floats) -> Linear(1574, 1024) + LeakyReLU -> Linear(1024, 512) + ReLU -> Linear(512, 4)
+ * and its update, ddqn_agent.py:113-152: q(s, a) of the source net, a* = argmax q_source(s', .),
+ * y = r + gamma * q_target(s', a*), MSE loss (mean), elementwise gradient clamp to +-1, AdamW.
+ * The reference's Dropout(p = 0.2) -- active in every forward because the nets are never put in eval() -- is
+ * NOT applied (documented deviation: parity is against the same net with dropout off).
+ *
+ * Parameters live in ONE flat fp32 buffer per net (source `params`, target `target`), laid out as
+ *   conv weight [32, 3, 3, 3] | conv bias [32] | fc1 weight [1024, 1600] | fc1 bias [1024] |
+ *   fc2 weight [512, 1024] | fc2 bias [512] | fc3 weight [4, 512] | fc3 bias [4]
+ * where fc1's 1600 input columns are the 1568 conv features (channel * 49 + row * 7 + col, as
+ * fw.view(batch, -1) orders them), the 6 state floats, and 26 zero columns (K padded to a multiple of 64 for the
+ * tensor-core tiles; their weights and gradients stay zero).  Gradients and the AdamW moments use the same
+ * layout.  The bf16 copies are the tensor-core operands: w1 / w2 as stored ([out, in], the forward pass) and
+ * transposed ([in, out], the backward-data pass); maze_dqn_net_refresh rebuilds them from the fp32 masters. */
+#define MAZE_NET_IN       1600   /* 1568 + 6, padded                                             */
+#define MAZE_NET_IN_USED  1574
+#define MAZE_NET_H1       1024
+#define MAZE_NET_H2       512
+#define MAZE_NET_OFF_CONV_W 0
+#define MAZE_NET_OFF_CONV_B 864
+#define MAZE_NET_OFF_W1     896
+#define MAZE_NET_OFF_B1     (MAZE_NET_OFF_W1 + MAZE_NET_H1 * MAZE_NET_IN)
+#define MAZE_NET_OFF_W2     (MAZE_NET_OFF_B1 + MAZE_NET_H1)
+#define MAZE_NET_OFF_B2     (MAZE_NET_OFF_W2 + MAZE_NET_H2 * MAZE_NET_H1)
+#define MAZE_NET_OFF_W3     (MAZE_NET_OFF_B2 + MAZE_NET_H2)
+#define MAZE_NET_OFF_B3     (MAZE_NET_OFF_W3 + 4 * MAZE_NET_H2)
+#define MAZE_NET_PARAMS     (MAZE_NET_OFF_B3 + 4)   /* 2 167 172 floats                         */
+typedef struct maze_dqn_net {
+    float*    params;     /* [MAZE_NET_PARAMS] source net, fp32 master                              */
+    float*    target;     /* [MAZE_NET_PARAMS] target net                                           */
+    float*    grads;      /* [MAZE_NET_PARAMS] gradient accumulators; zero between steps (training) */
+    float*    adam_m;     /* [MAZE_NET_PARAMS] AdamW first moment                      (training)   */
+    float*    adam_v;     /* [MAZE_NET_PARAMS] AdamW second moment                     (training)   */
+    uint16_t* w1_bf16;    /* [1024, 1600] bf16 source fc1 weight                                    */
+    uint16_t* w2_bf16;    /* [512, 1024]                                                            */
+    uint16_t* w1t_bf16;   /* [1600, 1024] transposed                                   (training)   */
+    uint16_t* w2t_bf16;   /* [1024, 512]                                               (training)   */
+    uint16_t* tw1_bf16;   /* target net operands                                                    */
+    uint16_t* tw2_bf16;
+    void*     workspace;  /* maze_dqn_net_workspace_bytes(max_batch) bytes, 256-byte aligned        */
+    float*    loss;       /* [1] loss of the last maze_dqn_backward                     (training)   */
+    int32_t   max_batch;  /* samples per call the workspace was sized for                           */
+    int32_t   reserved;
+} maze_dqn_net;
+
+int64_t maze_dqn_net_workspace_bytes(int max_batch);
+
+/* Rebuild the bf16 operand copies of one net (which = 0 source, 1 target) from its fp32 parameters: after
+ * initialisation, load_state_dict, or update_target (ddqn_agent.py:161-162: copy params -> target, then refresh 1). */
+int maze_dqn_net_refresh(maze_ctx* ctx, const maze_dqn_net* net, int which, void* stream);
+
+/* net(state) for n samples (ddqn_agent.py:44-49, :106): vec [n, 6] float32, win [n, MAZE_WINDOW_WORDS] packed windows
+ * (the replay ring's format: DeviceReplay.stage_vec / stage_win are valid inputs), q_out [n, 4] float32. */
+int maze_dqn_forward(maze_ctx* ctx, const maze_dqn_net* net, int which, const float* vec, const uint32_t* win, int n,
+                     float* q_out, void* stream);
+
+/* The conv stage alone: X [n, MAZE_NET_IN] bf16 feature rows; pool_idx (optional, [n, 1568] uint8: bits 0-1 the
+ * max-pool choice dy * 2 + dx, bit 2 pre-activation > 0).  Exposed for the parity tests. */
+int maze_dqn_features(maze_ctx* ctx, const maze_dqn_net* net, int which, const float* vec, const uint32_t* win, int n,
+                      uint16_t* X, uint8_t* pool_idx, void* stream);
+
+/* optimize_model up to loss.backward() (ddqn_agent.py:113-144) on a batch of n transitions (n a multiple of 8):
+ * adds d loss / d params into net->grads (so that ranks can be summed before the optimiser runs), writes the loss
+ * to net->loss and, if qsa_out is not NULL, q(s, a) [n].  action [n] uint8, reward [n] float32. */
+int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const float* vec, const uint32_t* win, const float* next_vec,
+                      const uint32_t* next_win, const uint8_t* action, const float* reward, int n, float gamma,
+                      float* qsa_out, void* stream);
+
+/* param.grad.clamp_(-clamp, clamp) (ddqn_agent.py:146-147; clamp <= 0 disables) on grads * grad_scale, then one
+ * torch.optim.AdamW step (`step` counts from 1), then zeroes the gradient accumulators and refreshes the source
+ * net's bf16 operands.  grad_scale = 1 / world_size after an all-reduce(sum) of net->grads reproduces DDP's mean. */
+int maze_dqn_adamw(maze_ctx* ctx, const maze_dqn_net* net, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int64_t step, float grad_scale, float clamp, void* stream);
+
+/* memory.sample(n) that keeps the windows packed: the same draw as maze_dqn_sample (same seed / draw -> same
+ * transitions), 212 bytes per transition instead of 5.5 KB.  action [n] uint8. */
+int maze_dqn_sample_packed(maze_ctx* ctx, const maze_replay* r, int n, uint64_t seed, uint64_t draw, float* vec, uint32_t* win,
+                           float* next_vec, uint32_t* next_win, uint8_t* action, float* reward, void* stream);
+
+/* The tensor-core GEMM underneath: C[M, N] = A[M, K] . B[N, K]^T with bf16 row-major operands (row pitches lda, ldb
+ * in elements, multiples of 8; 16-byte aligned bases), N a multiple of 8.  epilogue 0: C bf16 = act(acc + bias)
+ * (act 0 none, 1 LeakyReLU(0.01), 2 ReLU; bias may be NULL); 1: C bf16 = acc * act'(aux) with aux [M, ldaux] bf16 the
+ * stored activation; 2: C fp32 += acc (atomic, `splits` CTAs along K).  tile_n 128 or 256. */
+int maze_dqn_gemm_bf16(maze_ctx* ctx, const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc, int M, int N, int K,
+                       int epilogue, int act, const float* bias, const uint16_t* aux, int ldaux, int tile_n, int splits, void* stream);
 
 /* Difficulty metrics of pool mazes, one record of MAZE_METRIC_WORDS doubles per processed slot
  * (out[k] belongs to ids[k], or to slot k when ids is NULL):

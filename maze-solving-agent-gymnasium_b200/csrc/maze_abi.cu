@@ -44,6 +44,7 @@ extern "C" int maze_sizeof(int which) {
         case 1: return (int)sizeof(maze_q_agent);
         case 2: return (int)sizeof(maze_replay);
         case 3: return (int)sizeof(maze_step_trace);
+        case 4: return (int)sizeof(maze_dqn_net);
         default: return -1;
     }
 }
@@ -127,5 +128,47 @@ extern "C" int maze_reward_lut(maze_ctx* ctx, int kind, double* out) {
     else if (kind == 1) memcpy(out, inv, sizeof(inv));
     else if (kind == 2) { out[0] = -1 * 0.5 - 0.05; out[1] = 0 * 0.5 - 0.05; out[2] = 1 * 0.5 - 0.05; }
     else return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_reward_lut kind");
+    return 0;
+}
+
+// Host-only: packed step records -> the wide arrays (see MAZE_STEP_PACKED in the header).
+extern "C" int maze_step_decode_host(const uint32_t* records, int64_t n, const int32_t* shape, const uint8_t* toroidal, int32_t* agent,
+                                     int32_t* best_dir, double* reward, uint8_t* terminated, uint8_t* truncated) {
+    if (!records || n < 0) return MAZE_E_NULL;
+    double lut[4][256];
+    memset(lut, 0, sizeof(lut));
+    for (int i = 0; i < 256; ++i) {
+        lut[MAZE_REC_KIND_REVISIT][i] = 0.0 - (1 - std::exp(-0.2 * i));
+        lut[MAZE_REC_KIND_INVALID][i] = 0.0 - (1 - std::exp(-0.15 * i));
+    }
+    lut[MAZE_REC_KIND_SHAPING][0] = -1 * 0.5 - 0.05;
+    lut[MAZE_REC_KIND_SHAPING][1] = 0 * 0.5 - 0.05;
+    lut[MAZE_REC_KIND_SHAPING][2] = 1 * 0.5 - 0.05;
+    lut[MAZE_REC_KIND_CONST][MAZE_REC_CONST_ONE] = 1.0;
+    lut[MAZE_REC_KIND_CONST][MAZE_REC_CONST_MINUS_ONE] = -1.0;
+    for (int64_t e = 0; e < n; ++e) {
+        const uint32_t rec = records[e];
+        const int r = (int)(rec & 0xff), c = (int)((rec >> 8) & 0xff), code = (int)((rec >> MAZE_REC_CODE_SHIFT) & 7);
+        if (agent) { agent[2 * e] = r; agent[2 * e + 1] = c; }
+        if (best_dir) {
+            int br = 0, bc = 0;
+            if (code < 4) {
+                const int dr = (code == 0) - (code == 1), dc = (code == 2) - (code == 3);
+                int nr = r + dr, nc = c + dc;
+                if (toroidal && toroidal[e] && shape) {
+                    const int H = shape[2 * e], W = shape[2 * e + 1];
+                    nr = nr < 0 ? H - 1 : (nr >= H ? 0 : nr);
+                    nc = nc < 0 ? W - 1 : (nc >= W ? 0 : nc);
+                }
+                br = r - nr;
+                bc = c - nc;
+            }
+            best_dir[2 * e] = br;
+            best_dir[2 * e + 1] = bc;
+        }
+        if (reward) reward[e] = lut[(rec >> MAZE_REC_KIND_SHIFT) & 3][(rec >> MAZE_REC_INDEX_SHIFT) & 0xff];
+        if (terminated) terminated[e] = (uint8_t)((rec >> MAZE_REC_TERM_SHIFT) & 1);
+        if (truncated) truncated[e] = (uint8_t)((rec >> MAZE_REC_TRUNC_SHIFT) & 1);
+    }
     return 0;
 }

@@ -35,7 +35,7 @@ __device__ __forceinline__ PackedObs encode_obs(const maze_env_batch& b, int e) 
     int r0 = st.r - WIN / 2, c0 = st.c - WIN / 2;
     if (!mz.tor) {
         r0 = min(max(r0, 0), H - WIN);
-        c0 = min(max(c0, 0), H - WIN);
+        c0 = min(max(c0, 0), W - WIN);   // the reference clamps with len(maze) (maze_handler.py:21-29: square mazes only); W keeps a non-square slot in bounds
     }
     PackedObs o;
     o.word = 0;
@@ -248,6 +248,8 @@ extern "C" int maze_dqn_push(maze_ctx* ctx, const maze_env_batch* b, const maze_
     if (int rc = maze_check_batch(ctx, b)) return rc;
     if (int rc = check_replay(ctx, r, true)) return rc;
     if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_push: actions");
+    if (r->capacity < b->num_envs)   // one launch claims up to num_envs slots: a smaller ring would hand one slot to several warps
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_push: replay capacity must be >= num_envs");
     const int per = DQN_THREADS / 32;
     maze_dqn_push_kernel<<<(b->num_envs + per - 1) / per, DQN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r, actions);
     MAZE_CHECK(cudaGetLastError());

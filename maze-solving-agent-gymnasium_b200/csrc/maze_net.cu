@@ -1,0 +1,927 @@
+// DQN / DDQN network on the B200 tensor cores (sm_100a): forward, double-Q target, backward and AdamW of
+// the net of agents/ddqn_agent.py:18-52 (conv 3->32 3x3 pad 1, LeakyReLU, MaxPool 2 -> 1568 (+6) -> 1024
+// -> 512 -> 4) and its update agents/ddqn_agent.py:113-152 (double-Q target, MSE, gradient clamp +-1, AdamW),
+// reading the replay ring's bit-packed windows directly (csrc/maze_dqn.cu).  Dropout (p = 0.2 in the
+// reference, active because the reference never calls eval()) is not applied: see DESIGN.md.
+//
+// Dense contractions run as tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged by TMA:
+//   net_gemm_kernel   C[M,N] = A[M,K] . B[N,K]^T, both operands K-major bf16, 128 x BN x 64 tiles, SWIZZLE_128B,
+//                     4-6 stage TMA ring, one MMA-issuing thread, 4 epilogue warps reading TMEM; epilogues:
+//                     bias + activation (forward), activation-derivative mask (backward data), fp32 red.add
+//                     with split-K (weight gradients)
+//   net_features_kernel  the 3x3 convolution as an implicit GEMM: per sample a [(row, col16), (channel, dx)]
+//                     bf16 image matrix in shared memory, three accumulating MMAs per 128-position tile whose
+//                     A descriptors start 16 rows apart (dy = -1, 0, +1), bias + 2x2 max-pool + LeakyReLU in the
+//                     TMEM epilogue
+// Everything else (fc3 head, loss, conv weight gradient, transposes, AdamW) is CUDA-core work: < 2 % of the FLOPs.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "maze_common.cuh"
+#include "maze_tc.cuh"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int BM = 128, BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+enum { EPI_BIAS_ACT = 0, EPI_MASK = 1, EPI_RED_F32 = 2 };
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
+constexpr float LRELU_SLOPE = 0.01f;   // nn.LeakyReLU() default (ddqn_agent.py:28,38)
+
+struct GemmArgs {
+    int M, N, K;          // C[M, N] = A[M, K] . B[N, K]^T
+    void* C;              // bf16 (EPI_BIAS_ACT, EPI_MASK) or fp32 accumulators (EPI_RED_F32)
+    int ldc;
+    const float* bias;    // [N] or null                       (EPI_BIAS_ACT)
+    const bf16* aux;      // forward activation [M, ldaux]     (EPI_MASK: derivative of `act` taken at it)
+    int ldaux;
+    int act;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;   // + slack for the 1024-byte alignment
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms are 1024-byte aligned
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nkb_total = (g.K + BK - 1) / BK;
+    const int kb_begin = (int)((long long)nkb_total * blockIdx.z / gridDim.z);
+    const int kb_end = (int)((long long)nkb_total * (blockIdx.z + 1) / gridDim.z);
+    const int nkb = kb_end - kb_begin;
+    if (nkb <= 0) return;   // uniform over the CTA (the launcher never asks for more splits than k-blocks)
+    const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[STAGES]), accum_bar = tc::smem_u32(&bars[2 * STAGES]);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(full0 + 8 * s, 1);
+            tc::mbar_init(empty0 + 8 * s, 1);
+        }
+        tc::mbar_init(accum_bar, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tc::smem_u32(&tmem_slot), BN);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // TMA producer
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                tc::mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                tc::mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
+                const uint32_t a_dst = base + (uint32_t)s * Cfg::STAGE_BYTES;
+                tc::tma_load_2d(a_dst, &tmA, full0 + 8 * s, (kb_begin + i) * BK, m0);
+                tc::tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full0 + 8 * s, (kb_begin + i) * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // MMA issuer
+            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                tc::mbar_wait(full0 + 8 * s, ph);
+                tc::tc_fence_after();
+                const uint32_t a_addr = base + (uint32_t)s * Cfg::STAGE_BYTES;
+                const uint64_t da = tc::smem_desc(a_addr, 0, 1024, tc::SWIZZLE_128B);
+                const uint64_t db = tc::smem_desc(a_addr + Cfg::A_BYTES, 0, 1024, tc::SWIZZLE_128B);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)   // 16 bf16 = 32 bytes further along K inside the 128-byte swizzle row
+                    tc::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (uint32_t)((i | k) != 0));
+                tc::umma_commit(empty0 + 8 * s);   // frees the stage once these MMAs have read it
+            }
+            tc::umma_commit(accum_bar);
+        }
+    } else {   // epilogue: warp w may read TMEM lanes 32 (w % 4) .. + 31
+        const int q = warp & 3;
+        tc::mbar_wait(accum_bar, 0);
+        tc::tc_fence_after();
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < g.M;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= g.N) break;
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tc::tmem_ld_wait();
+            const int col0 = n0 + c0;
+            if constexpr (EPI == EPI_RED_F32) {
+                float* dst = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (row_ok && col0 + j + 4 <= g.N)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
+                }
+            } else {
+                uint32_t packed[16];
+                if constexpr (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
+                        if (g.bias) {
+                            x0 += col0 + j < g.N ? __ldg(g.bias + col0 + j) : 0.f;
+                            x1 += col0 + j + 1 < g.N ? __ldg(g.bias + col0 + j + 1) : 0.f;
+                        }
+                        if (g.act == ACT_LRELU) {
+                            x0 = x0 > 0.f ? x0 : LRELU_SLOPE * x0;
+                            x1 = x1 > 0.f ? x1 : LRELU_SLOPE * x1;
+                        } else if (g.act == ACT_RELU) {
+                            x0 = fmaxf(x0, 0.f);
+                            x1 = fmaxf(x1, 0.f);
+                        }
+                        packed[j >> 1] = tc::pack_bf16x2(x0, x1);
+                    }
+                } else {   // EPI_MASK: dL/d(pre-activation) = dL/d(activation) * act'(pre), sign taken from the stored activation
+                    const bf16* arow = g.aux + (size_t)row * g.ldaux + col0;
+                    const float neg = g.act == ACT_LRELU ? LRELU_SLOPE : 0.f;
+#pragma unroll
+                    for (int j8 = 0; j8 < 32; j8 += 8) {
+                        uint4 h = make_uint4(0, 0, 0, 0);
+                        if (row_ok && col0 + j8 + 8 <= g.N) h = __ldg(reinterpret_cast<const uint4*>(arow + j8));
+                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            // bf16 sign/zero test on the raw bits: > 0 <=> sign clear and magnitude non-zero
+                            const uint32_t lo = hw[t] & 0xffffu, hi = hw[t] >> 16;
+                            const float f0 = (lo != 0 && lo < 0x8000u) ? 1.f : neg, f1 = (hi != 0 && hi < 0x8000u) ? 1.f : neg;
+                            packed[(j8 >> 1) + t] = tc::pack_bf16x2(__uint_as_float(v[j8 + 2 * t]) * f0, __uint_as_float(v[j8 + 2 * t + 1]) * f1);
+                        }
+                    }
+                }
+                bf16* dst = reinterpret_cast<bf16*>(g.C) + (size_t)row * g.ldc + col0;
+#pragma unroll
+                for (int j8 = 0; j8 < 32; j8 += 8) {
+                    if (row_ok && col0 + j8 + 8 <= g.N)
+                        *reinterpret_cast<uint4*>(dst + j8) = make_uint4(packed[j8 >> 1], packed[(j8 >> 1) + 1], packed[(j8 >> 1) + 2], packed[(j8 >> 1) + 3]);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched at run time: the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 matrix [rows, cols] with row pitch ld (elements), tiles of box_rows x 64 columns, 128-byte swizzle
+int make_map(maze_ctx* ctx, CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return maze_fail_arg(ctx, MAZE_E_RANGE, "cuTensorMapEncodeTiled is not available from this driver");
+    if (((uintptr_t)ptr & 15) || (ld % 8) != 0) return maze_fail_arg(ctx, MAZE_E_ALIGN, "GEMM operand: 16-byte aligned base and row pitch");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (ctx) snprintf(ctx->err, sizeof(ctx->err), "cuTensorMapEncodeTiled failed with %d (rows %d cols %d ld %d box %d)", (int)r, rows, cols, ld, box_rows);
+        return MAZE_E_RANGE;
+    }
+    return 0;
+}
+
+template <int BN, int EPI>
+int launch_gemm_t(maze_ctx* ctx, const bf16* A, int lda, const bf16* B, int ldb, const GemmArgs& g, int splits, cudaStream_t st) {
+    CUtensorMap ta, tb;
+    if (int rc = make_map(ctx, &ta, A, g.M, g.K, lda, BM)) return rc;
+    if (int rc = make_map(ctx, &tb, B, g.N, g.K, ldb, BN)) return rc;
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        MAZE_CHECK(cudaFuncSetAttribute(net_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::SMEM));
+        attr_set = true;
+    }
+    const int nkb = (g.K + BK - 1) / BK;
+    if (splits < 1) splits = 1;
+    if (splits > nkb) splits = nkb;
+    const dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
+    net_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, st>>>(ta, tb, g);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_gemm(maze_ctx* ctx, int epi, int bn, const bf16* A, int lda, const bf16* B, int ldb, const GemmArgs& g, int splits, cudaStream_t st) {
+    if (g.M < 1 || g.N < 1 || g.K < 1 || (g.N % 8) != 0) return maze_fail_arg(ctx, MAZE_E_RANGE, "GEMM shape (N must be a multiple of 8)");
+    if (epi != EPI_RED_F32 && splits > 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "split-K needs the accumulate epilogue");
+    if (bn == 256) {
+        if (epi == EPI_BIAS_ACT) return launch_gemm_t<256, EPI_BIAS_ACT>(ctx, A, lda, B, ldb, g, splits, st);
+        if (epi == EPI_MASK) return launch_gemm_t<256, EPI_MASK>(ctx, A, lda, B, ldb, g, splits, st);
+        return launch_gemm_t<256, EPI_RED_F32>(ctx, A, lda, B, ldb, g, splits, st);
+    }
+    if (epi == EPI_BIAS_ACT) return launch_gemm_t<128, EPI_BIAS_ACT>(ctx, A, lda, B, ldb, g, splits, st);
+    if (epi == EPI_MASK) return launch_gemm_t<128, EPI_MASK>(ctx, A, lda, B, ldb, g, splits, st);
+    return launch_gemm_t<128, EPI_RED_F32>(ctx, A, lda, B, ldb, g, splits, st);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Convolution features.  Per sample, shared memory holds the image matrix
+//   R[(y', x), kk]   y' = 0..17 (image row y' - 1; rows -1, 15, 16 are zero), x = 0..15 (column 15 is padding),
+//                    kk = channel * 3 + dx' (dx' = 0..2 <-> column x + dx' - 1), 9 of 16 K slots used
+// in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices: the two K halves of an
+// 8-row group 128 bytes apart, groups 256 bytes apart).  Output position p = y * 16 + x of dy' uses R row
+// p + 16 dy', so the three vertical taps are three MMAs whose A descriptors start 512 bytes apart; the B
+// operands are the three [32 out-channels, 16] weight slices.  Tile t (positions 128 t .. 128 t + 127 = image
+// rows 8 t .. 8 t + 7) accumulates in TMEM columns 32 t .. 32 t + 31.
+constexpr int FEAT_THREADS = 128;
+constexpr int FEAT_R_ROWS = 288;                   // 18 x 16
+constexpr int FEAT_R_BYTES = FEAT_R_ROWS * 32;     // 9216
+constexpr int FEAT_W_BYTES = 3 * 32 * 32;          // three [32, 16] bf16 slices
+constexpr int NET_CONV_OUT = 32 * 49;              // 1568
+constexpr int NET_IN = 1600;                       // 1568 + 6, padded to a multiple of 64
+
+__device__ __forceinline__ uint32_t r_offset(int row, int chunk) {   // byte offset of (row, K half) in the no-swizzle layout
+    return (uint32_t)((row >> 3) * 256 + chunk * 128 + (row & 7) * 16);
+}
+
+template <bool SAVE_IDX>
+__global__ void __launch_bounds__(FEAT_THREADS)
+net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ win, int n, const float* __restrict__ conv_w,
+                    const float* __restrict__ conv_b, bf16* __restrict__ X, uint8_t* __restrict__ pool_idx) {
+    __shared__ __align__(128) uint8_t sR[FEAT_R_BYTES];
+    __shared__ __align__(128) uint8_t sW[FEAT_W_BYTES];
+    __shared__ __align__(16) bf16 sfeat[NET_CONV_OUT];
+    __shared__ __align__(16) uint8_t sidx[SAVE_IDX ? NET_CONV_OUT : 16];
+    __shared__ float sbias[32];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::mbar_init(tc::smem_u32(&bar), 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(tc::smem_u32(&tmem_slot), 64);
+        tc::tmem_relinquish();
+    }
+    // weight slices: sW[dy][o][kk] = conv_w[o][c][dy][dx], kk = c * 3 + dx (Conv2d.weight is [32, 3, 3, 3])
+    for (int i = tid; i < 3 * 32 * 16; i += FEAT_THREADS) {
+        const int dy = i / 512, o = (i >> 4) & 31, kk = i & 15;
+        float w = 0.f;
+        if (kk < 9) w = conv_w[o * 27 + (kk / 3) * 9 + dy * 3 + (kk % 3)];
+        *reinterpret_cast<bf16*>(sW + dy * 1024 + r_offset(o, kk >> 3) + (kk & 7) * 2) = __float2bfloat16(w);
+    }
+    if (tid < 32) sbias[tid] = conv_b[tid];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t bar_a = tc::smem_u32(&bar), r_base = tc::smem_u32(sR), w_base = tc::smem_u32(sW);
+    uint32_t phase = 0;
+
+    for (int s = blockIdx.x; s < n; s += gridDim.x) {
+        // ---- build R from the packed window (word ch * 8 + k: window rows 2 k in bits 0-14, 2 k + 1 in bits 16-30)
+        const uint32_t* words = win + (size_t)s * MAZE_WINDOW_WORDS;
+        for (int r = tid; r < FEAT_R_ROWS; r += FEAT_THREADS) {
+            const int iy = (r >> 4) - 1, x = r & 15;
+            uint32_t v9 = 0;
+            if (iy >= 0 && iy < MAZE_WINDOW) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t rowbits = (__ldg(words + c * 8 + (iy >> 1)) >> ((iy & 1) * 16)) & 0x7fffu;
+                    v9 |= (((rowbits << 1) >> x) & 7u) << (3 * c);   // columns x - 1, x, x + 1
+                }
+            }
+            uint32_t w[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {   // bf16 1.0 = 0x3F80
+                const uint32_t b2 = (v9 >> (2 * j)) & 3u;
+                w[j] = (b2 & 1u) * 0x3F80u + (b2 >> 1) * 0x3F800000u;
+            }
+            *reinterpret_cast<uint4*>(sR + r_offset(r, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(sR + r_offset(r, 1)) = make_uint4(w[4] & 0xffffu, 0, 0, 0);
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            constexpr uint32_t idesc = tc::idesc_bf16(128, 32);
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const uint64_t da = tc::smem_desc(r_base + (uint32_t)(t * 16 + dy * 2) * 256u, 128, 256, tc::SWIZZLE_NONE);
+                    const uint64_t db = tc::smem_desc(w_base + (uint32_t)dy * 1024u, 128, 256, tc::SWIZZLE_NONE);
+                    tc::umma_bf16(tmem_base + (uint32_t)t * 32u, da, db, idesc, (uint32_t)(dy != 0));
+                }
+            tc::umma_commit(bar_a);
+        }
+        tc::mbar_wait(bar_a, phase);
+        phase ^= 1u;
+        tc::tc_fence_after();
+        // ---- epilogue: bias, 2 x 2 max-pool (first maximum in scan order wins), LeakyReLU
+        const bool odd = lane & 1, upper = (lane >> 4) & 1;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * 32u, v);
+            tc::tmem_ld_wait();
+            // x pair: even lanes keep channels 0-15, odd lanes channels 16-31
+            float a[16];
+            uint32_t xbits = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float lo = __uint_as_float(v[j]), hi = __uint_as_float(v[j + 16]);
+                const float send = odd ? lo : hi, keep = odd ? hi : lo;
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                const float left = odd ? recv : keep, right = odd ? keep : recv;
+                a[j] = fmaxf(left, right);
+                xbits |= (uint32_t)(right > left) << j;
+            }
+            // y pair (lanes l, l ^ 16): lanes 0-15 keep the first 8 of their 16 channels, lanes 16-31 the last 8
+            const uint32_t other_xbits = __shfl_xor_sync(0xffffffffu, xbits, 16);
+            const int py = t * 4 + warp, px = (lane & 15) >> 1;
+            const bool valid = py < 7 && px < 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float send = upper ? a[j] : a[j + 8], keep = upper ? a[j + 8] : a[j];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+                const float top = upper ? recv : keep, bottom = upper ? keep : recv;
+                const int jj = upper ? j + 8 : j;                       // index into the 16 channels both lanes hold
+                const int ch = (odd ? 16 : 0) + jj;
+                const bool down = bottom > top;
+                float m = fmaxf(top, bottom) + sbias[ch];
+                if (valid) {
+                    if constexpr (SAVE_IDX) {
+                        const uint32_t xb_top = ((upper ? other_xbits : xbits) >> jj) & 1u, xb_bot = ((upper ? xbits : other_xbits) >> jj) & 1u;
+                        sidx[ch * 49 + py * 7 + px] = (uint8_t)((down ? 2u + xb_bot : xb_top) | (m > 0.f ? 4u : 0u));
+                    }
+                    m = m > 0.f ? m : LRELU_SLOPE * m;
+                    sfeat[ch * 49 + py * 7 + px] = __float2bfloat16(m);
+                }
+            }
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+        // ---- write the feature row: 1568 conv features, 6 state floats, zero padding up to 1600
+        bf16* xrow = X + (size_t)s * NET_IN;
+        for (int i = tid; i < NET_CONV_OUT / 8; i += FEAT_THREADS)
+            reinterpret_cast<uint4*>(xrow)[i] = reinterpret_cast<const uint4*>(sfeat)[i];
+        if (tid < 32) xrow[NET_CONV_OUT + tid] = __float2bfloat16(tid < 6 ? __ldg(vec + (size_t)s * 6 + tid) : 0.f);
+        if constexpr (SAVE_IDX) {
+            uint8_t* irow = pool_idx + (size_t)s * NET_CONV_OUT;
+            for (int i = tid; i < NET_CONV_OUT / 16; i += FEAT_THREADS)
+                reinterpret_cast<uint4*>(irow)[i] = reinterpret_cast<const uint4*>(sidx)[i];
+        }
+        // the next iteration rewrites sfeat / sidx only after its own __syncthreads
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fc3 head (512 -> 4, fp32 weights, CUDA cores).  q[n, 4] for action selection.
+constexpr int HEAD_THREADS = 256;
+constexpr int NET_H2 = 512, NET_H1 = 1024;
+
+__device__ __forceinline__ void head_load16(const bf16* row, int lane, float (&h)[16]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(row + lane * 16)), b = __ldg(reinterpret_cast<const uint4*>(row + lane * 16 + 8));
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        h[2 * i] = __uint_as_float(w[i] << 16);
+        h[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS)
+net_head_q_kernel(const bf16* __restrict__ h2, int n, const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ q) {
+    __shared__ float sw[4 * NET_H2];
+    for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS) sw[i] = w3[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int s = blockIdx.x * (HEAD_THREADS / 32) + (threadIdx.x >> 5); s < n; s += gridDim.x * (HEAD_THREADS / 32)) {
+        float h[16];
+        head_load16(h2 + (size_t)s * NET_H2, lane, h);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[a] = fmaf(h[i], sw[a * NET_H2 + lane * 16 + i], acc[a]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a] = warp_sum(acc[a]);
+        if (lane < 4) q[(size_t)s * 4 + lane] = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + b3[lane];
+    }
+}
+
+// Loss and the gradient at the head (ddqn_agent.py:131-143): q(s, a) from the source net, a* = argmax_a' q_source(s', a'),
+// y = r + gamma * q_target(s', a*), loss = mean (q(s, a) - y)^2.  Writes dL/d(pre-ReLU h2) [n, 512] bf16 and accumulates the
+// fc3 gradients.
+__global__ void __launch_bounds__(HEAD_THREADS)
+net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_sn, const bf16* __restrict__ h2_tn, int n,
+                     const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ tw3, const float* __restrict__ tb3,
+                     const uint8_t* __restrict__ action, const float* __restrict__ reward, float gamma, bf16* __restrict__ dh2,
+                     float* __restrict__ gw3, float* __restrict__ gb3, float* __restrict__ loss, float* __restrict__ qsa_out) {
+    __shared__ float sw[4 * NET_H2], stw[4 * NET_H2], sgw[4 * NET_H2];
+    __shared__ float sgb[4], sloss;
+    for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS) {
+        sw[i] = w3[i];
+        stw[i] = tw3[i];
+        sgw[i] = 0.f;
+    }
+    if (threadIdx.x < 4) sgb[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) sloss = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const float inv_n = 1.f / (float)n;
+    for (int s = blockIdx.x * (HEAD_THREADS / 32) + (threadIdx.x >> 5); s < n; s += gridDim.x * (HEAD_THREADS / 32)) {
+        float h[16], hn[16], ht[16];
+        head_load16(h2_s + (size_t)s * NET_H2, lane, h);
+        head_load16(h2_sn + (size_t)s * NET_H2, lane, hn);
+        head_load16(h2_tn + (size_t)s * NET_H2, lane, ht);
+        float qs[4], qn[4], qt[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float x = 0.f, y = 0.f, z = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                x = fmaf(h[i], sw[a * NET_H2 + lane * 16 + i], x);
+                y = fmaf(hn[i], sw[a * NET_H2 + lane * 16 + i], y);
+                z = fmaf(ht[i], stw[a * NET_H2 + lane * 16 + i], z);
+            }
+            qs[a] = warp_sum(x) + b3[a];
+            qn[a] = warp_sum(y) + b3[a];
+            qt[a] = warp_sum(z) + tb3[a];
+        }
+        int best = 0;   // .max(1)[1]: first maximum
+#pragma unroll
+        for (int a = 1; a < 4; ++a)
+            if (qn[a] > qn[best]) best = a;
+        const int act = action[s] & 3;
+        const float qsa = act == 0 ? qs[0] : act == 1 ? qs[1] : act == 2 ? qs[2] : qs[3];
+        const float qtb = best == 0 ? qt[0] : best == 1 ? qt[1] : best == 2 ? qt[2] : qt[3];
+        const float target = qtb * gamma + reward[s];
+        const float d = qsa - target;
+        const float gq = 2.f * d * inv_n;   // d mean((q - y)^2) / d q
+        uint32_t out[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            const float w0 = sw[act * NET_H2 + lane * 16 + i], w1 = sw[act * NET_H2 + lane * 16 + i + 1];
+            out[i >> 1] = tc::pack_bf16x2(h[i] > 0.f ? gq * w0 : 0.f, h[i + 1] > 0.f ? gq * w1 : 0.f);   // ReLU'
+        }
+        uint4* dst = reinterpret_cast<uint4*>(dh2 + (size_t)s * NET_H2 + lane * 16);
+        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(&sgw[act * NET_H2 + lane * 16 + i], gq * h[i]);
+        if (lane == 0) {
+            atomicAdd(&sgb[act], gq);
+            atomicAdd(&sloss, d * d * inv_n);
+            if (qsa_out) qsa_out[s] = qsa;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS)
+        if (sgw[i] != 0.f) atomicAdd(gw3 + i, sgw[i]);
+    if (threadIdx.x < 4) atomicAdd(gb3 + threadIdx.x, sgb[threadIdx.x]);
+    if (threadIdx.x == 0) atomicAdd(loss, sloss);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// [R, C] bf16 -> [C, R] bf16 (the weight-gradient GEMMs contract over the batch, so their operands are the
+// transposed activations), optionally with the column sums of the input (= the bias gradient).
+__global__ void __launch_bounds__(256)
+net_transpose_kernel(const bf16* __restrict__ in, int R, int C, int ld_in, bf16* __restrict__ out, int ld_out, float* __restrict__ colsum) {
+    __shared__ bf16 tile[64][66];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int i = ty; i < 64; i += 8) {
+        const int r = r0 + i;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int c = c0 + tx + 32 * k;
+            tile[i][tx + 32 * k] = (r < R && c < C) ? in[(size_t)r * ld_in + c] : __float2bfloat16(0.f);
+        }
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 8) {
+        const int c = c0 + i;
+        float part = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int r = r0 + tx + 32 * k;
+            const bf16 v = tile[tx + 32 * k][i];
+            if (c < C && r < R) out[(size_t)c * ld_out + r] = v;
+            part += __bfloat162float(v);
+        }
+        if (colsum) {
+            part = warp_sum(part);
+            if (tx == 0 && c < C) atomicAdd(colsum + c, part);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Convolution weight / bias gradient from dL/dX (conv part), the saved pool choices and the packed windows.
+// Thread (o, sub): output channel o, pooled positions sub, sub + 8, ...; 27 tap accumulators in registers.
+__global__ void __launch_bounds__(256)
+net_conv_bwd_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ pool_idx, const uint32_t* __restrict__ win, int n,
+                    float* __restrict__ gconv_w, float* __restrict__ gconv_b) {
+    __shared__ uint32_t sw[2][MAZE_WINDOW_WORDS];
+    const int o = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    float accb = 0.f;
+    int buf = 0;
+    for (int s = blockIdx.x; s < n; s += gridDim.x, buf ^= 1) {
+        if (threadIdx.x < MAZE_WINDOW_WORDS) sw[buf][threadIdx.x] = win[(size_t)s * MAZE_WINDOW_WORDS + threadIdx.x];
+        __syncthreads();   // double-buffered: the previous sample's readers are at most one iteration behind
+        const bf16* grow = dX + (size_t)s * NET_IN + o * 49;
+        const uint8_t* irow = pool_idx + (size_t)s * NET_CONV_OUT + o * 49;
+        for (int q = sub; q < 49; q += 8) {
+            float gq = __bfloat162float(grow[q]);
+            if (gq == 0.f) continue;
+            const uint32_t b = irow[q];
+            if (!(b & 4u)) gq *= LRELU_SLOPE;
+            const int y = 2 * (q / 7) + (int)((b >> 1) & 1u), x = 2 * (q % 7) + (int)(b & 1u);
+            accb += gq;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int iy = y + dy - 1;
+                    uint32_t t3 = 0;
+                    if (iy >= 0 && iy < MAZE_WINDOW) {
+                        const uint32_t rowbits = (sw[buf][c * 8 + (iy >> 1)] >> ((iy & 1) * 16)) & 0x7fffu;
+                        t3 = ((rowbits << 1) >> x) & 7u;
+                    }
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) acc[c * 9 + dy * 3 + dx] += ((t3 >> dx) & 1u) ? gq : 0.f;
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        float v = acc[k];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (sub == 0 && v != 0.f) atomicAdd(gconv_w + o * 27 + k, v);
+    }
+    accb += __shfl_xor_sync(0xffffffffu, accb, 1);
+    accb += __shfl_xor_sync(0xffffffffu, accb, 2);
+    accb += __shfl_xor_sync(0xffffffffu, accb, 4);
+    if (sub == 0 && accb != 0.f) atomicAdd(gconv_b + o, accb);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// AdamW (torch.optim.AdamW defaults, ddqn_agent.py:91) with the reference's elementwise gradient clamp
+// (ddqn_agent.py:146-147).  Zeroes the gradient accumulators for the next step.
+__global__ void __launch_bounds__(256)
+net_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int count, float lr, float beta1,
+                 float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float clamp) {
+    const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i >= count) return;
+    float4 P = *reinterpret_cast<float4*>(p + i), G = *reinterpret_cast<float4*>(g + i), M = *reinterpret_cast<float4*>(m + i),
+           V = *reinterpret_cast<float4*>(v + i);
+    float* pp = &P.x;
+    float* gg = &G.x;
+    float* mm = &M.x;
+    float* vv = &V.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float gr = gg[k] * grad_scale;
+        if (clamp > 0.f) gr = fminf(fmaxf(gr, -clamp), clamp);
+        pp[k] *= 1.f - lr * wd;
+        mm[k] = beta1 * mm[k] + (1.f - beta1) * gr;
+        vv[k] = beta2 * vv[k] + (1.f - beta2) * gr * gr;
+        const float denom = sqrtf(vv[k]) / bc2_sqrt + eps;
+        pp[k] -= (lr / bc1) * (mm[k] / denom);
+    }
+    *reinterpret_cast<float4*>(p + i) = P;
+    *reinterpret_cast<float4*>(m + i) = M;
+    *reinterpret_cast<float4*>(v + i) = V;
+    *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// fp32 [R, C] master weights -> bf16 [R, C] (GEMM B operand of the forward pass) and optionally bf16 [C, R]
+// (B operand of the backward-data pass)
+__global__ void __launch_bounds__(256)
+net_refresh_kernel(const float* __restrict__ w, int R, int C, bf16* __restrict__ wb, bf16* __restrict__ wt) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        const float x = (r < R && c < C) ? w[(size_t)r * C + c] : 0.f;
+        tile[i][tx] = x;
+        if (r < R && c < C) wb[(size_t)r * C + c] = __float2bfloat16(x);
+    }
+    if (!wt) return;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (r < R && c < C) wt[(size_t)c * R + r] = __float2bfloat16(tile[tx][i]);
+    }
+}
+
+// memory.sample(n) that leaves the windows bit-packed (the network kernels read them as they are)
+__global__ void __launch_bounds__(256)
+net_sample_packed_kernel(maze_replay r, int n, unsigned long long seed, unsigned long long draw, float* __restrict__ vec,
+                         uint32_t* __restrict__ win, float* __restrict__ next_vec, uint32_t* __restrict__ next_win,
+                         uint8_t* __restrict__ action, float* __restrict__ reward) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const unsigned long long pushed = *r.pushed;
+    const unsigned long long filled = pushed < (unsigned long long)r.capacity ? pushed : (unsigned long long)r.capacity;
+    if (filled == 0) return;
+    Philox rng;   // the same draw as maze_dqn_sample: slot k of draw `draw` is the same transition in both
+    rng.init(seed, draw, (uint32_t)k);
+    rng.refill();
+    const unsigned long long u = ((unsigned long long)rng.o0 << 32) | rng.o1;
+    const size_t slot = (size_t)__umul64hi(u, filled);
+    if (lane < 6) {
+        vec[(size_t)k * 6 + lane] = r.vec[slot * 6 + lane];
+        next_vec[(size_t)k * 6 + lane] = r.next_vec[slot * 6 + lane];
+    }
+    if (lane < MAZE_WINDOW_WORDS) {
+        win[(size_t)k * MAZE_WINDOW_WORDS + lane] = r.win[slot * MAZE_WINDOW_WORDS + lane];
+        next_win[(size_t)k * MAZE_WINDOW_WORDS + lane] = r.next_win[slot * MAZE_WINDOW_WORDS + lane];
+    }
+    if (lane == 0) {
+        action[k] = r.action[slot];
+        reward[k] = r.reward[slot];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Workspace carving (bf16 activations; rows padded to a multiple of 128 so every TMA box starts in bounds)
+struct Workspace {
+    int n, np;   // batch, padded batch
+    bf16 *X, *XT, *h1, *h1t_tn, *h1T, *h2, *h2_tn, *dh2, *dh2T, *dh1, *dh1T, *dX;
+    uint8_t* idx;
+    float* q;
+    size_t bytes;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+Workspace carve(void* base, int n) {
+    Workspace w{};
+    w.n = n;
+    w.np = (n + 127) / 128 * 128;
+    const size_t np = (size_t)w.np;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    w.X = (bf16*)take(2 * np * NET_IN * 2);          // rows 0..np-1 state, np..2np-1 next state
+    w.XT = (bf16*)take((size_t)NET_IN * np * 2);     // state features, transposed
+    w.h1 = (bf16*)take(2 * np * NET_H1 * 2);         // source net on both halves
+    w.h1t_tn = (bf16*)take(np * NET_H1 * 2);         // target net on the next states
+    w.h1T = (bf16*)take((size_t)NET_H1 * np * 2);
+    w.h2 = (bf16*)take(2 * np * NET_H2 * 2);
+    w.h2_tn = (bf16*)take(np * NET_H2 * 2);
+    w.dh2 = (bf16*)take(np * NET_H2 * 2);
+    w.dh2T = (bf16*)take((size_t)NET_H2 * np * 2);
+    w.dh1 = (bf16*)take(np * NET_H1 * 2);
+    w.dh1T = (bf16*)take((size_t)NET_H1 * np * 2);
+    w.dX = (bf16*)take(np * NET_IN * 2);
+    w.idx = (uint8_t*)take(np * NET_CONV_OUT);
+    w.q = (float*)take(2 * np * 4 * sizeof(float));
+    w.bytes = off;
+    return w;
+}
+
+int check_net(maze_ctx* ctx, const maze_dqn_net* net, bool train) {
+    if (!net) return maze_fail_arg(ctx, MAZE_E_NULL, "net");
+    if (!net->params || !net->target || !net->w1_bf16 || !net->w2_bf16 || !net->tw1_bf16 || !net->tw2_bf16 || !net->workspace)
+        return maze_fail_arg(ctx, MAZE_E_NULL, "net pointer");
+    if (train && (!net->grads || !net->adam_m || !net->adam_v || !net->w1t_bf16 || !net->w2t_bf16 || !net->loss))
+        return maze_fail_arg(ctx, MAZE_E_NULL, "net training pointer");
+    if (((uintptr_t)net->params & 15) || ((uintptr_t)net->target & 15) || ((uintptr_t)net->workspace & 255))
+        return maze_fail_arg(ctx, MAZE_E_ALIGN, "net params (16 bytes) / workspace (256 bytes)");
+    return 0;
+}
+
+int features(maze_ctx* ctx, bool save_idx, const float* vec, const uint32_t* win, int n, const float* params, bf16* X, uint8_t* idx, cudaStream_t st) {
+    const int grid = n < ctx->num_sms * 6 ? n : ctx->num_sms * 6;
+    if (save_idx)
+        net_features_kernel<true><<<grid, FEAT_THREADS, 0, st>>>(vec, win, n, params + MAZE_NET_OFF_CONV_W, params + MAZE_NET_OFF_CONV_B, X, idx);
+    else
+        net_features_kernel<false><<<grid, FEAT_THREADS, 0, st>>>(vec, win, n, params + MAZE_NET_OFF_CONV_W, params + MAZE_NET_OFF_CONV_B, X, idx);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// X [rows, 1600] -> h1 [rows, 1024] -> h2 [rows, 512] with one net's weights
+int mlp_forward(maze_ctx* ctx, const bf16* X, int rows, const bf16* w1b, const bf16* w2b, const float* params, bf16* h1, bf16* h2, cudaStream_t st) {
+    GemmArgs g{};
+    g.M = rows; g.N = NET_H1; g.K = NET_IN; g.C = h1; g.ldc = NET_H1; g.bias = params + MAZE_NET_OFF_B1; g.act = ACT_LRELU;
+    if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, 256, X, NET_IN, w1b, NET_IN, g, 1, st)) return rc;
+    g = GemmArgs{};
+    g.M = rows; g.N = NET_H2; g.K = NET_H1; g.C = h2; g.ldc = NET_H2; g.bias = params + MAZE_NET_OFF_B2; g.act = ACT_RELU;
+    return launch_gemm(ctx, EPI_BIAS_ACT, 256, h1, NET_H1, w2b, NET_H1, g, 1, st);
+}
+
+int transpose(maze_ctx* ctx, const bf16* in, int R, int C, int ld_in, bf16* out, int ld_out, float* colsum, cudaStream_t st) {
+    const dim3 grid((C + 63) / 64, (R + 63) / 64);
+    net_transpose_kernel<<<grid, 256, 0, st>>>(in, R, C, ld_in, out, ld_out, colsum);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" int64_t maze_dqn_net_workspace_bytes(int max_batch) {
+    if (max_batch < 1) return -1;
+    return (int64_t)carve(nullptr, max_batch).bytes;
+}
+
+extern "C" int maze_dqn_gemm_bf16(maze_ctx* ctx, const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc, int M, int N, int K,
+                                  int epilogue, int act, const float* bias, const uint16_t* aux, int ldaux, int tile_n, int splits, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (!A || !B || !C) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_gemm_bf16 pointer");
+    if (epilogue < 0 || epilogue > 2 || act < 0 || act > 2 || (tile_n != 128 && tile_n != 256)) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_gemm_bf16 epilogue / act / tile_n");
+    if (epilogue == EPI_MASK && !aux) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_gemm_bf16: aux");
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.bias = bias; g.aux = reinterpret_cast<const bf16*>(aux); g.ldaux = ldaux; g.act = act;
+    return launch_gemm(ctx, epilogue, tile_n, reinterpret_cast<const bf16*>(A), lda, reinterpret_cast<const bf16*>(B), ldb, g, splits,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int maze_dqn_net_refresh(maze_ctx* ctx, const maze_dqn_net* net, int which, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = check_net(ctx, net, false)) return rc;
+    if (which != 0 && which != 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_net_refresh: which (0 source, 1 target)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* p = which ? net->target : net->params;
+    bf16* w1b = reinterpret_cast<bf16*>(which ? net->tw1_bf16 : net->w1_bf16);
+    bf16* w2b = reinterpret_cast<bf16*>(which ? net->tw2_bf16 : net->w2_bf16);
+    bf16* w1t = which ? nullptr : reinterpret_cast<bf16*>(net->w1t_bf16);
+    bf16* w2t = which ? nullptr : reinterpret_cast<bf16*>(net->w2t_bf16);
+    net_refresh_kernel<<<dim3(NET_IN / 32, NET_H1 / 32), 256, 0, st>>>(p + MAZE_NET_OFF_W1, NET_H1, NET_IN, w1b, w1t);
+    net_refresh_kernel<<<dim3(NET_H1 / 32, NET_H2 / 32), 256, 0, st>>>(p + MAZE_NET_OFF_W2, NET_H2, NET_H1, w2b, w2t);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int maze_dqn_features(maze_ctx* ctx, const maze_dqn_net* net, int which, const float* vec, const uint32_t* win, int n,
+                                 uint16_t* X, uint8_t* pool_idx, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = check_net(ctx, net, false)) return rc;
+    if (!vec || !win || !X) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_features pointer");
+    if (n < 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_features: n");
+    return features(ctx, pool_idx != nullptr, vec, win, n, which ? net->target : net->params, reinterpret_cast<bf16*>(X), pool_idx,
+                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int maze_dqn_forward(maze_ctx* ctx, const maze_dqn_net* net, int which, const float* vec, const uint32_t* win, int n, float* q_out,
+                                void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = check_net(ctx, net, false)) return rc;
+    if (!vec || !win || !q_out) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_forward pointer");
+    if (n < 1 || n > net->max_batch) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_forward: n (1 .. max_batch)");
+    if (which != 0 && which != 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_forward: which (0 source, 1 target)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace w = carve(net->workspace, net->max_batch);
+    const float* p = which ? net->target : net->params;
+    if (int rc = features(ctx, false, vec, win, n, p, w.X, nullptr, st)) return rc;
+    if (int rc = mlp_forward(ctx, w.X, n, reinterpret_cast<const bf16*>(which ? net->tw1_bf16 : net->w1_bf16),
+                             reinterpret_cast<const bf16*>(which ? net->tw2_bf16 : net->w2_bf16), p, w.h1, w.h2, st))
+        return rc;
+    const int grid = (n + 7) / 8 < ctx->num_sms * 4 ? (n + 7) / 8 : ctx->num_sms * 4;
+    net_head_q_kernel<<<grid, HEAD_THREADS, 0, st>>>(w.h2, n, p + MAZE_NET_OFF_W3, p + MAZE_NET_OFF_B3, q_out);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const float* vec, const uint32_t* win, const float* next_vec,
+                                 const uint32_t* next_win, const uint8_t* action, const float* reward, int n, float gamma, float* qsa_out,
+                                 void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = check_net(ctx, net, true)) return rc;
+    if (!vec || !win || !next_vec || !next_win || !action || !reward) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_backward pointer");
+    if (n < 8 || (n % 8) != 0 || n > net->max_batch) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_backward: n (multiple of 8, <= max_batch)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace w = carve(net->workspace, net->max_batch);
+    const size_t np = (size_t)w.np;   // the next-state half starts at row np of X / h1 / h2
+    const float* p = net->params;
+    float* gr = net->grads;
+    const bf16 *w1b = reinterpret_cast<const bf16*>(net->w1_bf16), *w2b = reinterpret_cast<const bf16*>(net->w2_bf16);
+    const bf16 *w1t = reinterpret_cast<const bf16*>(net->w1t_bf16), *w2t = reinterpret_cast<const bf16*>(net->w2t_bf16);
+    MAZE_CHECK(cudaMemsetAsync(net->loss, 0, sizeof(float), st));
+    // forward: source net on states and next states, target net on next states
+    if (int rc = features(ctx, true, vec, win, n, p, w.X, w.idx, st)) return rc;
+    if (int rc = features(ctx, false, next_vec, next_win, n, p, w.X + np * NET_IN, nullptr, st)) return rc;
+    if (np == (size_t)n) {
+        if (int rc = mlp_forward(ctx, w.X, 2 * n, w1b, w2b, p, w.h1, w.h2, st)) return rc;
+    } else {
+        if (int rc = mlp_forward(ctx, w.X, n, w1b, w2b, p, w.h1, w.h2, st)) return rc;
+        if (int rc = mlp_forward(ctx, w.X + np * NET_IN, n, w1b, w2b, p, w.h1 + np * NET_H1, w.h2 + np * NET_H2, st)) return rc;
+    }
+    // the target net has its own conv weights: its features differ from the source net's
+    bf16* Xt = w.dX;   // dX is free until the backward-data GEMM
+    if (int rc = features(ctx, false, next_vec, next_win, n, net->target, Xt, nullptr, st)) return rc;
+    if (int rc = mlp_forward(ctx, Xt, n, reinterpret_cast<const bf16*>(net->tw1_bf16), reinterpret_cast<const bf16*>(net->tw2_bf16), net->target,
+                             w.h1t_tn, w.h2_tn, st))
+        return rc;
+    {
+        const int grid = (n + 7) / 8 < ctx->num_sms * 2 ? (n + 7) / 8 : ctx->num_sms * 2;
+        net_head_loss_kernel<<<grid, HEAD_THREADS, 0, st>>>(w.h2, w.h2 + np * NET_H2, w.h2_tn, n, p + MAZE_NET_OFF_W3, p + MAZE_NET_OFF_B3,
+                                                           net->target + MAZE_NET_OFF_W3, net->target + MAZE_NET_OFF_B3, action, reward, gamma,
+                                                           w.dh2, gr + MAZE_NET_OFF_W3, gr + MAZE_NET_OFF_B3, net->loss, qsa_out);
+        MAZE_CHECK(cudaGetLastError());
+    }
+    // fc2: dW2 = dh2^T . h1, db2 = colsum(dh2), dh1 = (dh2 . W2) * LeakyReLU'(h1)
+    if (int rc = transpose(ctx, w.dh2, n, NET_H2, NET_H2, w.dh2T, w.np, gr + MAZE_NET_OFF_B2, st)) return rc;
+    if (int rc = transpose(ctx, w.h1, n, NET_H1, NET_H1, w.h1T, w.np, nullptr, st)) return rc;
+    const int splits = n >= 4096 ? 4 : (n >= 1024 ? 2 : 1);
+    GemmArgs g{};
+    g.M = NET_H2; g.N = NET_H1; g.K = n; g.C = gr + MAZE_NET_OFF_W2; g.ldc = NET_H1;
+    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh2T, w.np, w.h1T, w.np, g, splits * 2, st)) return rc;
+    g = GemmArgs{};
+    g.M = n; g.N = NET_H1; g.K = NET_H2; g.C = w.dh1; g.ldc = NET_H1; g.aux = w.h1; g.ldaux = NET_H1; g.act = ACT_LRELU;
+    if (int rc = launch_gemm(ctx, EPI_MASK, 256, w.dh2, NET_H2, w2t, NET_H2, g, 1, st)) return rc;
+    // fc1: dW1 = dh1^T . X, db1 = colsum(dh1), dX = dh1 . W1
+    if (int rc = transpose(ctx, w.dh1, n, NET_H1, NET_H1, w.dh1T, w.np, gr + MAZE_NET_OFF_B1, st)) return rc;
+    if (int rc = transpose(ctx, w.X, n, NET_IN, NET_IN, w.XT, w.np, nullptr, st)) return rc;
+    g = GemmArgs{};
+    g.M = NET_H1; g.N = NET_IN; g.K = n; g.C = gr + MAZE_NET_OFF_W1; g.ldc = NET_IN;
+    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh1T, w.np, w.XT, w.np, g, splits, st)) return rc;
+    g = GemmArgs{};
+    g.M = n; g.N = NET_CONV_OUT; g.K = NET_H1; g.C = w.dX; g.ldc = NET_IN; g.act = ACT_NONE;
+    if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, 256, w.dh1, NET_H1, w1t, NET_H1, g, 1, st)) return rc;
+    {
+        const int grid = n < ctx->num_sms * 4 ? n : ctx->num_sms * 4;
+        net_conv_bwd_kernel<<<grid, 256, 0, st>>>(w.dX, w.idx, win, n, gr + MAZE_NET_OFF_CONV_W, gr + MAZE_NET_OFF_CONV_B);
+        MAZE_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int maze_dqn_adamw(maze_ctx* ctx, const maze_dqn_net* net, float lr, float beta1, float beta2, float eps, float weight_decay,
+                              int64_t step, float grad_scale, float clamp, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (int rc = check_net(ctx, net, true)) return rc;
+    if (step < 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_adamw: step counts from 1");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    net_adamw_kernel<<<(MAZE_NET_PARAMS / 4 + 255) / 256, 256, 0, st>>>(net->params, net->grads, net->adam_m, net->adam_v, MAZE_NET_PARAMS, lr, beta1,
+                                                                        beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, clamp);
+    MAZE_CHECK(cudaGetLastError());
+    return maze_dqn_net_refresh(ctx, net, 0, stream);
+}
+
+extern "C" int maze_dqn_sample_packed(maze_ctx* ctx, const maze_replay* r, int n, uint64_t seed, uint64_t draw, float* vec, uint32_t* win,
+                                      float* next_vec, uint32_t* next_win, uint8_t* action, float* reward, void* stream) {
+    if (!ctx) return MAZE_E_NULL;
+    if (!r || !r->pushed || !r->vec || !r->next_vec || !r->win || !r->next_win || !r->action || !r->reward)
+        return maze_fail_arg(ctx, MAZE_E_NULL, "replay pointer");
+    if (n < 1 || r->capacity < 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_sample_packed: n / capacity");
+    if (!vec || !win || !next_vec || !next_win || !action || !reward) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_sample_packed output");
+    net_sample_packed_kernel<<<(n + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(*r, n, seed, draw, vec, win, next_vec, next_win, action, reward);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -50,7 +50,7 @@ maze_window_kernel(maze_env_batch b, float* __restrict__ window, double* __restr
             int r0 = st.r - WIN / 2, c0 = st.c - WIN / 2;
             if (!tor) {   // extract_submaze: clamped, and the reference uses len(maze) for both axes
                 r0 = min(max(r0, 0), H - WIN);
-                c0 = min(max(c0, 0), H - WIN);
+                c0 = min(max(c0, 0), W - WIN);   // the reference clamps with len(maze) (maze_handler.py:21-29: square mazes only); W keeps a non-square slot in bounds
             }
             const uint8_t* tab = b.table + (size_t)m * b.slot;
             const uint64_t pol_table = l2_policy<MAZE_TABLE_POLICY>();

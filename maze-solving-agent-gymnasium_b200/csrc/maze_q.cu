@@ -210,7 +210,7 @@ maze_q_rollout_kernel(maze_env_batch b, maze_q_agent ag, int k_steps, uint32_t m
     QCursor cur = load_cursor(ag, B, e);
     double reward = 0.0;
     int term = 0, trunc = 0;
-    unsigned long long n_episodes = 0, n_wins = 0;
+    unsigned long long n_episodes = 0, n_wins = 0, n_steps = 0;
     double return_sum = 0.0;
 
     for (int k = 0; k < k_steps; ++k) {
@@ -232,6 +232,7 @@ maze_q_rollout_kernel(maze_env_batch b, maze_q_agent ag, int k_steps, uint32_t m
         const int a = q_get_action(ag, B, e, cur, nullptr);
         const StepResult r = env_transition(b, e, st, mz, a, luts);
         reward = r.reward; term = r.term; trunc = r.trunc;
+        ++n_steps;
         const uint32_t next_slot = q_find_or_insert(ag, q_key(st, mz.goal, agent_id));
         cur.ep_return = __dadd_rn(cur.ep_return, reward);
         q_learn(ag, B, e, cur, next_slot, a, reward, term != 0, ag.gamma[agent_id]);
@@ -249,11 +250,13 @@ maze_q_rollout_kernel(maze_env_batch b, maze_q_agent ag, int k_steps, uint32_t m
     store_cursor(ag, B, e, cur);
     reinterpret_cast<int2*>(b.agent)[e] = make_int2(st.r, st.c);
     reinterpret_cast<int2*>(b.target)[e] = make_int2(mz.goal & 0xffff, mz.goal >> 16);
-    if (b.target_dirty && threadIdx.x == 0) *b.target_dirty = 1;
+    if (b.target_dirty) *b.target_dirty = 1;
     reinterpret_cast<int2*>(b.best_dir)[e] = best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, mz.H, mz.W, mz.tor);
     b.reward[e] = reward;
     b.terminated[e] = (uint8_t)term;
     b.truncated[e] = (uint8_t)trunc;
+    if (b.ep_return) b.ep_return[e] = (term | trunc) ? 0.0 : cur.ep_return;   // the agent's running return is the env's
+    if (b.stats && n_steps) atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 3), n_steps);
     if (b.stats && n_episodes) {
         atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 0), n_episodes);
         if (n_wins) atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 1), n_wins);

@@ -118,6 +118,7 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
         const int max_steps = __ldg(b.meta + (size_t)m[k] * MAZE_META_WORDS + MAZE_META_MAX_STEPS);
         double reward = 0.0;
         int term = 0, trunc = 0;
+        uint32_t rcode = MAZE_REC_REWARD(MAZE_REC_KIND_CONST, MAZE_REC_CONST_ZERO);   // how `reward` was obtained (packed record)
         bool wrapped = false;
         EnvState st = unpack_state(raw[k]);
 
@@ -130,12 +131,15 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
                     if (npos[k] == goal) {
                         reward = 1.0;   // base_maze_env.py:185-187
                         term = 1;
+                        rcode = MAZE_REC_REWARD(MAZE_REC_KIND_CONST, MAZE_REC_CONST_ONE);
                     } else {            // :189-192, len(path) = D_goal + 1
                         const int dd = ((st.tab >> MAZE_TAB_D4_SHIFT) - (tb[k] >> MAZE_TAB_D4_SHIFT)) & 3;
                         reward = dd == 1 ? luts.shaping_closer : (dd == 3 ? luts.shaping_farther : luts.shaping_same);
+                        rcode = MAZE_REC_REWARD(MAZE_REC_KIND_SHAPING, dd == 1 ? 2u : (dd == 3 ? 0u : 1u));
                     }
                 } else {
                     reward = __ldg(luts.revisit + cnt);   // :194
+                    rcode = MAZE_REC_REWARD(MAZE_REC_KIND_REVISIT, (uint32_t)cnt);
                 }
 #ifndef MAZE_EXP_NOVISIT
                 visit_store(VISIT_AT(b, e, vidx[k]), (unsigned)((st.epoch << 8) | (cnt < 255 ? cnt + 1 : 255)), pol);   // :196
@@ -150,12 +154,14 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
             } else {
                 st.consec = st.consec < 255 ? st.consec + 1 : 255;   // :199-200
                 reward = __ldg(luts.invalid + st.consec);
+                rcode = MAZE_REC_REWARD(MAZE_REC_KIND_INVALID, (uint32_t)st.consec);
                 st.flags &= ~(MAZE_ST_NEEDS_RESET | MAZE_ST_WON);
             }
             st.steps = st.steps < 65535 ? st.steps + 1 : 65535;
             if (st.steps > max_steps) {   // :205-208 (overrides a goal reward on the same step)
                 trunc = 1;
                 reward = -1.0;
+                rcode = MAZE_REC_REWARD(MAZE_REC_KIND_CONST, MAZE_REC_CONST_MINUS_ONE);
             }
             if (term | trunc) st.flags |= MAZE_ST_NEEDS_RESET | (term ? MAZE_ST_WON : 0);
         }
@@ -163,11 +169,14 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
         // epoch wrap-around: the visit array must really be cleared (rare)
         const unsigned need = __ballot_sync(0xffffffffu, wrapped);
         if (need) warp_clear_visits(need, b, e);
+        if (kStats && b.stats) {   // stats[3]: transitions made (autoreset steps are not transitions); one atomic per warp
+            const unsigned stepped = __ballot_sync(0xffffffffu, valid[k] && !do_reset[k]);
+            if (stepped && (threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 3), (unsigned long long)__popc(stepped));
+        }
 
         if (!valid[k]) continue;
 
         pol_store<MAZE_STATE_POLICY>(reinterpret_cast<unsigned long long*>(b.state) + e, (unsigned long long)pack_state(st), pol_state);
-        st_cs(reinterpret_cast<int2*>(b.agent) + e, make_int2(st.r, st.c));
         // `target` only changes when the env's maze does: the restart after a win (next pool maze, or the
         // regenerated slot).  The buffer persists between steps, so it is rewritten only then, and
         // target_dirty tells a host mirror that this launch touched it.
@@ -175,11 +184,17 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
             st_cs(reinterpret_cast<int2*>(b.target) + e, make_int2(goal & 0xffff, goal >> 16));
             if (b.target_dirty) *b.target_dirty = 1;
         }
-        st_cs(reinterpret_cast<int2*>(b.best_dir) + e,
-              best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, H, W, tor[k] != 0));
-        st_cs(b.reward + e, reward);
-        __stcs(b.terminated + e, (uint8_t)term);
-        __stcs(b.truncated + e, (uint8_t)trunc);
+        if (mode & MAZE_STEP_PACKED)
+            __stcs(b.packed + e, (uint32_t)st.r | ((uint32_t)st.c << 8) | ((uint32_t)((st.tab >> MAZE_TAB_CODE_SHIFT) & 7) << MAZE_REC_CODE_SHIFT) |
+                                     ((uint32_t)term << MAZE_REC_TERM_SHIFT) | ((uint32_t)trunc << MAZE_REC_TRUNC_SHIFT) | rcode);
+        if (!(mode & MAZE_STEP_NO_WIDE)) {
+            st_cs(reinterpret_cast<int2*>(b.agent) + e, make_int2(st.r, st.c));
+            st_cs(reinterpret_cast<int2*>(b.best_dir) + e,
+                  best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, H, W, tor[k] != 0));
+            st_cs(b.reward + e, reward);
+            __stcs(b.terminated + e, (uint8_t)term);
+            __stcs(b.truncated + e, (uint8_t)trunc);
+        }
 
         if (kStats) {
             if (b.ep_return) {
@@ -230,7 +245,7 @@ maze_reset_kernel(maze_env_batch b, const uint8_t* __restrict__ mask) {
     b.state[e] = pack_state(s);
     reinterpret_cast<int2*>(b.agent)[e] = make_int2(s.r, s.c);
     reinterpret_cast<int2*>(b.target)[e] = make_int2(goal & 0xffff, goal >> 16);
-    if (b.target_dirty && threadIdx.x == 0) *b.target_dirty = 1;
+    if (b.target_dirty) *b.target_dirty = 1;   // every selected thread: a masked reset need not include lane 0 (benign race)
     reinterpret_cast<int2*>(b.best_dir)[e] =
         best_dir_from_code((s.tab >> MAZE_TAB_CODE_SHIFT) & 7, s.r, s.c, H, W, tor);
     b.reward[e] = 0.0;
@@ -253,7 +268,7 @@ maze_step_many_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, int
     double reward = 0.0, ep_return = b.ep_return ? b.ep_return[e] : 0.0;
     int term = 0, trunc = 0;
     bool target_changed = false;
-    unsigned long long n_episodes = 0, n_wins = 0;
+    unsigned long long n_episodes = 0, n_wins = 0, n_steps = 0;
     double return_sum = 0.0;
     for (int k = 0; k < k_steps; ++k) {
         if ((mode & MAZE_STEP_AUTORESET) && (st.flags & MAZE_ST_NEEDS_RESET)) {
@@ -273,6 +288,7 @@ maze_step_many_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, int
             const StepResult r = env_transition(b, e, st, mz, __ldcs(actions + (size_t)k * B + e) & 3, luts);
             reward = r.reward; term = r.term; trunc = r.trunc;
             ep_return += reward;
+            ++n_steps;
             if (term | trunc) {
                 ++n_episodes;
                 n_wins += term;
@@ -300,6 +316,7 @@ maze_step_many_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, int
     b.terminated[e] = (uint8_t)term;
     b.truncated[e] = (uint8_t)trunc;
     if (b.ep_return) b.ep_return[e] = ep_return;
+    if (b.stats && n_steps) atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 3), n_steps);
     if (n_episodes) {
         if (b.stats) {
             atomicAdd(reinterpret_cast<unsigned long long*>(b.stats + 0), n_episodes);
@@ -342,6 +359,10 @@ extern "C" int maze_step(maze_ctx* ctx, const maze_env_batch* b, const uint8_t* 
     if (!ctx) return MAZE_E_NULL;
     if (int rc = maze_check_batch(ctx, b)) return rc;
     if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "actions");
+    if ((mode & MAZE_STEP_PACKED) && (!b->packed || ((uintptr_t)b->packed & 3)))
+        return maze_fail_arg(ctx, MAZE_E_NULL, "maze_step: MAZE_STEP_PACKED needs batch.packed ([B] uint32)");
+    if ((mode & MAZE_STEP_NO_WIDE) && !(mode & MAZE_STEP_PACKED))
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_step: MAZE_STEP_NO_WIDE without MAZE_STEP_PACKED would drop the step's outputs");
     const StepLuts luts = step_luts(ctx);
     const bool stats = b->ep_return || b->stats || ((mode & MAZE_STEP_WIN_QUEUE) && b->queue);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

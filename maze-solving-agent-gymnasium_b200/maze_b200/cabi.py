@@ -6,7 +6,7 @@ import os
 
 from .build import LIB_PATH
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -14,7 +14,8 @@ META_H, META_W, META_START, META_GOAL, META_MAX_STEPS, META_FLAGS, META_SOL_LEN,
 FLAG_TOROIDAL = 1
 TAB_OPEN, TAB_CODE_SHIFT, TAB_D4_SHIFT = 0x01, 1, 4
 ST_NEEDS_RESET, ST_WON, ST_MOVE_SHIFT, ST_NMOVES_SHIFT = 0x01, 0x02, 2, 4
-STEP_AUTORESET, STEP_WIN_NEXT, STEP_WIN_QUEUE = 0x01, 0x02, 0x04
+STEP_AUTORESET, STEP_WIN_NEXT, STEP_WIN_QUEUE, STEP_PACKED, STEP_NO_WIDE = 0x01, 0x02, 0x04, 0x08, 0x10
+REC_CODE_SHIFT, REC_TERM_SHIFT, REC_TRUNC_SHIFT, REC_KIND_SHIFT, REC_INDEX_SHIFT = 16, 19, 20, 21, 23
 ALGO_RPRIM, ALGO_DFS, ALGO_PRIMKILL = 0, 1, 2
 MAX_DIM, GEN_MAX_DIM, WINDOW = 255, 131, 15
 METRIC_WORDS = 8
@@ -37,7 +38,7 @@ class MazeEnvBatch(C.Structure):
         ("queue", C.c_void_p), ("queue_count", C.c_void_p),
         ("visit_cell_stride", C.c_int64), ("visit_env_stride", C.c_int64),
         ("visit_tiled", C.c_int32), ("visit_slot", C.c_int32),
-        ("target_dirty", C.c_void_p),
+        ("target_dirty", C.c_void_p), ("packed", C.c_void_p),
     ]
 
 
@@ -70,6 +71,24 @@ class MazeStepTrace(C.Structure):
                 ("truncated", C.c_void_p)]
 
 
+class MazeDqnNet(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("target", C.c_void_p), ("grads", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p),
+                ("w1_bf16", C.c_void_p), ("w2_bf16", C.c_void_p), ("w1t_bf16", C.c_void_p), ("w2t_bf16", C.c_void_p),
+                ("tw1_bf16", C.c_void_p), ("tw2_bf16", C.c_void_p), ("workspace", C.c_void_p), ("loss", C.c_void_p),
+                ("max_batch", C.c_int32), ("reserved", C.c_int32)]
+
+
+# flat parameter layout of the DQN / DDQN net (include/maze_b200.h MAZE_NET_*)
+NET_IN, NET_IN_USED, NET_H1, NET_H2 = 1600, 1574, 1024, 512
+NET_OFF_CONV_W, NET_OFF_CONV_B, NET_OFF_W1 = 0, 864, 896
+NET_OFF_B1 = NET_OFF_W1 + NET_H1 * NET_IN
+NET_OFF_W2 = NET_OFF_B1 + NET_H1
+NET_OFF_B2 = NET_OFF_W2 + NET_H2 * NET_H1
+NET_OFF_W3 = NET_OFF_B2 + NET_H2
+NET_OFF_B3 = NET_OFF_W3 + 4 * NET_H2
+NET_PARAMS = NET_OFF_B3 + 4
+
+
 class MazeError(RuntimeError):
     pass
 
@@ -85,6 +104,9 @@ SIGNATURES = {
     "maze_reward_lut": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "maze_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "maze_step": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_uint32, C.c_void_p]),
+    "maze_step_decode_host": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
+    "maze_bench_scatter_rmw": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint32,
+                                         C.c_int, C.c_void_p]),
     "maze_step_many": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_int, C.c_uint32, C.POINTER(MazeStepTrace),
                                  C.c_int, C.c_void_p]),
     "maze_reset": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_void_p]),
@@ -104,6 +126,16 @@ SIGNATURES = {
                                   C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "maze_difficulty": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
+    "maze_dqn_net_workspace_bytes": (C.c_int64, [C.c_int]),
+    "maze_dqn_net_refresh": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet), C.c_int, C.c_void_p]),
+    "maze_dqn_forward": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "maze_dqn_features": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "maze_dqn_backward": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet)] + [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "maze_dqn_adamw": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet)] + [C.c_float] * 5 + [C.c_int64, C.c_float, C.c_float, C.c_void_p]),
+    "maze_dqn_sample_packed": (C.c_int, [C.c_void_p, C.POINTER(MazeReplay), C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 7),
+    "maze_dqn_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "maze_sizeof": (C.c_int, [C.c_int]),
     "maze_render": (C.c_int, [C.c_void_p, C.POINTER(MazeEnvBatch), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "maze_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
@@ -177,6 +209,36 @@ def reward_lut(kind: int):
     if rc != 0:
         raise MazeError(f"maze_reward_lut({kind}) -> {rc}")
     return np.array(out, dtype=np.float64)
+
+
+def reward_table():
+    """float64 [4, 256]: reward = table[kind, index] of a packed step record (include/maze_b200.h MAZE_REC_*)."""
+    import numpy as np
+    t = np.zeros((4, 256), dtype=np.float64)
+    t[0], t[1] = reward_lut(0), reward_lut(1)
+    t[2, :3] = reward_lut(2)[:3]
+    t[3, :3] = (0.0, 1.0, -1.0)
+    return t
+
+
+def decode_records(records, shape=None, toroidal=None):
+    """Packed step records (uint32 [n]) -> dict(agent [n, 2] int32, best_dir [n, 2] int32, reward [n] float64,
+    terminated / truncated [n] bool), bit-identical to maze_step's wide outputs.  Runs the library's host-side C loop
+    (maze_step_decode_host); shape [n, 2] int32 and toroidal [n] uint8 are needed for toroidal envs only."""
+    import numpy as np
+    rec = np.ascontiguousarray(records).view(np.uint32).reshape(-1)
+    n = rec.shape[0]
+    out = dict(agent=np.empty((n, 2), np.int32), best_dir=np.empty((n, 2), np.int32), reward=np.empty(n, np.float64),
+               terminated=np.empty(n, np.uint8), truncated=np.empty(n, np.uint8))
+    sh = None if shape is None else np.ascontiguousarray(shape, dtype=np.int32)
+    to = None if toroidal is None else np.ascontiguousarray(toroidal, dtype=np.uint8)
+    rc = lib().maze_step_decode_host(rec.ctypes.data, n, None if sh is None else sh.ctypes.data, None if to is None else to.ctypes.data,
+                                     out["agent"].ctypes.data, out["best_dir"].ctypes.data, out["reward"].ctypes.data,
+                                     out["terminated"].ctypes.data, out["truncated"].ctypes.data)
+    if rc != 0:
+        raise MazeError(f"maze_step_decode_host -> {rc}")
+    out["terminated"], out["truncated"] = out["terminated"].view(np.bool_), out["truncated"].view(np.bool_)
+    return out
 
 
 def ptr(t):

@@ -29,8 +29,8 @@ class DeviceReplay:
         self.batch = env.batch if hasattr(env, "batch") else env
         self.device, self.ctx = self.batch.device, self.batch.ctx
         self.capacity = int(capacity)
-        if self.capacity < 1:
-            raise ValueError("capacity must be positive")
+        if self.capacity < self.batch.num_envs:
+            raise ValueError("capacity must be at least num_envs (one push launch claims up to num_envs slots of the ring)")
         B, d, W = self.batch.num_envs, self.device, cabi.WINDOW_WORDS
         self.pushed = torch.zeros(1, dtype=torch.int64, device=d)
         self.vec = torch.zeros((self.capacity, 6), dtype=torch.float32, device=d)
@@ -69,10 +69,33 @@ class DeviceReplay:
         """(vec [B, 6] float32, window [B, 3, 15, 15] float32) of the staged observation."""
         return self.stage_vec, unpack_windows(self.stage_win)
 
-    def sample(self, n: int):
-        """-> (vec, window), action [n] int64, reward [n] float32, (next_vec, next_window)."""
+    def sample_packed(self, n: int, check: bool = False):
+        """memory.sample(n) for the tensor-core net (maze_b200.dqn_net.DQNNet): windows stay bit-packed.
+        -> vec [n, 6] f32, win [n, 24] i32, next_vec, next_win, action [n] u8, reward [n] f32 (the same transitions
+        sample() returns for the same draw).  check=True raises when fewer than n transitions are stored (one sync)."""
+        if check and len(self) < n:
+            raise ValueError(f"replay holds {len(self)} transitions, fewer than the batch of {n} (ddqn_agent.py:114-115 returns)")
+        d, W = self.device, cabi.WINDOW_WORDS
+        if getattr(self, "_packed_out", None) is None or self._packed_out["vec"].shape[0] != n:
+            self._packed_out = dict(vec=torch.zeros((n, 6), dtype=torch.float32, device=d), win=torch.zeros((n, W), dtype=torch.int32, device=d),
+                                    next_vec=torch.zeros((n, 6), dtype=torch.float32, device=d), next_win=torch.zeros((n, W), dtype=torch.int32, device=d),
+                                    action=torch.zeros(n, dtype=torch.uint8, device=d), reward=torch.zeros(n, dtype=torch.float32, device=d))
+        o = self._packed_out
+        self._draw += 1
+        rc = cabi.lib().maze_dqn_sample_packed(self.ctx.handle, C.byref(self._c), int(n), self.seed & (2**64 - 1), self._draw,
+                                               cabi.ptr(o["vec"]), cabi.ptr(o["win"]), cabi.ptr(o["next_vec"]), cabi.ptr(o["next_win"]),
+                                               cabi.ptr(o["action"]), cabi.ptr(o["reward"]), self._stream())
+        self.ctx.check(rc, "maze_dqn_sample_packed")
+        return o["vec"], o["win"], o["next_vec"], o["next_win"], o["action"], o["reward"]
+
+    def sample(self, n: int, check: bool = True):
+        """-> (vec, window), action [n] int64, reward [n] float32, (next_vec, next_window).  Raises when the ring is
+        empty (check=True costs one device sync; the reference returns early while len(memory) < batch_size,
+        ddqn_agent.py:114-115)."""
+        if check and len(self) == 0:
+            raise ValueError("the replay ring is empty")
         d = self.device
-        out = dict(vec=torch.empty((n, 6), dtype=torch.float32, device=d), win=torch.empty((n, 3, cabi.WINDOW, cabi.WINDOW), dtype=torch.float32, device=d),
+        out = dict(vec=torch.zeros((n, 6), dtype=torch.float32, device=d), win=torch.zeros((n, 3, cabi.WINDOW, cabi.WINDOW), dtype=torch.float32, device=d),
                    next_vec=torch.empty((n, 6), dtype=torch.float32, device=d),
                    next_win=torch.empty((n, 3, cabi.WINDOW, cabi.WINDOW), dtype=torch.float32, device=d),
                    action=torch.empty(n, dtype=torch.int64, device=d), reward=torch.empty(n, dtype=torch.float32, device=d))

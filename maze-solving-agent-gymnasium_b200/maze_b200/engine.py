@@ -253,6 +253,7 @@ class MazeBatch:
         self.queue = torch.zeros(B, dtype=torch.int32, device=d) if queue else None
         self.queue_count = torch.zeros(1, dtype=torch.int32, device=d) if queue else None
         self.target_dirty = torch.zeros(1, dtype=torch.int32, device=d)   # set by launches that write `target`
+        self.packed = torch.zeros(B, dtype=torch.int32, device=d)         # packed step records (cabi.STEP_PACKED)
         self.pool_stride = int(pool_stride)
         self._c = self._make_struct()
 
@@ -290,7 +291,7 @@ class MazeBatch:
             visit_cell_stride=self.num_envs if self.visit_layout == "cell" else 1,
             visit_env_stride=1 if self.visit_layout == "cell" else self.visit_slot,
             visit_tiled=1 if self.visit_layout == "tile" else 0, visit_slot=self.visit_slot,
-            target_dirty=self.target_dirty.data_ptr())
+            target_dirty=self.target_dirty.data_ptr(), packed=self.packed.data_ptr())
 
     def reset(self, mask: Optional[torch.Tensor] = None):
         if mask is not None:

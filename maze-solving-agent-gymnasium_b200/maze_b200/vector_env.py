@@ -94,6 +94,9 @@ class MazeVectorEnv(_VectorBase):
         self.slot_id_base = int(slot_id_base)
         self.enrich = bool(enrich)
         self.candidates = int(candidates)
+        if self.enrich and self.shape[0] != self.shape[1]:
+            raise ValueError("the enriched observation needs square mazes: the reference clamps the window's columns with the "
+                             "row count (lib/maze_handler.py:21-29)")
         if self.enrich and min(self.shape) < cabi.WINDOW:
             raise ValueError(f"the enriched observation needs mazes of at least {cabi.WINDOW} x {cabi.WINDOW} blocks")
         if pool is None:
@@ -141,6 +144,7 @@ class MazeVectorEnv(_VectorBase):
         self._d_actions = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
         self._h_out = None
         self._h_flag = None
+        self._h_packed = None
         self._h_bytes, self._h_calls = 0, 0
 
     # ------------------------------------------------------------------------------------------
@@ -181,15 +185,25 @@ class MazeVectorEnv(_VectorBase):
         self._d_actions.copy_(self._h_actions, non_blocking=True)
         return self._d_actions
 
-    def step(self, actions):
+    def drain_regeneration(self):
+        """Regenerate the maze slots whose env won on the previous step (the analogue of update_maze(),
+        off_policy_trainer.py:60-71 / :190-214).  It runs at the START of the next step(), right before the kernel
+        that autoresets those envs: everything the caller does with the terminal step in between -- the terminal
+        observation and window, DeviceReplay.push, maze_q_update -- still sees the maze the episode was played on, as
+        in the reference, where next_obs comes from env.step() before update_maze().  The three launches are
+        device-side no-ops when the queue is empty (its length is read on the device)."""
         b = self.batch
-        b.step(self._device_actions(actions), self._mode)
+        if self.grow or self.algorithm_schedule:
+            self.pool.curriculum(b.queue, b.queue_count, self.wins, self.grow, self.algorithm_schedule)
+        self.pool.generate(ids=b.queue, count_dev=b.queue_count, configure=False, seed=self.seed,
+                           slot_id_base=self.slot_id_base, candidates=self.candidates)
+        b.queue_count.zero_()
+
+    def step(self, actions, extra_mode: int = 0):
+        b = self.batch
         if self.on_win == "regenerate":
-            if self.grow or self.algorithm_schedule:
-                self.pool.curriculum(b.queue, b.queue_count, self.wins, self.grow, self.algorithm_schedule)
-            self.pool.generate(ids=b.queue, count_dev=b.queue_count, configure=False, seed=self.seed,
-                               slot_id_base=self.slot_id_base, candidates=self.candidates)
-            b.queue_count.zero_()
+            self.drain_regeneration()
+        b.step(self._device_actions(actions), self._mode | extra_mode)
         term, trunc = b.terminated.view(torch.bool), b.truncated.view(torch.bool)
         if self.reference_order:
             return self._obs(), b.reward, trunc, term, _LazyInfo(self)
@@ -227,6 +241,47 @@ class MazeVectorEnv(_VectorBase):
         if self.enrich:
             per += 3 * cabi.WINDOW * cabi.WINDOW * 4 + 2 * 16
         return self.num_envs * per
+
+    def step_host_packed(self, actions: np.ndarray, decode: bool = False):
+        """step_host() over the packed wire format: one host-to-device copy (actions), one kernel that writes a
+        single uint32 record per env instead of the 26 bytes of wide outputs (MAZE_STEP_PACKED | MAZE_STEP_NO_WIDE),
+        one device-to-host copy, one stream synchronisation.  Returns the pinned uint32 [B] record array (a view:
+        the next call overwrites it); `decode=True` returns what step_host() returns, bit for bit, by running
+        cabi.decode_records on it (a host-side C loop; `target` and the per-env shapes are refreshed from the
+        device only on the steps whose launch changed a maze).  -v0 observations only."""
+        if self.enrich:
+            raise cabi.MazeError("the packed wire format carries the -v0 observation; use step_host() with enrich=True")
+        b = self.batch
+        self.step(actions, extra_mode=cabi.STEP_PACKED | cabi.STEP_NO_WIDE)
+        if self._h_packed is None:
+            self._h_packed = torch.empty(self.num_envs, dtype=torch.int32, pin_memory=True)
+            self._h_flag = torch.ones(1, dtype=torch.int32, pin_memory=True)
+            self._h_target = torch.empty((self.num_envs, 2), dtype=torch.int32, pin_memory=True)
+            self._h_shape = torch.empty((self.num_envs, 2), dtype=torch.int32, pin_memory=True)
+            self._h_tor = torch.empty(self.num_envs, dtype=torch.uint8, pin_memory=True)
+        self._h_packed.copy_(b.packed, non_blocking=True)
+        self._h_flag.copy_(b.target_dirty, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device)
+        stream.synchronize()
+        nbytes = 4 * self.num_envs + 4
+        if int(self._h_flag[0]) != 0:   # a maze changed under some env: refresh target / shape / topology mirrors
+            b.target_dirty.zero_()
+            meta = self.pool.meta[b.env_maze.long()]
+            self._h_target.copy_(b.target, non_blocking=True)
+            self._h_shape.copy_(meta[:, :2].contiguous(), non_blocking=True)
+            self._h_tor.copy_((meta[:, cabi.META_FLAGS] & cabi.FLAG_TOROIDAL).to(torch.uint8), non_blocking=True)
+            stream.synchronize()
+            nbytes += self.num_envs * (8 + 8 + 1)
+        self._h_bytes += nbytes
+        self._h_calls += 1
+        rec = self._h_packed.numpy().view(np.uint32)
+        if not decode:
+            return rec
+        d = cabi.decode_records(rec, self._h_shape.numpy(), self._h_tor.numpy())
+        obs = {"agent": d["agent"], "target": self._h_target.numpy(), "best dir": d["best_dir"]}
+        if self.reference_order:
+            return obs, d["reward"], d["truncated"], d["terminated"], {}
+        return obs, d["reward"], d["terminated"], d["truncated"], {}
 
     def step_host(self, actions: np.ndarray):
         """Same transition as step() with HOST buffers on both sides: actions are copied to the

@@ -110,7 +110,13 @@ def run_trace(env, toroidal, n_steps, follow_p, rng, enrich):
     return {k: np.array(v) for k, v in rec.items()}
 
 
-def make_steps(out_path):
+def make_steps(out_path, specs=None, seed0=1000, budget81=90):
+    if specs is None:
+        specs = _default_step_specs()
+    _make_steps(out_path, specs, seed0, budget81)
+
+
+def _default_step_specs():
     specs = []
     for topo in ("euclid", "torus"):
         for algo in ("r-prim", "dfs", "prim&kill"):
@@ -120,10 +126,14 @@ def make_steps(out_path):
               ("euclid", "prim&kill", 15, False), ("torus", "r-prim", 15, False),
               ("euclid", "r-prim", 21, True), ("euclid", "dfs", 41, True), ("euclid", "prim&kill", 15, True),
               ("torus", "r-prim", 21, True), ("torus", "prim&kill", 41, True)]
+    return specs
+
+
+def _make_steps(out_path, specs, seed0, budget81):
     arrays, meta = {}, []
     for i, (topo, algo, shape, enrich) in enumerate(specs):
-        random.seed(1000 + i)
-        np.random.seed(1000 + i)
+        random.seed(seed0 + i)
+        np.random.seed(seed0 + i)
         BaseMazeEnv.ALGORITHM = algo
         toroidal = topo == "torus"
         cls = {(False, False): SimpleMazeEnv, (False, True): SimpleEnrichMazeEnv,
@@ -132,7 +142,7 @@ def make_steps(out_path):
         env = cls((shape, shape))
         rng = random.Random(77 + i)
         tapes = []
-        budget = 90 if shape == 81 else 260
+        budget = budget81 if shape == 81 else 260
         for j, (follow_p, n) in enumerate(((0.0, budget), (0.75, budget), (1.0, min(budget, env.max_steps_taken + 6)))):
             tr = run_trace(env, toroidal, n, follow_p, rng, enrich)
             for k, v in tr.items():
@@ -147,13 +157,14 @@ def make_steps(out_path):
     np.savez_compressed(out_path, **arrays)
 
 
-def make_bestdir(out_path):
+def make_bestdir(out_path, specs=None, seed0=2000):
     arrays, meta = {}, []
-    specs = [("euclid", a, s) for a in ("r-prim", "dfs", "prim&kill") for s in (15, 21, 41)]
-    specs += [("torus", a, s) for a in ("r-prim", "dfs", "prim&kill") for s in (15, 21, 41)]
-    specs += [("euclid", "dfs", 61), ("torus", "dfs", 61)]
+    if specs is None:
+        specs = [("euclid", a, s) for a in ("r-prim", "dfs", "prim&kill") for s in (15, 21, 41)]
+        specs += [("torus", a, s) for a in ("r-prim", "dfs", "prim&kill") for s in (15, 21, 41)]
+        specs += [("euclid", "dfs", 61), ("torus", "dfs", 61)]
     for i, (topo, algo, shape) in enumerate(specs):
-        random.seed(2000 + i)
+        random.seed(seed0 + i)
         BaseMazeEnv.ALGORITHM = algo
         toroidal = topo == "torus"
         env = (ToroidalMazeEnv if toroidal else SimpleMazeEnv)((shape, shape))
@@ -325,15 +336,34 @@ def _metric_table_job(args):
     return (r["difficulty"], r["complexity"], r["L"], r["DE"], r["D"])
 
 
-def make_metric_table(out_path, n=120):
+def make_metric_table_1000(out_path):
+    """Round 2: the README table at the README's own sample size (1000 mazes of (81, 81) per generator)."""
+    make_metric_table(out_path, n=1000, seed0=170000, procs=max(1, (os.cpu_count() or 2) - 2))
+
+
+def make_steps81(out_path):
+    """Round 2: reference traces at the headline size for the generator x topology pairs steps.npz lacks."""
+    specs = [("euclid", "prim&kill", 81, False), ("euclid", "dfs", 81, False), ("torus", "r-prim", 81, False),
+             ("torus", "prim&kill", 81, False), ("euclid", "r-prim", 81, True)]
+    make_steps(out_path, specs=specs, seed0=1500, budget81=160)
+
+
+def make_bestdir81(out_path):
+    """Round 2: _find_best_next_cell on every open block of 81 x 81 dfs mazes (goal farther than the A* depth
+    limit L = 162 from most blocks: the D > L branch of the closed form) and one r-prim maze per topology."""
+    specs = [("euclid", "dfs", 81), ("torus", "dfs", 81), ("euclid", "r-prim", 81), ("torus", "prim&kill", 81)]
+    make_bestdir(out_path, specs=specs, seed0=2500)
+
+
+def make_metric_table(out_path, n=120, seed0=70000, procs=None):
     """The README table (generation_algos_metrics_evaluations.py:31-43) as per-maze samples: n mazes
     of (81, 81) per generator from the unmodified reference, columns difficulty, complexity, L, DE, D."""
     import multiprocessing as mp
     out = {}
-    with mp.get_context("fork").Pool(os.cpu_count() or 1) as pool:
+    with mp.get_context("fork").Pool(procs or os.cpu_count() or 1) as pool:
         for k, algo in enumerate(("r-prim", "prim&kill", "dfs")):
             t0 = time.time()
-            rows = pool.map(_metric_table_job, [(algo, 70000 + 1000 * k + i) for i in range(n)])
+            rows = pool.map(_metric_table_job, [(algo, seed0 + 1000 * k + i) for i in range(n)], chunksize=4)
             out[algo] = np.array(rows, dtype=np.float64)
             print(f"metric_table {algo} n={n} mean={out[algo].mean(axis=0)} max_difficulty={out[algo][:, 0].max():.2f} {time.time()-t0:.0f}s", flush=True)
     np.savez_compressed(out_path, **out)
@@ -373,6 +403,7 @@ if __name__ == "__main__":
     for w in which:
         t0 = time.time()
         {"steps": make_steps, "bestdir": make_bestdir, "metrics": make_metrics, "qagent": make_qagent,
-         "genstats": make_genstats, "metric_table": make_metric_table, "metrics_ext": make_metrics_ext}[w](
+         "genstats": make_genstats, "metric_table": make_metric_table, "metrics_ext": make_metrics_ext,
+         "metric_table_1000": make_metric_table_1000, "steps81": make_steps81, "bestdir81": make_bestdir81}[w](
             os.path.join(HERE, f"{w}.npz"))
         print(f"== {w}.npz written in {time.time()-t0:.0f}s", flush=True)

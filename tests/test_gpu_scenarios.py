@@ -60,6 +60,7 @@ def test_config3_toroidal_mixed_generators_regenerate_on_win():
                 pending[e] = bool(ote or otr)
                 regenerated += int(ote)
             assert tuple(o["agent"]) == tuple(ag[e]), (t, e)
+    env.drain_regeneration()   # the winners of the last step (their slots are regenerated at the start of the next one)
     stats = env.episode_statistics()
     assert regenerated > 20 and stats["wins"] == regenerated
     gen_counts = pool.meta_host()[:, mb.cabi.META_SPARE]
@@ -118,6 +119,7 @@ def test_config4_variable_size_curriculum_with_double_q():
         obs, _, _, _, _ = env.step(acts)
         agent.update()
     agent.core.check_overflow()
+    env.drain_regeneration()
     wins = env.wins.cpu().numpy()
     meta = env.pool.meta_host()
     assert wins.max() >= 2 and wins.sum() > B and env.episode_statistics()["wins"] == wins.sum()
@@ -182,3 +184,69 @@ def test_checkpoint_resume_is_bit_identical(tmp_path, on_win):
     a, b = other.episode_statistics(), env.episode_statistics()
     assert {k: v for k, v in a.items() if k != "return_sum"} == {k: v for k, v in b.items() if k != "return_sum"}
     assert a["return_sum"] == pytest.approx(b["return_sum"], rel=1e-12)   # float atomics: summation order varies
+
+
+@pytest.mark.parametrize("topology", ["euclid", "toroidal"])
+def test_terminal_observation_and_replay_see_the_maze_the_episode_was_played_on(topology):
+    """Regenerate-on-win with the enriched observation and the device replay ring: the observation returned by the
+    winning step, the window pushed as next_state and the re-staged state all come from the OLD maze (the reference
+    takes next_obs from env.step() before update_maze(), off_policy_trainer.py:160-171); the new maze appears with the
+    autoreset of the following step."""
+    import maze_b200 as mb
+    from maze_b200.dqn import DeviceReplay, unpack_windows
+    B, S = 64, 15
+    tor = topology == "toroidal"
+    env = mb.MazeVectorEnv(B, shape=(S, S), topology=topology, algorithms=["r-prim", "dfs", "prim&kill"], seed=21, on_win="regenerate",
+                           enrich=True, stats=True)
+    mem = DeviceReplay(env, 1 << 14, seed=1)
+    obs, _ = env.reset()
+    mem.observe()
+    pool = env.pool
+
+    def oracle_for(e):
+        meta = pool.meta_host()[e]
+        return ClosedFormEnv(pool.grid_host(e).copy(), _meta_rc(meta[2]), _meta_rc(meta[3]), tor, enrich=True)
+
+    cur = [oracle_for(e) for e in range(B)]
+    for o in cur:
+        o.reset()
+    pending = np.zeros(B, bool)
+    rng = np.random.default_rng(4)
+    wins = 0
+    for t in range(260):
+        best = env.batch.best_dir.cpu().numpy()
+        greedy = np.zeros(B, dtype=np.uint8)
+        for a, (dr, dc) in enumerate(((1, 0), (-1, 0), (0, 1), (0, -1))):
+            hit = (np.sign(best[:, 0]) * (np.abs(best[:, 0]) == 1) == -dr) & (np.sign(best[:, 1]) * (np.abs(best[:, 1]) == 1) == -dc)
+            wrap = ((best[:, 0] == dr * (S - 1)) & (dr != 0) & (best[:, 1] == 0)) | ((best[:, 1] == dc * (S - 1)) & (dc != 0) & (best[:, 0] == 0))
+            greedy[hit | wrap] = a
+        acts = np.where(rng.random(B) < 0.85, greedy, rng.integers(0, 4, B)).astype(np.uint8)
+        acts_d = torch.from_numpy(acts).cuda()
+        obs, rew, term, trunc, _ = env.step(acts_d)
+        mem.push(acts_d)
+        win, an, tn = obs["window"].cpu().numpy(), obs["agent"].cpu().numpy(), obs["target"].cpu().numpy()
+        staged = unpack_windows(mem.stage_win).cpu().numpy()
+        svec = mem.stage_vec.cpu().numpy()
+        te = term.cpu().numpy()
+        for e in range(B):
+            if pending[e]:
+                cur[e] = oracle_for(e)
+                o, _ = cur[e].reset()
+                pending[e] = False
+            else:
+                o, r, otr, ote, _ = cur[e].step(int(acts[e]))
+                assert bool(ote) == bool(te[e]), (t, e)
+                pending[e] = bool(ote or otr)
+                wins += int(ote)
+            np.testing.assert_array_equal(win[e], o["window"], err_msg=f"window env {e} step {t} (terminal: {bool(te[e])})")
+            np.testing.assert_array_equal(an[e].view(np.uint64), np.asarray(o["agent"], np.float64).view(np.uint64))
+            np.testing.assert_array_equal(tn[e].view(np.uint64), np.asarray(o["target"], np.float64).view(np.uint64))
+            np.testing.assert_array_equal(staged[e], o["window"], err_msg=f"staged window env {e} step {t}")
+            np.testing.assert_array_equal(svec[e, :4], np.concatenate([o["agent"], o["target"]]).astype(np.float32))
+    assert wins > 15
+    # every goal transition in the ring ends ON its own episode's goal: next_state agent == next_state target
+    n = len(mem)
+    goal = (mem.reward[:n] == 1.0)
+    assert int(goal.sum()) == wins
+    nv = mem.next_vec[:n][goal]
+    assert torch.equal(nv[:, 0:2], nv[:, 2:4])
