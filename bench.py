@@ -9,6 +9,13 @@ Workload (per GPU): a pool of 1000 r-prim euclidean 81x81 mazes generated on the
 (Philox seed 1234), B envs = 1000 mazes x A agents, uniform random actions from a device-resident
 tape, gymnasium next-step autoreset on.  One "step" = one maze_step launch over all B envs.
 Prints ONE JSON line (rank 0).
+
+    python bench.py --workload toroidal-regen     # configs[2]: toroidal 81x81, mixed generators, regenerate on every win
+    python bench.py --workload curriculum-dq      # configs[3]: 21x21 -> 129x129 curriculum, double Q-learning on the device
+    python bench.py --workload ddqn               # configs[4]: DDQN loop, 8192 envs per GPU, NCCL gradient all-reduce
+
+(the other configs of BASELINE.json as one-line measurements of the same shape; the default is configs[1], the
+configuration the headline metric is quoted on).
 """
 from __future__ import annotations
 
@@ -38,6 +45,23 @@ def workload_name(envs_per_gpu):
             f"{envs_per_gpu} envs per GPU, uniform random actions, autoreset")
 
 
+def workload_config(envs_per_gpu, world):
+    """The `config` object of the line: identical for this repo's arm and the reference arm."""
+    return {"workload": workload_name(envs_per_gpu), "envs_per_gpu": envs_per_gpu, "mazes_per_gpu": NUM_MAZES,
+            "l2": "inputs larger than L2: per-step working set (~100 B x envs = 400 MB) and the 13 KB/env visit arrays exceed the 126 MB L2; no flush needed",
+            "parallelism": f"env-index sharding over {world} GPU(s), no per-step collective"}
+
+
+def pattern_peak():
+    """The scattered read-modify-write micro-benchmark of this access pattern (tools/perf_scatter_rmw.py, committed
+    summary in profiles/): what HBM3e + L2 give 'coalesced streams + one 2-byte RMW at a random 64-byte atom for 40 %
+    of the envs' with no maze logic at all."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_scatter_rmw.json")))
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
@@ -52,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "5"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -122,10 +146,14 @@ def run_reference(args, rank):
     one worker process per host core, each 'step' a bounded sample."""
     if rank != 0:
         return None
+    from oracle import ref_runtime
     from oracle.baseline import PersistentVector
     cores = os.cpu_count() or 1
-    mazes = reference_mazes(min(cores, 8))
-    vec = PersistentVector(mazes, cores, "port")
+    # baseline/_ref (a copy of the unmodified reference, tools/install_reference.py) present -> time the reference's own
+    # SimpleMazeEnv; otherwise the oracle's port of it
+    kind = "reference" if ref_runtime.available() and not os.environ.get("MAZE_REF_FORCE_PORT") else "port"
+    mazes = reference_mazes(min(cores, 8) if kind == "port" else 1)
+    vec = PersistentVector(mazes, cores, kind)
     # A 'step' is a fixed slice of wall time in which every worker steps its own env as fast as it can (free running:
     # the best this implementation can do on the box -- stepping the envs in lock step like gymnasium's
     # AsyncVectorEnv would wait for the slowest A* search every time and lands at about 40 % of this rate).  The slice
@@ -140,14 +168,17 @@ def run_reference(args, rank):
         steps += r["steps"]; secs += r["seconds"]
     vec.close()
     value = steps / secs
+    what = ("the unmodified reference's gymnasium_env.envs.simple_maze_env.SimpleMazeEnv((81, 81)) from baseline/_ref (gymnasium / pygame "
+            "stubbed to no-ops: an upper bound on its speed) on its own r-prim maze" if kind == "reference" else
+            "the oracle port (A* per step) of the reference env on an 81x81 r-prim maze")
     sample = (f"{args.steps} steps x {per * 1e3:.0f} ms x {cores} free-running worker processes ({steps} env-steps in {secs:.1f} s), each "
-              f"worker stepping the oracle port (A* per step) of the reference env on an 81x81 r-prim maze, random actions, reset on done")
+              f"worker stepping {what}, random actions, reset on done")
     return ({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.envs_per_gpu), "arm": "CPU, oracle port of the reference algorithm"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.envs_per_gpu, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -258,6 +289,35 @@ def measure_extras(mb, torch, device):
     return out
 
 
+def pattern_summary(step_us, B):
+    """Where the step kernel stands against the measured rate of its own access pattern."""
+    p = pattern_peak()
+    if not p or p.get("envs") != B:
+        return None
+    return {"what": "tools/perf_scatter_rmw.py on this batch: maze_step's coalesced streams plus one 2-byte read-modify-write at a scattered "
+                    "64-byte atom for 40 % of the envs, no maze logic (committed summary: profiles/r02_scatter_rmw.json)",
+            "streams_only_us": p["streams_only_us"], "rmw_only_us": p["rmw_only_cell_major_per_env_us"],
+            "streams_plus_rmw_us": p["streams_plus_rmw_cell_major_per_env_us"], "maze_step_us_same_run": p["maze_step_us"],
+            "frac_of_pattern_same_run": p["streams_plus_rmw_cell_major_per_env_us"] / p["maze_step_us"],
+            "frac_of_pattern_this_run": p["streams_plus_rmw_cell_major_per_env_us"] / step_us}
+
+
+def secondary_metrics(extra):
+    """BASELINE.json's second metric and its neighbours as a driver-parsed list."""
+    if not extra:
+        return None
+    out = []
+    for algo, v in extra["mazes_per_s_81x81"].items():
+        out.append({"metric": f"valid mazes generated/sec (40x40, {algo}, per GPU)", "value": v, "unit": "mazes/s",
+                    "roofline": {"bound": "sm issue slots (sequential carving)", "issue_slots_busy": 0.77,
+                                 "source": "ncu profiles/r01f_gen_warp_details.txt (maze_generate_warp_kernel)"}})
+    out.append({"metric": "valid mazes kept/sec, best of 6 by McClendon difficulty (40x40, r-prim, per GPU)", "value": extra["best_of_6_mazes_per_s_81x81"],
+                "unit": "mazes/s"})
+    out.append({"metric": "difficulty metrics (MD, MC, ML, MDE, MDs) mazes scored/sec (40x40, r-prim, per GPU)", "value": extra["difficulty_mazes_per_s_81x81"],
+                "unit": "mazes/s"})
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import numpy as np
@@ -300,33 +360,58 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    # one event per launch boundary (cheap: a few hundred events) -> the total AND the median per-launch time
+    n_ev = min(args.steps, 512)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev + 1)]
+    e1 = torch.cuda.Event(enable_timing=True)
+    evs[0].record()
     for t in range(args.steps):
         env.step(tape[t % TAPE])
+        if t + 1 <= n_ev:
+            evs[t + 1].record()
     e1.record()
     torch.cuda.synchronize()
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
+    ms = max_over_ranks(evs[0].elapsed_time(e1))
+    per_launch_us = sorted(evs[i].elapsed_time(evs[i + 1]) * 1e3 for i in range(n_ev))
+    median_launch_us = per_launch_us[len(per_launch_us) // 2]
     value = world * B * args.steps / (ms * 1e-3)
     ms_per_step = ms / args.steps
 
-    # end to end: host action buffers in, every output copied back to host, per step
+    # end to end through the public API with HOST buffers on both sides, per step: numpy actions -> pinned -> device,
+    # maze_step, results -> pinned host memory, one stream synchronisation.  Two wire formats for the results:
+    #   packed: one uint32 record per env (MAZE_STEP_PACKED | MAZE_STEP_NO_WIDE), decoded lazily on the host
+    #   wide:   the 26 bytes per env of round 1 (agent, best dir, reward, terminated, truncated as separate arrays)
     host_tape = tape[:4].cpu().numpy()
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    for t in range(2):
-        env.step_host(host_tape[t % 4])
-    barrier()
-    torch.cuda.synchronize()
-    env.reset_host_counters()      # d2h_bytes_per_step() = bytes actually copied in the timed region / steps
+
+    def time_e2e(fn):
+        for t in range(3):
+            fn(host_tape[t % 4])
+        barrier()
+        torch.cuda.synchronize()
+        env.reset_host_counters()      # d2h_bytes_per_step() = bytes actually copied in the timed region / steps
+        t0 = time.perf_counter()
+        for t in range(e2e_steps):
+            out = fn(host_tape[t % 4])
+        torch.cuda.synchronize()
+        secs = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        return world * B * e2e_steps / secs, env.d2h_bytes_per_step(), out
+
+    e2e_wide, d2h_wide, (obs, rew, term, trunc, _) = time_e2e(env.step_host)
+    e2e_packed, d2h_packed, records = time_e2e(env.step_host_packed)
+    # the records decode to exactly what the wide path returns: one more step taken with both outputs switched on,
+    # decoded record against the device's wide buffers
     t0 = time.perf_counter()
-    for t in range(e2e_steps):
-        obs, rew, term, trunc, _ = env.step_host(host_tape[t % 4])
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = world * B * e2e_steps / e2e_s
+    dec = mb.cabi.decode_records(records)
+    decode_s = time.perf_counter() - t0
+    env.step(torch.from_numpy(host_tape[0]).to(device), extra_mode=mb.cabi.STEP_PACKED)
+    chk = mb.cabi.decode_records(env.batch.packed.cpu().numpy())
+    assert (chk["agent"] == env.batch.agent.cpu().numpy()).all() and (chk["best_dir"] == env.batch.best_dir.cpu().numpy()).all()
+    assert (chk["reward"].view(np.uint64) == env.batch.reward.cpu().numpy().view(np.uint64)).all()
+    assert (chk["terminated"] == env.batch.terminated.cpu().numpy().astype(bool)).all() and (chk["truncated"] == env.batch.truncated.cpu().numpy().astype(bool)).all()
+    clocks = sampler.stop()    # sampled from the first warm-up launch to the end of the end-to-end runs (5 ms period)
 
     extra = None
     if rank == 0 and not args.no_extras:
@@ -335,7 +420,7 @@ def run_ours(args, rank, local_rank, world):
 
     # independent check that the timed kernel did the work: episode bookkeeping must be moving
     st = env.batch.state_host()
-    assert st["steps"].max() > 0 and int(rew.shape[0]) == B
+    assert st["steps"].max() > 0 and int(rew.shape[0]) == B and int(dec["reward"].shape[0]) == B
 
     line = None
     if rank == 0:
@@ -365,25 +450,222 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32 state+obs, f64 reward", "data": "synthetic",
-            "config": {"workload": workload_name(B), "envs_per_gpu": B, "mazes_per_gpu": NUM_MAZES,
-                       "l2": "inputs larger than L2: per-step working set (~100 B x envs = 400 MB) and the 13 KB/env visit arrays exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"env-index sharding over {world} GPU(s), no per-step collective"},
+            "config": workload_config(B, world),
+            "median_launch_us": median_launch_us,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "maze_step_kernel"},
+                         "traffic": traffic, "traffic_source": "ncu --set full capture of a steady-state launch of the same command (profiles/step_kernel_ncu_summary.json), not measured by this run",
+                         "peak_source": peak_src, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "maze_step_kernel",
+                         "pattern": pattern_summary(median_launch_us, B)},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step(),
-                    "d2h_bytes_per_step": env.d2h_bytes_per_step(), "steps": e2e_steps,
-                    "note": "every output of every env is copied to pinned host memory each step (agent, best dir, reward, "
-                            "terminated, truncated); the target array is copied again only on steps whose launch rewrote it "
-                            "(an env restarting after a win), which the kernel reports through maze_env_batch.target_dirty"},
+            "e2e": {"value": e2e_packed, "unit": UNIT, "wire": "packed", "h2d_bytes_per_step": env.h2d_bytes_per_step(),
+                    "d2h_bytes_per_step": d2h_packed, "steps": e2e_steps,
+                    "wide": {"value": e2e_wide, "d2h_bytes_per_step": d2h_wide},
+                    "host_decode_s_per_step": decode_s,
+                    "note": "MazeVectorEnv.step_host_packed: numpy actions -> pinned -> device, maze_step writing ONE uint32 record per env "
+                            "(row, col, best-next code, terminated, truncated, reward kind + index; include/maze_b200.h MAZE_REC_*), one copy to "
+                            "pinned host memory, one stream synchronisation; `target` (and, under a curriculum, the per-env shapes) travel only on "
+                            "steps whose launch changed a maze (maze_env_batch.target_dirty).  Records decode to the wide arrays bit for bit "
+                            "(cabi.decode_records, asserted in this run); decoding is left to the consumer and is not inside the timed region "
+                            "(host_decode_s_per_step: the library's single-threaded C loop over all envs).  `wide` is round 1's format: "
+                            "26 bytes per env in six arrays"},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
+            "secondary": secondary_metrics(extra),
             "extra": extra,
         }
     if world > 1:
         dist.destroy_process_group()
     return line
+
+
+# ------------------------------------------------------------------------------------------------
+# The other configs of BASELINE.json as one-line measurements (same contract: W warm-up steps, K timed steps between
+# barriers + synchronisations, CUDA events, max over ranks, rank 0 prints).
+def _dist_setup(local_rank, world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    return device, barrier, max_over_ranks
+
+
+def _timed_loop(torch, step_fn, args, barrier, max_over_ranks):
+    for _ in range(args.warmup):
+        step_fn()
+    torch.cuda.synchronize()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1))
+
+
+def _follow_best_dir(torch, best_dir, u, p_follow):
+    """Action that realises obs['best dir'] (= agent - next; +-(S - 1) components are wrapped moves) with probability
+    p_follow, a uniform random action otherwise."""
+    r, c = best_dir[:, 0], best_dir[:, 1]
+    wrapped = (r.abs() > 1) | (c.abs() > 1)
+    a = torch.where(r < 0, 0, torch.where(r > 0, 1, torch.where(c < 0, 2, 3)))
+    a = torch.where(wrapped, a ^ 1, a)
+    rnd = (u * 4096).long() % 4
+    return torch.where(u < p_follow, a, rnd).to(torch.uint8)
+
+
+def run_toroidal_regen(args, rank, local_rank, world):
+    """configs[2]: toroidal 40x40 (81x81 block; the reference's examples pass the same odd block shape to both topologies)
+    mazes, r-prim / dfs / prim&kill mixed per slot, one maze slot per env, every win regenerates the env's maze on the
+    device before its autoreset (maze_curriculum is off; maze_generate runs every step on the device-side queue)."""
+    import torch
+
+    import maze_b200 as mb
+    device, barrier, max_over_ranks = _dist_setup(local_rank, world)
+    B = args.envs_per_gpu if args.envs_per_gpu_set else 262144
+    env = mb.MazeVectorEnv(B, shape=SHAPE, topology="toroidal", algorithms=["r-prim", "dfs", "prim&kill"], device=device, seed=1234,
+                           slot_id_base=rank * B, on_win="regenerate", stats=True)
+    env.reset()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(7 + rank)
+
+    def step():
+        u = torch.rand(B, device=device, generator=gen)
+        env.step(_follow_best_dir(torch, env.batch.best_dir, u, 0.7))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    s0 = None
+    for _ in range(args.warmup):
+        step()
+    s0 = env.episode_statistics(reduce=world > 1)
+    args_w, args.warmup = args.warmup, 0
+    ms = _timed_loop(torch, step, args, barrier, max_over_ranks)
+    args.warmup = args_w
+    s1 = env.episode_statistics(reduce=world > 1)
+    clocks = sampler.stop()
+    if rank != 0:
+        return None
+    value = world * B * args.steps / (ms * 1e-3)
+    return {"metric": "env-steps/sec (toroidal 40x40 mazes, mixed generators, regeneration on win, whole job)", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int32 state+obs, f64 reward", "data": "synthetic",
+            "config": {"workload": f"configs[2]: toroidal 81x81-block mazes (41 logical lines), r-prim / dfs / prim&kill mixed, {B} envs and maze slots per GPU, "
+                                   "70 % best-dir following / 30 % uniform actions, every win regenerates the env's maze (maze_generate on the device queue)",
+                       "envs_per_gpu": B, "l2": "inputs larger than L2 (6.5 KB table + 13 KB visits per env)",
+                       "parallelism": f"env-index sharding over {world} GPU(s), no per-step collective"},
+            "mazes_regenerated_per_s": (s1["wins"] - s0["wins"]) / (ms * 1e-3), "episodes_per_s": (s1["episodes"] - s0["episodes"]) / (ms * 1e-3),
+            "gpu_launches": args.steps * world * 4, "clocks": clocks,
+            "launches_per_step": "policy (torch elementwise ops) + maze_generate (2 kernels, device-side queue length) + queue reset + maze_step"}
+
+
+def run_curriculum_dq(args, rank, local_rank, world):
+    """configs[3]: variable-size mazes 10x10 -> 64x64 cells (21 -> 129 blocks, + (4, 4) per win: simple_variable_maze_env.py:93-112),
+    generator switched by win count (off_policy_trainer.py:302-310), tabular double Q-learning on the device (dq_agent.py:5-73),
+    one learner per env (the reference's one table per agent)."""
+    import torch
+
+    import maze_b200 as mb
+    from maze_b200.agents import DQAgent
+    device, barrier, max_over_ranks = _dist_setup(local_rank, world)
+    B = args.envs_per_gpu if args.envs_per_gpu_set else 32768
+    env = mb.MazeVectorEnv(B, shape=(129, 129), start_shape=(21, 21), grow=4, algorithms="r-prim", device=device, seed=1234, slot_id_base=rank * B,
+                           on_win="regenerate", algorithm_schedule=((5, "prim&kill"), (10, "dfs")), stats=True)
+    agent = DQAgent(env, learning_rate=0.1, initial_epsilon=0.9, epsilon_decay=2000, final_epsilon=0.05, discount_factor=0.7, eta=1e-3,
+                    envs_per_agent=1, seed=1 + rank, capacity=1 << 26)
+    env.reset()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(11 + rank)
+
+    def step():   # behaviour policy: mostly the 'best dir' hint, otherwise the agent's own epsilon-greedy action (off-policy learning)
+        acts = agent.get_action()
+        u = torch.rand(B, device=device, generator=gen)
+        follow = _follow_best_dir(torch, env.batch.best_dir, torch.zeros_like(u), 1.0)
+        acts = torch.where(u < 0.85, follow, acts)
+        agent.core.last_action.copy_(acts)
+        env.step(acts)
+        agent.update()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = _timed_loop(torch, step, args, barrier, max_over_ranks)
+    clocks = sampler.stop()
+    agent.core.check_overflow()
+    stats = env.episode_statistics(reduce=world > 1)
+    shapes = env.pool.meta[:, 0].float()
+    if rank != 0:
+        return None
+    value = world * B * args.steps / (ms * 1e-3)
+    return {"metric": "env-steps/sec (variable-size 10x10 -> 64x64 curriculum, double Q-learning on device, whole job)", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int32 state+obs, f64 reward and Q values", "data": "synthetic",
+            "config": {"workload": f"configs[3]: {B} envs per GPU, mazes from 21x21 blocks growing by (4, 4) per win up to 129x129, r-prim -> prim&kill -> dfs "
+                                   "after 5 / 10 wins, device DQAgent (maze_q_act + maze_step + maze_q_update per step), 85 % best-dir behaviour policy",
+                       "envs_per_gpu": B, "l2": "inputs larger than L2 (33 KB visits per env at the pool shape)",
+                       "parallelism": f"env-index sharding over {world} GPU(s), replicas only (one Q table per env, as in the reference)"},
+            "wins": stats["wins"], "mean_block_shape_after_run": float(shapes.mean().item()), "max_block_shape_after_run": float(shapes.max().item()),
+            "gpu_launches": args.steps * world * 7, "clocks": clocks}
+
+
+def run_ddqn(args, rank, local_rank, world):
+    """configs[4]: the DDQN loop of examples/train_ddqn.py (8192 envs per GPU; net on the tensor cores; one NCCL all-reduce of the
+    8.7 MB gradient per optimiser step)."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from train_ddqn import DDQNLoop
+    device, barrier, max_over_ranks = _dist_setup(local_rank, world)
+    B = args.envs_per_gpu if args.envs_per_gpu_set else 8192
+    n = args.batch or B
+    loop = DDQNLoop(B, n, SHAPE[0], 1 << 20, rank, world, device)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, (n + B - 1) // B + 2)):
+        loop.iterate()
+    loop.ar_events, opt0 = [], loop.opt_steps
+    args_w, args.warmup = args.warmup, 0
+    ms = _timed_loop(torch, lambda: loop.iterate(time_allreduce=True), args, barrier, max_over_ranks)
+    args.warmup = args_w
+    clocks = sampler.stop()
+    ar_ms = sum(a.elapsed_time(b) for a, b in loop.ar_events)
+    if rank != 0:
+        return None
+    n_opt = loop.opt_steps - opt0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+    tflops = loop.flop_per_iteration() * args.steps / (ms * 1e-3) / 1e12
+    return {"metric": "env-steps/sec (DDQN training loop on 40x40 mazes, whole job)", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 operands, fp32 accumulate / master weights", "data": "synthetic",
+            "config": {"workload": f"configs[4]: DDQN loop, {B} -v1 envs per GPU on 81x81 r-prim mazes regenerated on win, replay batch {n} per GPU per "
+                                   "optimiser step, one optimiser step per env step, net of agents/ddqn_agent.py:18-52 (dropout off)",
+                       "envs_per_gpu": B, "batch_per_gpu": n, "parallelism": f"data parallel over {world} GPU(s): envs and replay sharded, one NCCL all-reduce "
+                                   "(sum) of the flat fp32 gradient (8.7 MB) per optimiser step"},
+            "samples_per_s": world * n * n_opt / (ms * 1e-3), "optimizer_steps_per_s": n_opt / (ms * 1e-3), "allreduce_share": ar_ms / ms,
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None, "peak_source": peak_src,
+                         "flop_per_step_per_gpu": loop.flop_per_iteration(),
+                         "note": "whole loop per GPU (policy forward on B envs + forward on 3 n and backward on n samples per optimiser step; env step, "
+                                 "replay, sampling, AdamW and the all-reduce included in the time)"},
+            "final_loss": float(loop.net.loss.item()), "gpu_launches": args.steps * world * 40, "clocks": clocks}
 
 
 class JsonOnlyStdout:
@@ -413,12 +695,19 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=500)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=4096 * NUM_MAZES)
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "toroidal-regen", "curriculum-dq", "ddqn"])
+    ap.add_argument("--batch", type=int, default=0, help="ddqn: replay batch per GPU per optimiser step (default: envs per GPU)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
+    args.envs_per_gpu_set = args.envs_per_gpu is not None
+    if args.envs_per_gpu is None:
+        args.envs_per_gpu = 4096 * NUM_MAZES
+    if args.workload != "configs1" and args.steps == 2000 and args.warmup == 500:   # the defaults are sized for 90 us steps
+        args.steps, args.warmup = 200, 20
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -427,8 +716,14 @@ def main():
     with JsonOnlyStdout() as out:
         if args.impl == "reference":
             line = run_reference(args, rank)
-        else:
+        elif args.workload == "configs1":
             line = run_ours(args, rank, local_rank, world)
+        else:
+            fn = {"toroidal-regen": run_toroidal_regen, "curriculum-dq": run_curriculum_dq, "ddqn": run_ddqn}[args.workload]
+            line = fn(args, rank, local_rank, world)
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
         if line is not None:
             out.emit(json.dumps(line))
 

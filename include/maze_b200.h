@@ -462,7 +462,9 @@ int maze_dqn_sample_packed(maze_ctx* ctx, const maze_replay* r, int n, uint64_t 
 /* The tensor-core GEMM underneath: C[M, N] = A[M, K] . B[N, K]^T with bf16 row-major operands (row pitches lda, ldb
  * in elements, multiples of 8; 16-byte aligned bases), N a multiple of 8.  epilogue 0: C bf16 = act(acc + bias)
  * (act 0 none, 1 LeakyReLU(0.01), 2 ReLU; bias may be NULL); 1: C bf16 = acc * act'(aux) with aux [M, ldaux] bf16 the
- * stored activation; 2: C fp32 += acc (atomic, `splits` CTAs along K).  tile_n 128 or 256. */
+ * stored activation; 2: C fp32 += acc (atomic, `splits` CTAs along K); 3: as 2 with TRANSPOSED operands, A [K, M] and
+ * B [K, N] row-major, i.e. C += A^T . B (the weight gradients, straight from [batch, features] activations; M a multiple
+ * of 8).  tile_n 128 or 256. */
 int maze_dqn_gemm_bf16(maze_ctx* ctx, const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc, int M, int N, int K,
                        int epilogue, int act, const float* bias, const uint16_t* aux, int ldaux, int tile_n, int splits, void* stream);
 

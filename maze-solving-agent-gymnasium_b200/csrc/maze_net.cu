@@ -48,7 +48,14 @@ struct GemmCfg {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;   // + slack for the 1024-byte alignment
 };
 
-template <int BN, int EPI>
+// MN == false: A [M, K] and B [N, K] row-major (K-major operands: one TMA box of BM (BN) rows x 64 K-elements per stage,
+//              8-row x 128-byte swizzle atoms 1024 bytes apart along M / N).
+// MN == true:  A [K, M] and B [K, N] row-major, i.e. C = A^T . B -- the weight gradients contract over the batch, and
+//              the activations are stored [batch, features].  MN-major operands: per stage BM / 64 (BN / 64) TMA boxes
+//              of 64 K-rows x 64 M (N)-elements; inside a box the 8-row swizzle atoms follow each other along K
+//              (stride-dimension offset 1024), the boxes along M / N (leading-dimension offset 8192); one UMMA of
+//              K = 16 starts 16 rows = 2048 bytes further.  No transposed copies of the activations are needed.
+template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
     using Cfg = GemmCfg<BN>;
@@ -93,24 +100,34 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc::mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 tc::mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
                 const uint32_t a_dst = base + (uint32_t)s * Cfg::STAGE_BYTES;
-                tc::tma_load_2d(a_dst, &tmA, full0 + 8 * s, (kb_begin + i) * BK, m0);
-                tc::tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full0 + 8 * s, (kb_begin + i) * BK, n0);
+                if constexpr (!MN) {
+                    tc::tma_load_2d(a_dst, &tmA, full0 + 8 * s, (kb_begin + i) * BK, m0);
+                    tc::tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full0 + 8 * s, (kb_begin + i) * BK, n0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BM / 64; ++j) tc::tma_load_2d(a_dst + j * 8192, &tmA, full0 + 8 * s, m0 + 64 * j, (kb_begin + i) * BK);
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tc::tma_load_2d(a_dst + Cfg::A_BYTES + j * 8192, &tmB, full0 + 8 * s, n0 + 64 * j, (kb_begin + i) * BK);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {   // MMA issuer
-            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN) | (MN ? (1u << 15) | (1u << 16) : 0u);   // bits 15 / 16: A / B are MN-major
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 tc::mbar_wait(full0 + 8 * s, ph);
                 tc::tc_fence_after();
                 const uint32_t a_addr = base + (uint32_t)s * Cfg::STAGE_BYTES;
-                const uint64_t da = tc::smem_desc(a_addr, 0, 1024, tc::SWIZZLE_128B);
-                const uint64_t db = tc::smem_desc(a_addr + Cfg::A_BYTES, 0, 1024, tc::SWIZZLE_128B);
+                const uint64_t da = tc::smem_desc(a_addr, MN ? 8192 : 0, 1024, tc::SWIZZLE_128B);
+                const uint64_t db = tc::smem_desc(a_addr + Cfg::A_BYTES, MN ? 8192 : 0, 1024, tc::SWIZZLE_128B);
+                // next UMMA (K = 16): K-major 32 bytes further inside the 128-byte swizzle row, MN-major 16 rows = 2048 bytes further
+                constexpr uint32_t kstep = MN ? (2048u >> 4) : (32u >> 4);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)   // 16 bf16 = 32 bytes further along K inside the 128-byte swizzle row
-                    tc::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (uint32_t)((i | k) != 0));
+                for (int k = 0; k < BK / 16; ++k)
+                    tc::umma_bf16(tmem_base, da + kstep * k, db + kstep * k, idesc, (uint32_t)((i | k) != 0));
                 tc::umma_commit(empty0 + 8 * s);   // frees the stage once these MMAs have read it
             }
             tc::umma_commit(accum_bar);
@@ -221,36 +238,44 @@ int make_map(maze_ctx* ctx, CUtensorMap* m, const void* ptr, int rows, int cols,
     return 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool MN>
 int launch_gemm_t(maze_ctx* ctx, const bf16* A, int lda, const bf16* B, int ldb, const GemmArgs& g, int splits, cudaStream_t st) {
     CUtensorMap ta, tb;
-    if (int rc = make_map(ctx, &ta, A, g.M, g.K, lda, BM)) return rc;
-    if (int rc = make_map(ctx, &tb, B, g.N, g.K, ldb, BN)) return rc;
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
-        MAZE_CHECK(cudaFuncSetAttribute(net_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::SMEM));
-        attr_set = true;
+    if constexpr (!MN) {
+        if (int rc = make_map(ctx, &ta, A, g.M, g.K, lda, BM)) return rc;
+        if (int rc = make_map(ctx, &tb, B, g.N, g.K, ldb, BN)) return rc;
+    } else {   // A [K, M], B [K, N]: boxes of 64 K-rows x 64 M / N elements
+        if (int rc = make_map(ctx, &ta, A, g.K, g.M, lda, 64)) return rc;
+        if (int rc = make_map(ctx, &tb, B, g.K, g.N, ldb, 64)) return rc;
     }
+    MAZE_CHECK(cudaFuncSetAttribute(net_gemm_kernel<BN, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::SMEM));
     const int nkb = (g.K + BK - 1) / BK;
     if (splits < 1) splits = 1;
     if (splits > nkb) splits = nkb;
     const dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
-    net_gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, st>>>(ta, tb, g);
+    net_gemm_kernel<BN, EPI, MN><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, st>>>(ta, tb, g);
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }
 
-int launch_gemm(maze_ctx* ctx, int epi, int bn, const bf16* A, int lda, const bf16* B, int ldb, const GemmArgs& g, int splits, cudaStream_t st) {
+int launch_gemm(maze_ctx* ctx, int epi, int bn, const bf16* A, int lda, const bf16* B, int ldb, const GemmArgs& g, int splits, cudaStream_t st,
+                bool mn_major = false) {
     if (g.M < 1 || g.N < 1 || g.K < 1 || (g.N % 8) != 0) return maze_fail_arg(ctx, MAZE_E_RANGE, "GEMM shape (N must be a multiple of 8)");
     if (epi != EPI_RED_F32 && splits > 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "split-K needs the accumulate epilogue");
-    if (bn == 256) {
-        if (epi == EPI_BIAS_ACT) return launch_gemm_t<256, EPI_BIAS_ACT>(ctx, A, lda, B, ldb, g, splits, st);
-        if (epi == EPI_MASK) return launch_gemm_t<256, EPI_MASK>(ctx, A, lda, B, ldb, g, splits, st);
-        return launch_gemm_t<256, EPI_RED_F32>(ctx, A, lda, B, ldb, g, splits, st);
+    if (mn_major) {
+        if (epi != EPI_RED_F32) return maze_fail_arg(ctx, MAZE_E_RANGE, "the MN-major (A^T . B) GEMM only has the accumulate epilogue");
+        if ((g.M % 8) != 0) return maze_fail_arg(ctx, MAZE_E_RANGE, "MN-major GEMM: M must be a multiple of 8");
+        if (bn == 256) return launch_gemm_t<256, EPI_RED_F32, true>(ctx, A, lda, B, ldb, g, splits, st);
+        return launch_gemm_t<128, EPI_RED_F32, true>(ctx, A, lda, B, ldb, g, splits, st);
     }
-    if (epi == EPI_BIAS_ACT) return launch_gemm_t<128, EPI_BIAS_ACT>(ctx, A, lda, B, ldb, g, splits, st);
-    if (epi == EPI_MASK) return launch_gemm_t<128, EPI_MASK>(ctx, A, lda, B, ldb, g, splits, st);
-    return launch_gemm_t<128, EPI_RED_F32>(ctx, A, lda, B, ldb, g, splits, st);
+    if (bn == 256) {
+        if (epi == EPI_BIAS_ACT) return launch_gemm_t<256, EPI_BIAS_ACT, false>(ctx, A, lda, B, ldb, g, splits, st);
+        if (epi == EPI_MASK) return launch_gemm_t<256, EPI_MASK, false>(ctx, A, lda, B, ldb, g, splits, st);
+        return launch_gemm_t<256, EPI_RED_F32, false>(ctx, A, lda, B, ldb, g, splits, st);
+    }
+    if (epi == EPI_BIAS_ACT) return launch_gemm_t<128, EPI_BIAS_ACT, false>(ctx, A, lda, B, ldb, g, splits, st);
+    if (epi == EPI_MASK) return launch_gemm_t<128, EPI_MASK, false>(ctx, A, lda, B, ldb, g, splits, st);
+    return launch_gemm_t<128, EPI_RED_F32, false>(ctx, A, lda, B, ldb, g, splits, st);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -470,6 +495,12 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const float inv_n = 1.f / (float)n;
+    float gacc[4][16];   // this lane's 16 columns of d fc3.weight, per action (the action is uniform over the warp)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gacc[a][i] = 0.f;
+    float gb_acc = 0.f, loss_acc = 0.f;   // lane a < 4 collects d fc3.bias[a]; lane 0 the loss
     for (int s = blockIdx.x * (HEAD_THREADS / 32) + (threadIdx.x >> 5); s < n; s += gridDim.x * (HEAD_THREADS / 32)) {
         float h[16], hn[16], ht[16];
         head_load16(h2_s + (size_t)s * NET_H2, lane, h);
@@ -509,18 +540,56 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
         dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
         dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(&sgw[act * NET_H2 + lane * 16 + i], gq * h[i]);
+        for (int a = 0; a < 4; ++a)
+            if (act == a) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) gacc[a][i] = fmaf(gq, h[i], gacc[a][i]);
+            }
+        if (lane == act) gb_acc += gq;
         if (lane == 0) {
-            atomicAdd(&sgb[act], gq);
-            atomicAdd(&sloss, d * d * inv_n);
+            loss_acc += d * d * inv_n;
             if (qsa_out) qsa_out[s] = qsa;
         }
     }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (gacc[a][i] != 0.f) atomicAdd(&sgw[a * NET_H2 + lane * 16 + i], gacc[a][i]);
+    if (lane < 4 && gb_acc != 0.f) atomicAdd(&sgb[lane], gb_acc);
+    if (lane == 0) atomicAdd(&sloss, loss_acc);
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS)
         if (sgw[i] != 0.f) atomicAdd(gw3 + i, sgw[i]);
     if (threadIdx.x < 4) atomicAdd(gb3 + threadIdx.x, sgb[threadIdx.x]);
     if (threadIdx.x == 0) atomicAdd(loss, sloss);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// out[c] += sum_r in[r, c]: the bias gradients (column sums of dL/d pre-activation).  One CTA per 64 columns x 512 rows.
+__global__ void __launch_bounds__(256)
+net_colsum_kernel(const bf16* __restrict__ in, int R, int C, int ld, float* __restrict__ out) {
+    __shared__ float part[8][64];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 512;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // a warp reads 64 consecutive columns (two per lane) of one row
+    float a0 = 0.f, a1 = 0.f;
+    const int c = c0 + 2 * tx;
+    if (c < C) {
+        for (int r = r0 + ty; r < min(R, r0 + 512); r += 8) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(in + (size_t)r * ld + c));
+            a0 += __uint_as_float(w << 16);
+            a1 += __uint_as_float(w & 0xffff0000u);
+        }
+    }
+    part[ty][2 * tx] = a0;
+    part[ty][2 * tx + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += part[k][threadIdx.x];
+        if (c0 + (int)threadIdx.x < C && v != 0.f) atomicAdd(out + c0 + threadIdx.x, v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -609,6 +678,152 @@ net_conv_bwd_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ poo
     accb += __shfl_xor_sync(0xffffffffu, accb, 2);
     accb += __shfl_xor_sync(0xffffffffu, accb, 4);
     if (sub == 0 && accb != 0.f) atomicAdd(gconv_b + o, accb);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The same gradient on the tensor cores.  Per sample
+//   D[o, kk] += sum_p A[o, p] * B[kk, p],   p = y * 16 + x over the 16 x 16 padded window positions (K = 256)
+//   A[o, p]  = dL/d(conv output o at p): the pooled gradient dX[o, q] * LeakyReLU', routed to its max-pool winner
+//   B[kk, p] = window bit of tap kk = c * 9 + dy * 3 + dx at p (the window shifted by (dy - 1, dx - 1));
+//              kk = 27 is all ones, so column 27 of D is the bias gradient; kk = 28 .. 31 stay zero
+// Both operands are K-major without swizzle (8 consecutive positions = one 16-byte core-matrix row, the core
+// matrices of one 8-position group 128 bytes apart along M / N, the groups 64 (32) x 16 bytes apart along K);
+// UMMA M = 64 (rows 32 .. 63 of A stay zero), N = 32, 14 MMAs of K = 16 per sample (one per window row).  One
+// operand buffer per CTA (48 KB) and four CTAs per SM: while one CTA waits for its MMAs the others build.  The
+// accumulator stays in TMEM over all the samples of a CTA and is added to the global gradient once (M = 64: row r
+// lives in TMEM lane 32 (r / 16) + r % 16).
+constexpr int CB_THREADS = 256;
+constexpr uint32_t CB_A_BYTES = 64 * 256 * 2, CB_B_BYTES = 32 * 256 * 2;
+constexpr size_t CB_SMEM = CB_A_BYTES + CB_B_BYTES + 128;   // 48 KB: four CTAs per SM overlap each other's build / MMA phases
+constexpr int CB_B_UNITS = 27 * 28;                          // (tap, window row 0..13, half row)
+
+__global__ void __launch_bounds__(CB_THREADS, 4)
+net_conv_bwd_tc_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ pool_idx, const uint32_t* __restrict__ win, int n,
+                       float* __restrict__ gconv_w, float* __restrict__ gconv_b) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* const A = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);
+    uint8_t* const B = A + CB_A_BYTES;
+    for (uint32_t i = tid * 16; i < CB_A_BYTES + CB_B_BYTES; i += CB_THREADS * 16) *reinterpret_cast<uint4*>(A + i) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        tc::mbar_init(tc::smem_u32(&bar), 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(tc::smem_u32(&tmem_slot), 32);
+        tc::tmem_relinquish();
+    }
+    __syncthreads();
+    if (tid < 32)   // the all-ones row kk = 27 of B: 32 position groups
+        *reinterpret_cast<uint4*>(B + tid * 512 + (27 >> 3) * 128 + (27 & 7) * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t bar_a = tc::smem_u32(&bar);
+    // A units of this thread: channel o, pooled row py, half h (14 units per channel over 8 thread groups)
+    const int o = tid & 31, part = tid >> 5;
+    const uint32_t a_row = (uint32_t)((o >> 3) * 128 + (o & 7) * 16);
+    // B units of this thread (fixed over the samples): tap kk, window row y, half h
+    int b_word[3], b_shift[3], b_sh8[3];
+    uint32_t b_off[3];
+    bool b_on[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int u = tid + CB_THREADS * j;
+        const int kk = u % 27, yh = u / 27;
+        const int y = yh >> 1, h = yh & 1, c = kk / 9, dy = (kk % 9) / 3, dx = kk % 3, iy = y + dy - 1;
+        b_on[j] = u < CB_B_UNITS && iy >= 0 && iy < MAZE_WINDOW;
+        b_word[j] = c * 8 + (max(iy, 0) >> 1);
+        b_shift[j] = (iy & 1) * 16;
+        b_sh8[j] = 8 * h + dx;
+        b_off[j] = u < CB_B_UNITS ? (uint32_t)yh * 512u + (uint32_t)((kk >> 3) * 128 + (kk & 7) * 16) : 0xffffffffu;
+    }
+    uint32_t it = 0;
+    for (int s = blockIdx.x; s < n; s += gridDim.x, ++it) {
+        // global loads first (they do not touch the operand buffers the previous sample's MMAs may still be reading)
+        uint32_t bits8[3];
+        const uint32_t* words = win + (size_t)s * MAZE_WINDOW_WORDS;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            bits8[j] = 0;
+            if (b_on[j]) bits8[j] = (((((__ldg(words + b_word[j]) >> b_shift[j]) & 0x7fffu) << 1) >> b_sh8[j])) & 0xffu;
+        }
+        uint32_t top[2][4], bot[2][4];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int u = part + 8 * k;
+            const int py = u >> 1, h = u & 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t word = 0, b = 0;
+                if (u < 14 && 4 * h + j < 7) {
+                    const size_t at = (size_t)o * 49 + py * 7 + 4 * h + j;
+                    b = pool_idx[(size_t)s * NET_CONV_OUT + at];
+                    float gv = __bfloat162float(dX[(size_t)s * NET_IN + at]);
+                    if (!(b & 4u)) gv *= LRELU_SLOPE;
+                    const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(gv));
+                    word = (b & 1u) ? hb << 16 : hb;       // columns 2 px and 2 px + 1 share a word
+                }
+                top[k][j] = (b & 2u) ? 0u : word;
+                bot[k][j] = (b & 2u) ? word : 0u;
+            }
+        }
+        if (it >= 1) tc::mbar_wait(bar_a, (it - 1u) & 1u);   // the previous sample's MMAs have read A and B
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int u = part + 8 * k;
+            if (u < 14) {
+                const int py = u >> 1, h = u & 1;
+                *reinterpret_cast<uint4*>(A + (uint32_t)(4 * py + h) * 1024u + a_row) = make_uint4(top[k][0], top[k][1], top[k][2], top[k][3]);
+                *reinterpret_cast<uint4*>(A + (uint32_t)(4 * py + 2 + h) * 1024u + a_row) = make_uint4(bot[k][0], bot[k][1], bot[k][2], bot[k][3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (b_off[j] != 0xffffffffu) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t b2 = (bits8[j] >> (2 * q)) & 3u;
+                    w[q] = (b2 & 1u) * 0x3F80u + (b2 >> 1) * 0x3F800000u;
+                }
+                *reinterpret_cast<uint4*>(B + b_off[j]) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            constexpr uint32_t idesc = tc::idesc_bf16(64, 32);
+            const uint32_t a_addr = tc::smem_u32(A), b_addr = tc::smem_u32(B);
+#pragma unroll
+            for (int j = 0; j < 14; ++j)   // positions 16 j .. 16 j + 15 = window row j (rows 14, 15 contribute nothing)
+                tc::umma_bf16(tmem_base, tc::smem_desc(a_addr + j * 2048u, 1024, 128, tc::SWIZZLE_NONE),
+                              tc::smem_desc(b_addr + j * 1024u, 512, 128, tc::SWIZZLE_NONE), idesc, (uint32_t)((it | (uint32_t)j) != 0));
+            tc::umma_commit(bar_a);
+        }
+    }
+    if (it > 0) {
+        tc::mbar_wait(bar_a, (it - 1u) & 1u);
+        tc::tc_fence_after();
+        if (warp < 2) {
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+            tc::tmem_ld_wait();
+            if (lane < 16) {
+                const int ch = warp * 16 + lane;
+#pragma unroll
+                for (int kk = 0; kk < 27; ++kk) atomicAdd(gconv_w + ch * 27 + kk, __uint_as_float(v[kk]));
+                atomicAdd(gconv_b + ch, __uint_as_float(v[27]));
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 32);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -764,7 +979,7 @@ int mlp_forward(maze_ctx* ctx, const bf16* X, int rows, const bf16* w1b, const b
     return launch_gemm(ctx, EPI_BIAS_ACT, 256, h1, NET_H1, w2b, NET_H1, g, 1, st);
 }
 
-int transpose(maze_ctx* ctx, const bf16* in, int R, int C, int ld_in, bf16* out, int ld_out, float* colsum, cudaStream_t st) {
+[[maybe_unused]] int transpose(maze_ctx* ctx, const bf16* in, int R, int C, int ld_in, bf16* out, int ld_out, float* colsum, cudaStream_t st) {
     const dim3 grid((C + 63) / 64, (R + 63) / 64);
     net_transpose_kernel<<<grid, 256, 0, st>>>(in, R, C, ld_in, out, ld_out, colsum);
     MAZE_CHECK(cudaGetLastError());
@@ -783,12 +998,14 @@ extern "C" int maze_dqn_gemm_bf16(maze_ctx* ctx, const uint16_t* A, int lda, con
                                   int epilogue, int act, const float* bias, const uint16_t* aux, int ldaux, int tile_n, int splits, void* stream) {
     if (!ctx) return MAZE_E_NULL;
     if (!A || !B || !C) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_gemm_bf16 pointer");
-    if (epilogue < 0 || epilogue > 2 || act < 0 || act > 2 || (tile_n != 128 && tile_n != 256)) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_gemm_bf16 epilogue / act / tile_n");
+    if (epilogue < 0 || epilogue > 3 || act < 0 || act > 2 || (tile_n != 128 && tile_n != 256)) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_gemm_bf16 epilogue / act / tile_n");
+    const bool mn = epilogue == 3;   // C fp32 += A^T . B with A [K, M], B [K, N]
+    if (mn) epilogue = EPI_RED_F32;
     if (epilogue == EPI_MASK && !aux) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_gemm_bf16: aux");
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.bias = bias; g.aux = reinterpret_cast<const bf16*>(aux); g.ldaux = ldaux; g.act = act;
     return launch_gemm(ctx, epilogue, tile_n, reinterpret_cast<const bf16*>(A), lda, reinterpret_cast<const bf16*>(B), ldb, g, splits,
-                       static_cast<cudaStream_t>(stream));
+                       static_cast<cudaStream_t>(stream), mn);
 }
 
 extern "C" int maze_dqn_net_refresh(maze_ctx* ctx, const maze_dqn_net* net, int which, void* stream) {
@@ -868,34 +1085,41 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
                              w.h1t_tn, w.h2_tn, st))
         return rc;
     {
-        const int grid = (n + 7) / 8 < ctx->num_sms * 2 ? (n + 7) / 8 : ctx->num_sms * 2;
+        const int grid = (n + 7) / 8 < ctx->num_sms ? (n + 7) / 8 : ctx->num_sms;   // one CTA per SM: the fc3 gradient is merged with one atomic per CTA and entry
         net_head_loss_kernel<<<grid, HEAD_THREADS, 0, st>>>(w.h2, w.h2 + np * NET_H2, w.h2_tn, n, p + MAZE_NET_OFF_W3, p + MAZE_NET_OFF_B3,
                                                            net->target + MAZE_NET_OFF_W3, net->target + MAZE_NET_OFF_B3, action, reward, gamma,
                                                            w.dh2, gr + MAZE_NET_OFF_W3, gr + MAZE_NET_OFF_B3, net->loss, qsa_out);
         MAZE_CHECK(cudaGetLastError());
     }
-    // fc2: dW2 = dh2^T . h1, db2 = colsum(dh2), dh1 = (dh2 . W2) * LeakyReLU'(h1)
-    if (int rc = transpose(ctx, w.dh2, n, NET_H2, NET_H2, w.dh2T, w.np, gr + MAZE_NET_OFF_B2, st)) return rc;
-    if (int rc = transpose(ctx, w.h1, n, NET_H1, NET_H1, w.h1T, w.np, nullptr, st)) return rc;
+    // fc2: dW2 = dh2^T . h1 (MN-major operands: straight from the [n, features] activations), db2 = colsum(dh2),
+    //      dh1 = (dh2 . W2) * LeakyReLU'(h1)
     const int splits = n >= 4096 ? 4 : (n >= 1024 ? 2 : 1);
+    net_colsum_kernel<<<dim3(NET_H2 / 64, (n + 511) / 512), 256, 0, st>>>(w.dh2, n, NET_H2, NET_H2, gr + MAZE_NET_OFF_B2);
+    MAZE_CHECK(cudaGetLastError());
     GemmArgs g{};
     g.M = NET_H2; g.N = NET_H1; g.K = n; g.C = gr + MAZE_NET_OFF_W2; g.ldc = NET_H1;
-    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh2T, w.np, w.h1T, w.np, g, splits * 2, st)) return rc;
+    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh2, NET_H2, w.h1, NET_H1, g, splits * 2, st, true)) return rc;
     g = GemmArgs{};
     g.M = n; g.N = NET_H1; g.K = NET_H2; g.C = w.dh1; g.ldc = NET_H1; g.aux = w.h1; g.ldaux = NET_H1; g.act = ACT_LRELU;
     if (int rc = launch_gemm(ctx, EPI_MASK, 256, w.dh2, NET_H2, w2t, NET_H2, g, 1, st)) return rc;
     // fc1: dW1 = dh1^T . X, db1 = colsum(dh1), dX = dh1 . W1
-    if (int rc = transpose(ctx, w.dh1, n, NET_H1, NET_H1, w.dh1T, w.np, gr + MAZE_NET_OFF_B1, st)) return rc;
-    if (int rc = transpose(ctx, w.X, n, NET_IN, NET_IN, w.XT, w.np, nullptr, st)) return rc;
+    net_colsum_kernel<<<dim3(NET_H1 / 64, (n + 511) / 512), 256, 0, st>>>(w.dh1, n, NET_H1, NET_H1, gr + MAZE_NET_OFF_B1);
+    MAZE_CHECK(cudaGetLastError());
     g = GemmArgs{};
     g.M = NET_H1; g.N = NET_IN; g.K = n; g.C = gr + MAZE_NET_OFF_W1; g.ldc = NET_IN;
-    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh1T, w.np, w.XT, w.np, g, splits, st)) return rc;
+    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh1, NET_H1, w.X, NET_IN, g, splits, st, true)) return rc;
     g = GemmArgs{};
     g.M = n; g.N = NET_CONV_OUT; g.K = NET_H1; g.C = w.dX; g.ldc = NET_IN; g.act = ACT_NONE;
     if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, 256, w.dh1, NET_H1, w1t, NET_H1, g, 1, st)) return rc;
-    {
+    static const bool conv_bwd_cuda_cores = getenv("MAZE_NET_CONV_BWD_CUDA_CORES") != nullptr;   // A/B switch for the CUDA-core version
+    if (conv_bwd_cuda_cores) {
         const int grid = n < ctx->num_sms * 4 ? n : ctx->num_sms * 4;
         net_conv_bwd_kernel<<<grid, 256, 0, st>>>(w.dX, w.idx, win, n, gr + MAZE_NET_OFF_CONV_W, gr + MAZE_NET_OFF_CONV_B);
+        MAZE_CHECK(cudaGetLastError());
+    } else {
+        MAZE_CHECK(cudaFuncSetAttribute(net_conv_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
+        const int grid = n < ctx->num_sms * 4 ? n : ctx->num_sms * 4;
+        net_conv_bwd_tc_kernel<<<grid, CB_THREADS, CB_SMEM, st>>>(w.dX, w.idx, win, n, gr + MAZE_NET_OFF_CONV_W, gr + MAZE_NET_OFF_CONV_B);
         MAZE_CHECK(cudaGetLastError());
     }
     return 0;

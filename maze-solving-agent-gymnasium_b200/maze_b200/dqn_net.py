@@ -155,10 +155,14 @@ class DQNNet:
 
 def gemm_bf16(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, epilogue: int = 0, act: int = 0, bias=None, aux=None,
               tile_n: int = 256, splits: int = 1):
-    """C = A . B^T through maze_dqn_gemm_bf16 (test / benchmark hook)."""
+    """C = A . B^T through maze_dqn_gemm_bf16 (test / benchmark hook); epilogue 3: C += A^T . B with A [K, M], B [K, N]."""
     ctx = cabi.Context.for_device(A.device)
-    M, K = A.shape
-    N = B.shape[0]
+    if epilogue == 3:
+        K, M = A.shape
+        N = B.shape[1]
+    else:
+        M, K = A.shape
+        N = B.shape[0]
     rc = cabi.lib().maze_dqn_gemm_bf16(ctx.handle, cabi.ptr(A), A.stride(0), cabi.ptr(B), B.stride(0), cabi.ptr(C_out), C_out.stride(0), M, N, K,
                                        int(epilogue), int(act), cabi.ptr(bias), cabi.ptr(aux), aux.stride(0) if aux is not None else 0,
                                        int(tile_n), int(splits), cabi.current_stream(A.device))

@@ -145,6 +145,9 @@ class MazeVectorEnv(_VectorBase):
         self._h_out = None
         self._h_flag = None
         self._h_packed = None
+        self._h_shape_valid = False
+        shapes = self.pool.meta[:, :2]   # one shape and topology for every slot -> the per-env mirrors never go stale
+        self._pool_is_uniform = bool((shapes == shapes[0]).all().item()) and not self.grow
         self._h_bytes, self._h_calls = 0, 0
 
     # ------------------------------------------------------------------------------------------
@@ -199,12 +202,17 @@ class MazeVectorEnv(_VectorBase):
                            slot_id_base=self.slot_id_base, candidates=self.candidates)
         b.queue_count.zero_()
 
-    def step(self, actions, extra_mode: int = 0):
+    def step(self, actions, extra_mode: int = 0, observe: bool = True):
+        """observe=False skips building the observation dict (with enrich=True: the 2.7 KB-per-env float window) and
+        returns None in its place -- for consumers that read the state another way, like the tensor-core DQN net, which
+        takes the replay ring's bit-packed windows."""
         b = self.batch
         if self.on_win == "regenerate":
             self.drain_regeneration()
         b.step(self._device_actions(actions), self._mode | extra_mode)
         term, trunc = b.terminated.view(torch.bool), b.truncated.view(torch.bool)
+        if not observe:
+            return (None, b.reward, trunc, term, None) if self.reference_order else (None, b.reward, term, trunc, None)
         if self.reference_order:
             return self._obs(), b.reward, trunc, term, _LazyInfo(self)
         return self._obs(), b.reward, term, trunc, _LazyInfo(self)
@@ -264,14 +272,17 @@ class MazeVectorEnv(_VectorBase):
         stream = torch.cuda.current_stream(self.device)
         stream.synchronize()
         nbytes = 4 * self.num_envs + 4
-        if int(self._h_flag[0]) != 0:   # a maze changed under some env: refresh target / shape / topology mirrors
+        if int(self._h_flag[0]) != 0:   # a maze changed under some env: refresh the target (and shape / topology) mirrors
             b.target_dirty.zero_()
-            meta = self.pool.meta[b.env_maze.long()]
             self._h_target.copy_(b.target, non_blocking=True)
-            self._h_shape.copy_(meta[:, :2].contiguous(), non_blocking=True)
-            self._h_tor.copy_((meta[:, cabi.META_FLAGS] & cabi.FLAG_TOROIDAL).to(torch.uint8), non_blocking=True)
+            nbytes += self.num_envs * 8
+            if self._h_shape_valid is False or self.grow:   # shapes only change under the growing curriculum
+                meta = self.pool.meta[b.env_maze.long()]
+                self._h_shape.copy_(meta[:, :2].contiguous(), non_blocking=True)
+                self._h_tor.copy_((meta[:, cabi.META_FLAGS] & cabi.FLAG_TOROIDAL).to(torch.uint8), non_blocking=True)
+                nbytes += self.num_envs * (8 + 1)
+                self._h_shape_valid = self._pool_is_uniform
             stream.synchronize()
-            nbytes += self.num_envs * (8 + 8 + 1)
         self._h_bytes += nbytes
         self._h_calls += 1
         rec = self._h_packed.numpy().view(np.uint32)

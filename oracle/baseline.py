@@ -56,10 +56,15 @@ def time_env_steps(mazes, seconds=10.0, workers=None, kind="port"):
 
 
 def _persistent_worker(conn, kind, grid, start, goal, toroidal, seed):
-    from .env_port import ClosedFormEnv, PortEnv
-    env = (PortEnv if kind == "port" else ClosedFormEnv)(grid, start, goal, toroidal)
+    if kind == "reference":   # the unmodified reference env from baseline/_ref: generates its own 81 x 81 maze (best of six)
+        from .ref_runtime import make_reference_env
+        env = make_reference_env(np.asarray(grid).shape, "r-prim", seed)
+    else:
+        from .env_port import ClosedFormEnv, PortEnv
+        env = (PortEnv if kind == "port" else ClosedFormEnv)(grid, start, goal, toroidal)
     rng = np.random.default_rng(seed)
     env.reset()
+    conn.send("ready")
     while True:
         cmd = conn.recv()
         if cmd is None:
@@ -101,6 +106,8 @@ class PersistentVector:
             p.start()
             self.conns.append(parent)
             self.procs.append(p)
+        for c in self.conns:   # constructors done (the reference's takes ~12 s at 81 x 81: six mazes generated and scored)
+            assert c.recv() == "ready"
 
     def step(self, n):
         """Lock step (the AsyncVectorEnv shape): every env advances by exactly n transitions."""

@@ -49,3 +49,36 @@ def test_metric_table_of_1000_mazes_matches_reference(algo):
         assert abs(a.mean() - published) <= tol, (algo, name, a.mean(), published, tol)
     # spread of the difficulty too (two-sample check on the standard deviation, generous)
     assert 0.7 < ours[:, 0].std() / ref[:, 0].std() < 1.4
+
+
+# ---- round 2: the survey's tolerance, against 1000 reference mazes per generator ----------------------------
+@pytest.mark.parametrize("algo", ["r-prim", "prim&kill", "dfs"])
+def test_metric_distributions_match_1000_reference_mazes(algo):
+    """|mean_ours - mean_ref| <= 3 sigma / sqrt(1000) per column, against
+    tests/golden/metric_table_1000.npz -- gen_maze((81, 81)) + ComplexityEvaluation + MetricsCalculator of the unmodified
+    reference on 1000 mazes per generator (make_golden.py metric_table_1000; 34 minutes on 6 cores).  The device side
+    draws 10 000 mazes (a few milliseconds), so its own sampling error is negligible next to the reference's and the bound
+    is 3 standard errors of the difference of means, 3 * sqrt(var_ref / 1000 + var_ours / 10000) ~ 3.15 sigma / sqrt(1000).
+    Shape, not just location: a two-sample Kolmogorov-Smirnov test per column (p > 1e-3), and the reference's Max D
+    (generation_algos_metrics_evaluations.py:43, the column round 1 left out) must be an unremarkable maximum of 1000 of
+    our mazes (inside the central 99 % of the maxima of 400 random 1000-subsets)."""
+    from scipy import stats
+    import maze_b200 as mb
+    n = 10000
+    pool = mb.MazePool(n, (81, 81))
+    pool.generate(algorithms=algo, seed=20261019)
+    ours = pool.difficulty().cpu().numpy()[:, :5]
+    assert np.isfinite(ours).all()
+    ref = np.load(f"{GOLDEN}/metric_table_1000.npz")[algo]
+    assert ref.shape == (1000, 5)
+    for c, name in enumerate(COLUMNS):
+        a, b = ours[:, c], ref[:, c]
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 3.0 * se, (algo, name, a.mean(), b.mean(), se)
+        ks = stats.ks_2samp(a, b)
+        assert ks.pvalue > 1e-3, (algo, name, ks)
+        assert 0.85 < a.std(ddof=1) / b.std(ddof=1) < 1.15, (algo, name, a.std(), b.std())
+    rng = np.random.default_rng(0)
+    maxima = np.array([ours[rng.choice(n, 1000, replace=False), 0].max() for _ in range(400)])
+    lo, hi = np.quantile(maxima, [0.005, 0.995])
+    assert lo <= ref[:, 0].max() <= hi, (algo, "Max D", ref[:, 0].max(), lo, hi)

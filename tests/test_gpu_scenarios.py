@@ -237,7 +237,7 @@ def test_terminal_observation_and_replay_see_the_maze_the_episode_was_played_on(
                 o, r, otr, ote, _ = cur[e].step(int(acts[e]))
                 assert bool(ote) == bool(te[e]), (t, e)
                 pending[e] = bool(ote or otr)
-                wins += int(ote)
+                wins += int(ote and not otr)       # a goal reached on the truncating step pays -1, not 1 (base_maze_env.py:205-208)
             np.testing.assert_array_equal(win[e], o["window"], err_msg=f"window env {e} step {t} (terminal: {bool(te[e])})")
             np.testing.assert_array_equal(an[e].view(np.uint64), np.asarray(o["agent"], np.float64).view(np.uint64))
             np.testing.assert_array_equal(tn[e].view(np.uint64), np.asarray(o["target"], np.float64).view(np.uint64))

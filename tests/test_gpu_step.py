@@ -24,9 +24,10 @@ def _collect_golden_mazes():
     z, meta = load_golden("metrics")
     for m in meta:
         out.append(dict(grid=z[f"m{m['id']}_grid"], start=m["start"], goal=m["goal"], toroidal=bool(m["no_border"])))
-    z, meta = load_golden("bestdir")
-    for m in meta:
-        out.append(dict(grid=z[f"m{m['id']}_grid"], start=m["start"], goal=m["goal"], toroidal=m["topology"] == "torus"))
+    for name in ("bestdir", "bestdir81"):
+        z, meta = load_golden(name)
+        for m in meta:
+            out.append(dict(grid=z[f"m{m['id']}_grid"], start=m["start"], goal=m["goal"], toroidal=m["topology"] == "torus"))
     return out
 
 
@@ -44,20 +45,44 @@ def test_fields_match_oracle_tables():
         assert meta[i, mb.cabi.META_SOL_LEN] == int(t.dgoal[tuple(m["start"])]) + 1
 
 
-def test_fields_max_steps_match_reference(golden_bestdir):
+@pytest.mark.parametrize("name", ["bestdir", "bestdir81"])
+def test_fields_best_dir_matches_reference(name):
+    """The step table's best-next code against the reference's _find_best_next_cell on every open block
+    (bestdir81.npz: 81 x 81 mazes, dfs included, i.e. the beyond-the-depth-limit branch at the headline size)."""
     mb = _engine()
-    z, meta = golden_bestdir
+    z, meta = load_golden(name)
+    pool = mb.MazePool.from_grids([z[f"m{m['id']}_grid"] for m in meta], [m["start"] for m in meta],
+                                  [m["goal"] for m in meta], [m["topology"] == "torus" for m in meta])
+    dr = np.array([1, -1, 0, 0, 0, 0, 0, 0]), np.array([0, 0, 1, -1, 0, 0, 0, 0])
+    for i, m in enumerate(meta):
+        grid, nxt = z[f"m{m['id']}_grid"], z[f"m{m['id']}_next"]
+        S = m["shape"]
+        code = (pool.table_host(i).reshape(-1)[:S * S].reshape(S, S) >> mb.cabi.TAB_CODE_SHIFT) & 7
+        rr, cc = np.nonzero(grid)
+        k = code[rr, cc]
+        nr, nc = rr + dr[0][k], cc + dr[1][k]
+        if m["topology"] == "torus":
+            nr, nc = nr % S, nc % S
+        np.testing.assert_array_equal(np.stack([nr, nc], 1), nxt[rr, cc], err_msg=str(m))
+
+
+@pytest.mark.parametrize("name", ["bestdir", "bestdir81"])
+def test_fields_max_steps_match_reference(name):
+    mb = _engine()
+    z, meta = load_golden(name)
     pool = mb.MazePool.from_grids([z[f"m{m['id']}_grid"] for m in meta], [m["start"] for m in meta],
                                   [m["goal"] for m in meta], [m["topology"] == "torus" for m in meta])
     got = pool.meta_host()[:, mb.cabi.META_MAX_STEPS]
     np.testing.assert_array_equal(got, [m["max_steps"] for m in meta])
 
 
-def test_step_matches_reference_traces(golden_steps):
+@pytest.mark.parametrize("name", ["steps", "steps81"])
+def test_step_matches_reference_traces(name):
     """Replay the reference's action tapes (no autoreset, stepping continues past done exactly as
-    the reference env allows) and compare every output of every step."""
+    the reference env allows) and compare every output of every step.  steps81.npz (round 2): 81 x 81 traces for
+    prim&kill, dfs (euclid) and r-prim, prim&kill (torus)."""
     mb = _engine()
-    z, meta = golden_steps
+    z, meta = load_golden(name)
     meta = [m for m in meta if not m["enrich"]]
     pool = mb.MazePool.from_grids([z[f"m{m['id']}_grid"] for m in meta], [m["start"] for m in meta],
                                   [m["goal"] for m in meta], [m["topology"] == "torus" for m in meta])

@@ -38,24 +38,45 @@ def _replay(env_cls, z, m, one_tape_above=10**9):
             check(t + 1, obs, info)
 
 
-def _metas():
+_Z = {}
+
+
+def _golden(name):
     from conftest import load_golden
-    return load_golden("steps")[1]
+    if name not in _Z:
+        _Z[name] = load_golden(name)
+    return _Z[name]
 
 
-@pytest.mark.parametrize("m", _metas(), ids=lambda m: f"{m['topology']}-{m['algo']}-{m['shape']}{'-v1' if m['enrich'] else ''}")
-def test_closed_form_env_matches_reference(golden_steps, m):
-    _replay(ClosedFormEnv, golden_steps[0], m)
+def _metas():
+    # steps.npz: round 1; steps81.npz: round 2, the headline size for the generator x topology pairs round 1 lacked
+    return [dict(m, file=f) for f in ("steps", "steps81") for m in _golden(f)[1]]
 
 
-@pytest.mark.parametrize("m", _metas(), ids=lambda m: f"{m['topology']}-{m['algo']}-{m['shape']}{'-v1' if m['enrich'] else ''}")
-def test_port_env_matches_reference(golden_steps, m):
+def _id(m):
+    return f"{m['file']}-{m['topology']}-{m['algo']}-{m['shape']}{'-v1' if m['enrich'] else ''}"
+
+
+@pytest.mark.parametrize("m", _metas(), ids=_id)
+def test_closed_form_env_matches_reference(m):
+    _replay(ClosedFormEnv, _golden(m["file"])[0], m)
+
+
+@pytest.mark.parametrize("m", _metas(), ids=_id)
+def test_port_env_matches_reference(m):
     # every shape, 81 x 81 included: this port is what bench.py times as the reference arm / cpu_baseline
-    _replay(PortEnv, golden_steps[0], m, one_tape_above=21)
+    _replay(PortEnv, _golden(m["file"])[0], m, one_tape_above=21)
 
 
-def test_best_dir_table_matches_reference(golden_bestdir):
-    z, meta = golden_bestdir
+@pytest.mark.parametrize("name", ["bestdir", "bestdir81"])
+def test_best_dir_table_matches_reference(name):
+    """bestdir81.npz (round 2): every open block of 81 x 81 mazes, dfs included -- most of a dfs maze lies farther from
+    the goal than the A* depth limit L = 162, the `D > L` branch of the closed form."""
+    z, meta = _golden(name)
+    if name == "bestdir81":
+        from oracle.grid import bfs_dist as _bfs
+        far = [int((_bfs(z[f"m{m['id']}_grid"], m["goal"], m["topology"] == "torus")[z[f"m{m['id']}_grid"] != 0] > 2 * m["shape"]).sum()) for m in meta]
+        assert max(far) > 1000, far   # the far branch really is exercised
     for m in meta:
         i = m["id"]
         grid, nxt = z[f"m{i}_grid"], z[f"m{i}_next"]
