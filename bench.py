@@ -382,7 +382,13 @@ def run_ours(args, rank, local_rank, world):
     # maze_step, results -> pinned host memory, one stream synchronisation.  Two wire formats for the results:
     #   packed: one uint32 record per env (MAZE_STEP_PACKED | MAZE_STEP_NO_WIDE), decoded lazily on the host
     #   wide:   the 26 bytes per env of round 1 (agent, best dir, reward, terminated, truncated as separate arrays)
-    host_tape = tape[:4].cpu().numpy()
+    # the actions of a step live in pinned host memory (env.pinned_actions(): the buffer a policy on the host writes into)
+    host_tape = []
+    for i in range(4):
+        buf = env.pinned_actions()
+        buf.copy_(tape[i])
+        host_tape.append(buf)
+    torch.cuda.synchronize()
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
 
     def time_e2e(fn):
@@ -406,7 +412,7 @@ def run_ours(args, rank, local_rank, world):
     t0 = time.perf_counter()
     dec = mb.cabi.decode_records(records)
     decode_s = time.perf_counter() - t0
-    env.step(torch.from_numpy(host_tape[0]).to(device), extra_mode=mb.cabi.STEP_PACKED)
+    env.step(host_tape[0].to(device), extra_mode=mb.cabi.STEP_PACKED)
     chk = mb.cabi.decode_records(env.batch.packed.cpu().numpy())
     assert (chk["agent"] == env.batch.agent.cpu().numpy()).all() and (chk["best_dir"] == env.batch.best_dir.cpu().numpy()).all()
     assert (chk["reward"].view(np.uint64) == env.batch.reward.cpu().numpy().view(np.uint64)).all()
@@ -461,7 +467,7 @@ def run_ours(args, rank, local_rank, world):
                     "d2h_bytes_per_step": d2h_packed, "steps": e2e_steps,
                     "wide": {"value": e2e_wide, "d2h_bytes_per_step": d2h_wide},
                     "host_decode_s_per_step": decode_s,
-                    "note": "MazeVectorEnv.step_host_packed: numpy actions -> pinned -> device, maze_step writing ONE uint32 record per env "
+                    "note": "MazeVectorEnv.step_host_packed: actions in pinned host memory -> device, maze_step writing ONE uint32 record per env "
                             "(row, col, best-next code, terminated, truncated, reward kind + index; include/maze_b200.h MAZE_REC_*), one copy to "
                             "pinned host memory, one stream synchronisation; `target` (and, under a curriculum, the per-env shapes) travel only on "
                             "steps whose launch changed a maze (maze_env_batch.target_dirty).  Records decode to the wide arrays bit for bit "

@@ -353,6 +353,10 @@ typedef struct maze_replay {
     /* per-env staging: the observation the env's next transition starts from */
     float*    stage_vec;    /* [B, 6]                                                             */
     uint32_t* stage_win;    /* [B, MAZE_WINDOW_WORDS]                                             */
+    int32_t   without_replacement; /* 1: a batch holds n DISTINCT transitions (random.sample, lib/replay_memory.py:20-21;
+                               falls back to independent draws while fewer than n are stored); 0: independent
+                               uniform draws                                                        */
+    int32_t   reserved;
 } maze_replay;
 
 /* Encode the current observation of every env into the staging area (after maze_reset). */
@@ -364,8 +368,10 @@ int maze_dqn_observe(maze_ctx* ctx, const maze_env_batch* b, const maze_replay* 
  * observation.  Envs whose step was an autoreset only re-stage. */
 int maze_dqn_push(maze_ctx* ctx, const maze_env_batch* b, const maze_replay* r, const uint8_t* actions, void* stream);
 
-/* memory.sample(n): n transitions drawn uniformly (with replacement; Philox keyed by seed / draw)
- * from the filled part of the ring, unpacked into dense tensors: vec / next_vec [n, 6] float32,
+/* memory.sample(n): n transitions drawn uniformly from the filled part of the ring (distinct ones when
+ * replay.without_replacement is set -- random.sample, lib/replay_memory.py:20-21 -- by taking the first n images of a
+ * keyed pseudo-random permutation of the filled slots; Philox keyed by seed / draw either way), unpacked into dense
+ * tensors: vec / next_vec [n, 6] float32,
  * win / next_win [n, 3, 15, 15] float32, action [n] int64, reward [n] float32. */
 int maze_dqn_sample(maze_ctx* ctx, const maze_replay* r, int n, uint64_t seed, uint64_t draw, float* vec, float* win,
                     float* next_vec, float* next_win, int64_t* action, float* reward, void* stream);

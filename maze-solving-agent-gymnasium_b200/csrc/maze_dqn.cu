@@ -7,6 +7,7 @@
 // (one ballot per two window rows and channel), so a transition costs 2 x (24 + 96) + 5 = 245 B of HBM
 // instead of 5.5 KB, and a 1 M-transition ring fits in 245 MB.
 #include "maze_env.cuh"
+#include "maze_replay.cuh"
 
 namespace {
 
@@ -141,11 +142,7 @@ maze_dqn_sample_kernel(maze_replay r, int n, unsigned long long seed, unsigned l
     const unsigned long long pushed = *r.pushed;
     const unsigned long long filled = pushed < (unsigned long long)r.capacity ? pushed : (unsigned long long)r.capacity;
     if (filled == 0) return;
-    Philox rng;
-    rng.init(seed, draw, (uint32_t)k);
-    rng.refill();
-    const unsigned long long u = ((unsigned long long)rng.o0 << 32) | rng.o1;
-    const size_t slot = (size_t)__umul64hi(u, filled);   // uniform in [0, filled)
+    const size_t slot = replay_slot(r, filled, n, seed, draw, k);
     if (lane < 6) {
         vec[(size_t)k * 6 + lane] = r.vec[slot * 6 + lane];
         next_vec[(size_t)k * 6 + lane] = r.next_vec[slot * 6 + lane];

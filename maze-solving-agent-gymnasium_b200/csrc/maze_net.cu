@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "maze_common.cuh"
+#include "maze_replay.cuh"
 #include "maze_tc.cuh"
 
 namespace {
@@ -888,11 +889,7 @@ net_sample_packed_kernel(maze_replay r, int n, unsigned long long seed, unsigned
     const unsigned long long pushed = *r.pushed;
     const unsigned long long filled = pushed < (unsigned long long)r.capacity ? pushed : (unsigned long long)r.capacity;
     if (filled == 0) return;
-    Philox rng;   // the same draw as maze_dqn_sample: slot k of draw `draw` is the same transition in both
-    rng.init(seed, draw, (uint32_t)k);
-    rng.refill();
-    const unsigned long long u = ((unsigned long long)rng.o0 << 32) | rng.o1;
-    const size_t slot = (size_t)__umul64hi(u, filled);
+    const size_t slot = replay_slot(r, filled, n, seed, draw, k);   // the same draw as maze_dqn_sample
     if (lane < 6) {
         vec[(size_t)k * 6 + lane] = r.vec[slot * 6 + lane];
         next_vec[(size_t)k * 6 + lane] = r.next_vec[slot * 6 + lane];

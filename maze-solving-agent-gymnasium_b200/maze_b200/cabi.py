@@ -57,7 +57,7 @@ class MazeReplay(C.Structure):
     _fields_ = [
         ("capacity", C.c_int64), ("pushed", C.c_void_p), ("vec", C.c_void_p), ("next_vec", C.c_void_p),
         ("win", C.c_void_p), ("next_win", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
-        ("stage_vec", C.c_void_p), ("stage_win", C.c_void_p),
+        ("stage_vec", C.c_void_p), ("stage_win", C.c_void_p), ("without_replacement", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

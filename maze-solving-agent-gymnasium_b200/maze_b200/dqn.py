@@ -25,7 +25,9 @@ from .agents import epsilon_lut
 
 
 class DeviceReplay:
-    def __init__(self, env, capacity: int, seed: int = 0):
+    def __init__(self, env, capacity: int, seed: int = 0, without_replacement: bool = True):
+        """without_replacement=True: a sampled batch holds distinct transitions, like random.sample in the reference's
+        ReplayMemory.sample (lib/replay_memory.py:20-21); False: independent uniform draws."""
         self.batch = env.batch if hasattr(env, "batch") else env
         self.device, self.ctx = self.batch.device, self.batch.ctx
         self.capacity = int(capacity)
@@ -45,7 +47,8 @@ class DeviceReplay:
         self._c = cabi.MazeReplay(
             capacity=self.capacity, pushed=self.pushed.data_ptr(), vec=self.vec.data_ptr(), next_vec=self.next_vec.data_ptr(),
             win=self.win.data_ptr(), next_win=self.next_win.data_ptr(), action=self.action.data_ptr(),
-            reward=self.reward.data_ptr(), stage_vec=self.stage_vec.data_ptr(), stage_win=self.stage_win.data_ptr())
+            reward=self.reward.data_ptr(), stage_vec=self.stage_vec.data_ptr(), stage_win=self.stage_win.data_ptr(),
+            without_replacement=int(bool(without_replacement)), reserved=0)
 
     def _stream(self):
         return cabi.current_stream(self.device)

@@ -293,6 +293,27 @@ class MazeBatch:
             visit_tiled=1 if self.visit_layout == "tile" else 0, visit_slot=self.visit_slot,
             target_dirty=self.target_dirty.data_ptr(), packed=self.packed.data_ptr())
 
+    def view_struct(self, lo: int, hi: int) -> cabi.MazeEnvBatch:
+        """maze_env_batch over the envs [lo, hi) of this batch: the same buffers with every per-env pointer advanced by
+        lo (the visit array by lo env strides), so that a launch on the view touches exactly those envs.  The shared
+        fields (statistics, regeneration queue, target_dirty) stay shared."""
+        if not 0 <= lo < hi <= self.num_envs:
+            raise ValueError("env range outside the batch")
+        c = cabi.MazeEnvBatch.from_buffer_copy(self._c)
+        c.num_envs = hi - lo
+        for name, per_env_bytes in (("env_maze", 4), ("state", 8), ("agent", 8), ("target", 8), ("best_dir", 8), ("reward", 8),
+                                    ("terminated", 1), ("truncated", 1), ("ep_return", 8), ("packed", 4)):
+            base = getattr(self._c, name)
+            if base:
+                setattr(c, name, base + lo * per_env_bytes)
+        c.visits = self._c.visits + lo * self._c.visit_env_stride * 2
+        return c
+
+    def step_view(self, view: cabi.MazeEnvBatch, actions_ptr, mode: int, stream):
+        """maze_step on a view_struct(); actions_ptr points at the view's first action; `stream` is a raw cudaStream_t."""
+        rc = cabi.lib().maze_step(self.ctx.handle, C.byref(view), actions_ptr, mode, stream)
+        self.ctx.check(rc, "maze_step")
+
     def reset(self, mask: Optional[torch.Tensor] = None):
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()

@@ -250,28 +250,64 @@ class MazeVectorEnv(_VectorBase):
             per += 3 * cabi.WINDOW * cabi.WINDOW * 4 + 2 * 16
         return self.num_envs * per
 
-    def step_host_packed(self, actions: np.ndarray, decode: bool = False):
-        """step_host() over the packed wire format: one host-to-device copy (actions), one kernel that writes a
-        single uint32 record per env instead of the 26 bytes of wide outputs (MAZE_STEP_PACKED | MAZE_STEP_NO_WIDE),
-        one device-to-host copy, one stream synchronisation.  Returns the pinned uint32 [B] record array (a view:
-        the next call overwrites it); `decode=True` returns what step_host() returns, bit for bit, by running
-        cabi.decode_records on it (a host-side C loop; `target` and the per-env shapes are refreshed from the
-        device only on the steps whose launch changed a maze).  -v0 observations only."""
+    def pinned_actions(self) -> torch.Tensor:
+        """A fresh uint8 [B] tensor in pinned host memory: actions written into it go to the device without the extra
+        host-side staging copy that pageable numpy arrays need (4 MB per step at 4 M envs)."""
+        return torch.zeros(self.num_envs, dtype=torch.uint8, pin_memory=True)
+
+    def step_host_packed(self, actions, decode: bool = False, chunks: Optional[int] = None):
+        """step_host() over the packed wire format: the actions go host -> device, the kernel writes a single uint32
+        record per env instead of the 26 bytes of wide outputs (MAZE_STEP_PACKED | MAZE_STEP_NO_WIDE), the records come
+        back to pinned host memory, one synchronisation.  With chunks > 1 (default 4 for batches of 256 k envs and more)
+        the batch is cut into env ranges whose copy-in / kernel / copy-out run on alternating streams, so that the PCIe
+        transfers of one range overlap the kernel of the next and the two directions overlap each other; the result is
+        the same launch by launch (envs are independent).  Returns the pinned uint32 [B] record array (a view: the next
+        call overwrites it); `decode=True` returns what step_host() returns, bit for bit, by running
+        cabi.decode_records on it (a host-side C loop; `target` and the per-env shapes are refreshed from the device
+        only on the steps whose launch changed a maze).  -v0 observations only."""
         if self.enrich:
             raise cabi.MazeError("the packed wire format carries the -v0 observation; use step_host() with enrich=True")
         b = self.batch
-        self.step(actions, extra_mode=cabi.STEP_PACKED | cabi.STEP_NO_WIDE)
+        B = self.num_envs
+        if chunks is None:
+            chunks = 4 if B >= 262144 else 1
         if self._h_packed is None:
-            self._h_packed = torch.empty(self.num_envs, dtype=torch.int32, pin_memory=True)
+            self._h_packed = torch.empty(B, dtype=torch.int32, pin_memory=True)
             self._h_flag = torch.ones(1, dtype=torch.int32, pin_memory=True)
-            self._h_target = torch.empty((self.num_envs, 2), dtype=torch.int32, pin_memory=True)
-            self._h_shape = torch.empty((self.num_envs, 2), dtype=torch.int32, pin_memory=True)
-            self._h_tor = torch.empty(self.num_envs, dtype=torch.uint8, pin_memory=True)
-        self._h_packed.copy_(b.packed, non_blocking=True)
-        self._h_flag.copy_(b.target_dirty, non_blocking=True)
+            self._h_target = torch.empty((B, 2), dtype=torch.int32, pin_memory=True)
+            self._h_shape = torch.empty((B, 2), dtype=torch.int32, pin_memory=True)
+            self._h_tor = torch.empty(B, dtype=torch.uint8, pin_memory=True)
+            self._h_actions = torch.empty(B, dtype=torch.uint8, pin_memory=True) if self._h_actions is None else self._h_actions
+            self._side_streams = [torch.cuda.Stream(self.device) for _ in range(2)]
         stream = torch.cuda.current_stream(self.device)
+        mode = self._mode | cabi.STEP_PACKED | cabi.STEP_NO_WIDE
+        if chunks <= 1:
+            self.step(actions, extra_mode=cabi.STEP_PACKED | cabi.STEP_NO_WIDE, observe=False)
+            self._h_packed.copy_(b.packed, non_blocking=True)
+        else:
+            if self.on_win == "regenerate":
+                self.drain_regeneration()
+            if isinstance(actions, torch.Tensor) and actions.device.type == "cpu" and actions.is_pinned() and actions.dtype == torch.uint8:
+                src = actions.reshape(-1)      # already in pinned host memory: copied to the device from where it is
+            else:
+                self._h_actions.numpy()[:] = np.ascontiguousarray(actions, dtype=np.uint8).reshape(-1)
+                src = self._h_actions
+            start = torch.cuda.Event()
+            start.record(stream)
+            bounds = [B * k // chunks // 512 * 512 for k in range(chunks)] + [B]    # whole CTAs per range
+            for k in range(chunks):
+                lo, hi = bounds[k], bounds[k + 1]
+                side = self._side_streams[k % 2]
+                side.wait_event(start)
+                with torch.cuda.stream(side):
+                    self._d_actions[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                    b.step_view(b.view_struct(lo, hi), self._d_actions.data_ptr() + lo, mode, side.cuda_stream)
+                    self._h_packed[lo:hi].copy_(b.packed[lo:hi], non_blocking=True)
+            for side in self._side_streams:
+                stream.wait_stream(side)
+        self._h_flag.copy_(b.target_dirty, non_blocking=True)
         stream.synchronize()
-        nbytes = 4 * self.num_envs + 4
+        nbytes = 4 * B + 4
         if int(self._h_flag[0]) != 0:   # a maze changed under some env: refresh the target (and shape / topology) mirrors
             b.target_dirty.zero_()
             self._h_target.copy_(b.target, non_blocking=True)

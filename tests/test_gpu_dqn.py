@@ -126,3 +126,43 @@ def test_masked_epsilon_greedy_matches_reference_distribution():
     assert (counts[p == 0] == 0).all()
     assert np.abs(counts / N - p).max() < 4.5 * np.sqrt(0.25 / N)
     assert int(explore.steps_done.cpu()[0]) == N
+
+
+def test_sampling_without_replacement_is_random_sample():
+    """ReplayMemory.sample is random.sample(memory, batch_size) (lib/replay_memory.py:20-21): a batch holds DISTINCT
+    transitions.  The ring's default reproduces that (first n images of a keyed pseudo-random permutation of the stored
+    slots): a batch of the whole ring is a permutation of it, every smaller batch is duplicate-free, every slot is equally
+    likely, and different draws give different batches.  without_replacement=False is the round-1 behaviour
+    (independent uniform draws, duplicates expected)."""
+    from maze_b200.dqn import DeviceReplay
+    mb, batch, _ = _setup(B_per_maze=8)
+    B = batch.num_envs
+    N = 3000                                              # stored transitions: not a power of two
+    mem = DeviceReplay(batch, capacity=4096, seed=11)
+    assert mem._c.without_replacement == 1
+    mem.reward[:N] = torch.arange(N, dtype=torch.float32, device="cuda")    # tag every slot
+    mem.pushed.fill_(N)
+    _, _, reward, _ = mem.sample(N)
+    assert torch.equal(reward.sort()[0], torch.arange(N, dtype=torch.float32, device="cuda"))
+    counts = torch.zeros(N, device="cuda")
+    first = None
+    for d in range(300):
+        r = mem.sample_packed(500)[5]
+        assert r.unique().numel() == 500 and r.max() < N
+        counts += torch.bincount(r.long(), minlength=N).float()
+        if d == 0:
+            first = r.clone()
+        elif d == 1:
+            assert not torch.equal(first, r)
+    expected = 300 * 500 / N                               # 50 per slot; binomial sd ~ 6.5
+    assert counts.min() > expected - 6 * 6.5 and counts.max() < expected + 6 * 6.5
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    assert chi2 < N * (1 - 500 / N) + 6 * (2 * N) ** 0.5   # hypergeometric draws: variance a little below binomial
+    # n larger than what is stored: the reference's agent returns before sampling (ddqn_agent.py:114-115); here the draws
+    # fall back to independent ones instead of failing on the device
+    r = mem.sample_packed(4000)[5]
+    assert r.max() < N and r.unique().numel() < 4000
+    loose = DeviceReplay(batch, capacity=4096, seed=11, without_replacement=False)
+    loose.reward[:N] = torch.arange(N, dtype=torch.float32, device="cuda")
+    loose.pushed.fill_(N)
+    assert loose.sample_packed(2000)[5].unique().numel() < 2000

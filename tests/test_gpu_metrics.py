@@ -119,6 +119,56 @@ def test_best_of_k_selection(algo, toroidal):
     assert (prev_d <= d1 * (1 + 1e-12)).all() and (prev_d < d1 * (1 - 1e-9)).mean() > 0.5
 
 
+@pytest.mark.parametrize("algo,toroidal", [("r-prim", False), ("dfs", False), ("prim&kill", False), ("r-prim", True)])
+def test_best_of_six_keeps_the_reference_winner(algo, toroidal, monkeypatch):
+    """generate_maze (base_maze_env.py:78-97, toroidal_maze_env.py:40-54): of the six draws the FIRST strict minimum of
+    the McClendon difficulty is kept.  Every candidate is materialised on its own (the MAZE_GEN_CANDIDATE_BASE test hook
+    shifts the RNG key, candidates = 1), re-scored with the ORACLE (oracle.metrics.mcclendon, itself pinned to the
+    reference's values), and the oracle's winner must be the maze the best-of-six launch kept -- through both code paths:
+    the bulk pipeline (planes kernel + scoring kernel) and the single-kernel path of the regeneration queue."""
+    import maze_b200 as mb
+    from oracle.metrics import mcclendon
+    n, S = 40, 21
+    cands = []
+    for c in range(6):
+        monkeypatch.setenv("MAZE_GEN_CANDIDATE_BASE", str(c))
+        pool = mb.MazePool(n, (S, S))
+        pool.generate(algorithms=algo, toroidal=toroidal, seed=99)
+        meta = pool.meta_host()
+        cands.append([(pool.grid_host(m).copy(), int(meta[m, 2]), int(meta[m, 3])) for m in range(n)])
+    monkeypatch.delenv("MAZE_GEN_CANDIDATE_BASE")
+
+    def oracle_score(grid, start, goal):
+        s, g = (start & 0xffff, start >> 16), (goal & 0xffff, goal >> 16)
+        if toroidal:   # scored on the bordered maze before stripping (lib/maze_generation.py:48-56)
+            grid, s, g = np.pad(grid, 1), (s[0] + 1, s[1] + 1), (g[0] + 1, g[1] + 1)
+        return mcclendon(grid, s, g)[0]
+
+    winners = []
+    for m in range(n):
+        scores = [oracle_score(*cands[c][m]) for c in range(6)]
+        best = 0
+        for c in range(1, 6):
+            if scores[c] < scores[best]:       # strict <: the first minimum wins
+                best = c
+        winners.append((best, scores))
+    assert len({w for w, _ in winners}) >= 4          # the winner is not always the same candidate
+
+    bulk = mb.MazePool(n, (S, S))
+    dout = torch.zeros(n, dtype=torch.float64, device="cuda")
+    bulk.generate(algorithms=algo, toroidal=toroidal, seed=99, candidates=6, difficulty_out=dout)
+    queue = mb.MazePool(n, (S, S))
+    queue.generate(algorithms=algo, toroidal=toroidal, seed=99)                       # configure the slots, generation count 1 ...
+    queue.meta[:, mb.cabi.META_SPARE] = 0                                             # ... back to 0: same RNG keys as `bulk`
+    ids, count = torch.arange(n, dtype=torch.int32, device="cuda"), torch.tensor([n], dtype=torch.int32, device="cuda")
+    queue.generate(ids=ids, count_dev=count, configure=False, seed=99, candidates=6)  # device-side count: the single-kernel path
+    for m in range(n):
+        best, scores = winners[m]
+        for pool in (bulk, queue):
+            np.testing.assert_array_equal(pool.grid_host(m), cands[best][m][0], err_msg=f"slot {m}: kept maze is not candidate {best} {scores}")
+        assert dout[m].item() == pytest.approx(scores[best], rel=1e-9)
+
+
 def _ext_vector(d):
     return np.array([d["density"], d["T"], d["J"], d["CR"], d["AC"], d["FDE"], d["BDE"], d["L_DE"],
                      *d["T_DE"], *d["D_sharp"], *d["L_sharp"]], dtype=np.float64)

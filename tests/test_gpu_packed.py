@@ -70,8 +70,10 @@ def test_no_wide_mode_leaves_the_wide_buffers_alone_and_steps_identically():
         envs[0].batch.step(acts, mb.cabi.STEP_NO_WIDE)
 
 
+@pytest.mark.parametrize("chunks", [1, 3])
 @pytest.mark.parametrize("topology", ["euclid", "toroidal"])
-def test_step_host_packed_equals_step_host(topology):
+def test_step_host_packed_equals_step_host(topology, chunks):
+    """chunks = 3: the batch is stepped as three env ranges on alternating streams (copy-in / kernel / copy-out overlapped)."""
     import maze_b200 as mb
     kw = dict(shape=(21, 21), topology=topology, algorithms=["r-prim", "dfs"], num_mazes=100, seed=5, on_win="next")
     a, b = mb.MazeVectorEnv(3000, **kw), mb.MazeVectorEnv(3000, **kw)
@@ -81,7 +83,7 @@ def test_step_host_packed_equals_step_host(topology):
     for t in range(120):
         acts = rng.integers(0, 4, 3000).astype(np.uint8)
         oa, ra, ta, ua, _ = a.step_host(acts)
-        ob, rb, tb, ub, _ = b.step_host_packed(acts, decode=True)
+        ob, rb, tb, ub, _ = b.step_host_packed(acts, decode=True, chunks=chunks)
         for k in ("agent", "target", "best dir"):
             np.testing.assert_array_equal(oa[k], ob[k], err_msg=f"{k} step {t}")
         np.testing.assert_array_equal(ra.view(np.uint64), rb.view(np.uint64))
@@ -90,6 +92,7 @@ def test_step_host_packed_equals_step_host(topology):
     # euclid: 4 B per env and step.  The short toroidal episodes change some env's maze on most steps here, and every such
     # step also refreshes the `target` mirror (8 B per env)
     assert b.d2h_bytes_per_step() < (0.3 if topology == "euclid" else 0.5) * a.d2h_bytes_per_step()
+    assert torch.equal(a.batch.state, b.batch.state) and torch.equal(a.batch.visits, b.batch.visits)
 
 
 def test_statistics_count_steps():

@@ -250,3 +250,119 @@ def test_terminal_observation_and_replay_see_the_maze_the_episode_was_played_on(
     assert int(goal.sum()) == wins
     nv = mem.next_vec[:n][goal]
     assert torch.equal(nv[:, 0:2], nv[:, 2:4])
+
+
+# ---- configs[2] and configs[3] at their stated sizes (BASELINE.json) ---------------------------
+class _SampledOracle:
+    """Replays a sample of envs of a regenerate-on-win MazeVectorEnv through the closed-form oracle: rebuilt from the
+    pool's grid whenever the env restarts after a win (the slot then holds the regenerated maze)."""
+
+    def __init__(self, env, ids, toroidal):
+        self.env, self.ids, self.tor = env, [int(i) for i in ids], toroidal
+        self.cur = [self._make(e) for e in self.ids]
+        for o in self.cur:
+            o.reset()
+        self.pending = [False] * len(self.ids)
+        self.won = [False] * len(self.ids)
+        self.wins = self.steps = self.rebuilt = 0
+
+    def _make(self, e):
+        meta = self.env.pool.meta[e].cpu().numpy()
+        grid = self.env.pool.grid_host(e).copy()
+        assert check_perfect_maze(np.pad(grid, 1) if self.tor else grid)[0], e
+        return ClosedFormEnv(grid, _meta_rc(meta[2]), _meta_rc(meta[3]), self.tor)
+
+    def check(self, t, acts, agent, best, reward, term, trunc):
+        for k, e in enumerate(self.ids):
+            if self.pending[k]:
+                if self.won[k]:
+                    self.cur[k] = self._make(e)
+                    self.rebuilt += 1
+                o, _ = self.cur[k].reset()
+                self.pending[k] = False
+                assert reward[e] == 0.0 and not term[e] and not trunc[e], (t, e)
+            else:
+                o, r, otr, ote, _ = self.cur[k].step(int(acts[e]))
+                assert np.float64(r).view(np.uint64) == np.float64(reward[e]).view(np.uint64), (t, e, r, reward[e])
+                assert bool(ote) == bool(term[e]) and bool(otr) == bool(trunc[e]), (t, e)
+                self.pending[k], self.won[k] = bool(ote or otr), bool(ote)
+                self.wins += int(ote)
+                self.steps += 1
+            assert tuple(o["agent"]) == tuple(agent[e]) and tuple(o["best dir"]) == tuple(best[e]), (t, e)
+
+
+def _greedy(best, S_of_env, rng, p):
+    """Follow obs['best dir'] (= agent - next; +-(S - 1) components are wrapped moves) with probability p."""
+    B = best.shape[0]
+    g = np.zeros(B, dtype=np.uint8)
+    r, c = best[:, 0], best[:, 1]
+    g[(r == -1) | (r == S_of_env - 1)] = 0
+    g[(r == 1) | (r == -(S_of_env - 1))] = 1
+    g[(c == -1) | (c == S_of_env - 1)] = 2
+    g[(c == 1) | (c == -(S_of_env - 1))] = 3
+    return np.where(rng.random(B) < p, g, rng.integers(0, 4, B)).astype(np.uint8)
+
+
+def test_config3_at_size_toroidal_81_mixed_generators_regenerate_on_win():
+    """configs[2] at its stated size: toroidal 40x40 = 81 x 81 blocks (the shape the reference's examples pass to both
+    topologies, test_q_toroid.py:17; 41 logical lines), r-prim / dfs / prim&kill mixed per slot, 4096 envs, every win
+    regenerates the env's maze; 64 sampled envs are replayed through the oracle, all envs are checked by invariants."""
+    import maze_b200 as mb
+    B, S = 4096, 81
+    env = mb.MazeVectorEnv(B, shape=(S, S), topology="toroidal", algorithms=["r-prim", "dfs", "prim&kill"], seed=31, on_win="regenerate", stats=True)
+    obs, _ = env.reset()
+    rng = np.random.default_rng(1)
+    ora = _SampledOracle(env, rng.choice(B, 64, replace=False), True)
+    for t in range(450):
+        acts = _greedy(obs["best dir"].cpu().numpy(), S, rng, 0.8)
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(acts).cuda())
+        ora.check(t, acts, obs["agent"].cpu().numpy(), obs["best dir"].cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy())
+    env.drain_regeneration()
+    stats = env.episode_statistics()
+    meta = env.pool.meta_host()
+    assert ora.rebuilt >= 20 and stats["wins"] > 20 * B // 64
+    assert meta[:, mb.cabi.META_SPARE].sum() == B + stats["wins"]               # one generation per slot + one per win
+    assert (meta[:, 0] == S).all() and (meta[:, 1] == S).all() and (meta[:, mb.cabi.META_FLAGS] & 1).all()
+    algos = (meta[:, mb.cabi.META_FLAGS] >> 8) & 0xff
+    assert set(np.unique(algos)) == {0, 1, 2}
+    st = env.batch.state_host()
+    tab = env.pool.table[torch.arange(B, device="cuda"), torch.from_numpy(st["r"] * S + st["c"]).cuda()]
+    assert bool((tab & 1).all())                                                # nobody stands in a wall of its (possibly new) maze
+
+
+def test_config4_at_size_curriculum_21_to_129_with_double_q():
+    """configs[3] at its stated size: mazes from 10x10 cells (21 blocks) growing by (4, 4) blocks per win towards 64x64
+    cells (129 blocks) (simple_variable_maze_env.py:93-112), generator switched after 5 and 10 wins
+    (off_policy_trainer.py:302-310), device DQAgent learning off-policy; 16 sampled envs replayed through the oracle on
+    every maze they meet, shape / generator invariants for all."""
+    import maze_b200 as mb
+    from maze_b200.agents import DQAgent
+    B = 512
+    env = mb.MazeVectorEnv(B, shape=(129, 129), start_shape=(21, 21), grow=4, algorithms="r-prim", seed=5, on_win="regenerate",
+                           algorithm_schedule=((5, "prim&kill"), (10, "dfs")), stats=True)
+    agent = DQAgent(env, learning_rate=0.2, initial_epsilon=0.9, epsilon_decay=300, final_epsilon=0.05, discount_factor=0.8, eta=1e-3,
+                    envs_per_agent=1, seed=1, capacity=1 << 22)
+    obs, _ = env.reset()
+    rng = np.random.default_rng(2)
+    ora = _SampledOracle(env, rng.choice(B, 16, replace=False), False)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(3000):
+        acts = agent.get_action()
+        bd = obs["best dir"]
+        follow = torch.where(bd[:, 0] == -1, 0, torch.where(bd[:, 0] == 1, 1, torch.where(bd[:, 1] == -1, 2, 3))).to(torch.uint8)
+        acts = torch.where(torch.rand(B, device="cuda", generator=gen) < 0.9, follow, acts)
+        agent.core.last_action.copy_(acts)
+        obs, rew, term, trunc, _ = env.step(acts)
+        agent.update()
+        ora.check(t, acts.cpu().numpy(), obs["agent"].cpu().numpy(), obs["best dir"].cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(),
+                  trunc.cpu().numpy())
+    agent.core.check_overflow()
+    env.drain_regeneration()
+    wins = env.wins.cpu().numpy()
+    meta = env.pool.meta_host()
+    assert env.episode_statistics()["wins"] == wins.sum() and ora.rebuilt > 50
+    assert meta[:, 0].max() >= 61, meta[:, 0].max()          # the curriculum climbed well past the sizes round 1 tested (31)
+    for e in range(B):
+        assert meta[e, 0] == meta[e, 1] == min(129, 21 + 4 * int(wins[e]))
+        algo = (int(meta[e, mb.cabi.META_FLAGS]) >> 8) & 0xff
+        assert algo == (mb.cabi.ALGO_DFS if wins[e] >= 10 else mb.cabi.ALGO_PRIMKILL if wins[e] >= 5 else mb.cabi.ALGO_RPRIM)
