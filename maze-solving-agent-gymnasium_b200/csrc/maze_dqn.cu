@@ -8,6 +8,7 @@
 // instead of 5.5 KB, and a 1 M-transition ring fits in 245 MB.
 #include "maze_env.cuh"
 #include "maze_replay.cuh"
+#include "maze_window.cuh"
 
 namespace {
 
@@ -17,105 +18,114 @@ constexpr int WIN_CELLS = WIN * WIN;
 constexpr int WORDS = MAZE_WINDOW_WORDS;
 constexpr unsigned FULL = 0xffffffffu;
 
-// Observation of env e by one warp: vec[6] (lanes 0-5 hold the values) and the packed window
-// (lane w < 24 holds word w).  Same rules as maze_window_kernel (maze_obs.cu).
+// Observation of one env by HALF a warp (16 lanes, two envs per warp): lane r < 15 of the half owns window row r --
+// it walks the 15 blocks of its row (one table byte and one visit word each; a 4 x 4 visit tile is one 32-byte sector,
+// shared by the four lanes whose rows cross it) and assembles the row's three 15-bit masks in registers; lane 2 k then
+// takes row 2 k + 1's masks from its neighbour and holds word k of each channel (window rows 2 k in bits 0-14,
+// 2 k + 1 in bits 16-30).  Round 1 used a whole warp per env with one ballot per block pair and channel: ~850 warp
+// instructions per env (profiles/r01i_dqn_push_details.txt); this form needs about a sixth of that.
+// Same rules as maze_window_kernel (maze_obs.cu).
 struct PackedObs {
-    float vec;       // lane < 6
-    unsigned word;   // lane < 24
+    float vec;          // half-lane < 6: the state vector
+    unsigned word[3];   // even half-lane 2 k: word k of channels 0 (wall), 1 (floor), 2 (not visited); k = 0..7
 };
 
-__device__ __forceinline__ PackedObs encode_obs(const maze_env_batch& b, int e) {
-    const int lane = threadIdx.x & 31;
-    const EnvState st = unpack_state(b.state[e]);
-    const int m = b.env_maze[e];
-    const MazeView mz = load_maze(b, m);
-    const int H = mz.H, W = mz.W;
-    const int start_idx = (mz.start & 0xffff) * W + (mz.start >> 16);
-    const int goal_idx = (mz.goal & 0xffff) * W + (mz.goal >> 16);
-    const bool ok = H >= WIN && W >= WIN;
-    int r0 = st.r - WIN / 2, c0 = st.c - WIN / 2;
-    if (!mz.tor) {
-        r0 = min(max(r0, 0), H - WIN);
-        c0 = min(max(c0, 0), W - WIN);   // the reference clamps with len(maze) (maze_handler.py:21-29: square mazes only); W keeps a non-square slot in bounds
-    }
+__device__ __forceinline__ PackedObs encode_obs16(const maze_env_batch& b, int e, bool valid, int hl) {
     PackedObs o;
-    o.word = 0;
-    // Lane -> window block: lanes 0-14 take the columns of window row 2 k, lanes 16-30 those of row 2 k + 1 (lanes
-    // 15 / 31 and row 15 are idle), so word k of a channel holds two window rows and the column part of every index
-    // is fixed per lane (the kernel is issue-bound: per-block div / mod and index arithmetic were half of it).
-    const int half = lane >> 4, col = lane & 15;
-    const bool col_ok = ok && col < WIN;
-    int cc = c0 + min(col, WIN - 1);
-    if (mz.tor) cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
-#pragma unroll
-    for (int k = 0; k < (WIN + 1) / 2; ++k) {
-        bool wall = false, floor = false, fresh = false;
-        if (col_ok && 2 * k + half < WIN) {
-            int rr = r0 + 2 * k + half;
-            if (mz.tor) rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
-            const int idx = rr * W + cc;
-            const bool open = (__ldg(mz.tab + idx) & MAZE_TAB_OPEN) != 0;
-            wall = !open;
-            floor = open && idx != goal_idx;
-            if (open && idx != start_idx) {
-                const unsigned v = *VISIT_AT(b, e, visit_index(b, rr, cc, W));
-                fresh = !((int)(v >> 8) == st.epoch && (v & 0xffu) != 0);
-            }
-        }
-        const unsigned w0 = __ballot_sync(FULL, wall), w1 = __ballot_sync(FULL, floor), w2 = __ballot_sync(FULL, fresh);
-        if (lane == k) o.word = w0;
-        if (lane == 8 + k) o.word = w1;
-        if (lane == 16 + k) o.word = w2;
+    o.vec = 0.f;
+    o.word[0] = o.word[1] = o.word[2] = 0u;
+    unsigned m0 = 0, m1 = 0, m2 = 0;
+    EnvState st{};
+    MazeView mz{};
+    if (valid) {
+        st = unpack_state(b.state[e]);
+        mz = load_maze(b, b.env_maze[e]);
+        window_row_masks(b, e, st, mz, hl, m0, m1, m2);
     }
-    // float32 of the float64 quotient, like torch.tensor(np.concatenate([...]), dtype=float32)
-    const int2 bd = best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, H, W, mz.tor);
-    // one division for the whole warp (lanes 0-3 hold the four quotients): a switch with a __ddiv_rn per case made
-    // the warp run the division subroutine four times
-    const double num = (double)(lane == 0 ? st.r : (lane == 1 ? st.c : (lane == 2 ? (mz.goal & 0xffff) : (mz.goal >> 16))));
-    const double q = __ddiv_rn(num, (double)((lane & 1) ? W : H));
-    const double v = lane < 4 ? q : (lane == 4 ? (double)bd.x : (lane == 5 ? (double)bd.y : 0.0));
-    o.vec = (float)v;
+    // odd rows move to the even lane above them (all 32 lanes take part in the shuffles)
+    const unsigned n0 = __shfl_down_sync(FULL, m0, 1), n1 = __shfl_down_sync(FULL, m1, 1), n2 = __shfl_down_sync(FULL, m2, 1);
+    if (!(hl & 1)) {
+        const bool has_odd = hl + 1 < WIN;
+        o.word[0] = m0 | (has_odd ? n0 << 16 : 0u);
+        o.word[1] = m1 | (has_odd ? n1 << 16 : 0u);
+        o.word[2] = m2 | (has_odd ? n2 << 16 : 0u);
+    }
+    if (valid && hl < 6) {
+        // float32 of the float64 quotient, like torch.tensor(np.concatenate([...]), dtype=float32); one division per lane
+        const int2 bd = best_dir_from_code((st.tab >> MAZE_TAB_CODE_SHIFT) & 7, st.r, st.c, mz.H, mz.W, mz.tor);
+        const double num = (double)(hl == 0 ? st.r : (hl == 1 ? st.c : (hl == 2 ? (mz.goal & 0xffff) : (mz.goal >> 16))));
+        const double q = __ddiv_rn(num, (double)((hl & 1) ? mz.W : mz.H));
+        o.vec = (float)(hl < 4 ? q : (hl == 4 ? (double)bd.x : (double)bd.y));
+    }
     return o;
+}
+
+__device__ __forceinline__ void store_obs16(const PackedObs& o, int hl, float* __restrict__ vec6, uint32_t* __restrict__ words24) {
+    if (hl < 6) vec6[hl] = o.vec;
+    if (!(hl & 1)) {
+        const int k = hl >> 1;
+        words24[k] = o.word[0];
+        words24[8 + k] = o.word[1];
+        words24[16 + k] = o.word[2];
+    }
 }
 
 __global__ void __launch_bounds__(DQN_THREADS)
 maze_dqn_observe_kernel(maze_env_batch b, maze_replay r) {
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (DQN_THREADS / 32) + (threadIdx.x >> 5);
-    if (e >= b.num_envs) return;
-    const PackedObs o = encode_obs(b, e);
-    if (lane < 6) r.stage_vec[(size_t)e * 6 + lane] = o.vec;
-    if (lane < WORDS) r.stage_win[(size_t)e * WORDS + lane] = o.word;
+    const int hl = threadIdx.x & 15;
+    const int e = blockIdx.x * (DQN_THREADS / 16) + (threadIdx.x >> 4);
+    const bool valid = e < b.num_envs;
+    const PackedObs o = encode_obs16(b, e, valid, hl);
+    if (valid) store_obs16(o, hl, r.stage_vec + (size_t)e * 6, r.stage_win + (size_t)e * WORDS);
 }
 
-__global__ void __launch_bounds__(DQN_THREADS)
+// The kernel is bound by the latency of its dependent loads (state -> maze record -> table / visit rows -> ring), not by
+// bytes or instructions (ncu, profiles/r02i_obs_details.txt: long-scoreboard stalls, 36 % occupancy).  So everything that
+// does not depend on the gather is issued before it: the slot claim (one atomicAdd per warp for its two envs) and the loads
+// of the staged observation travel while the window rows are fetched.
+constexpr int PUSH_THREADS = 256;
+
+__global__ void __launch_bounds__(PUSH_THREADS, 4)
 maze_dqn_push_kernel(maze_env_batch b, maze_replay r, const uint8_t* __restrict__ actions) {
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (DQN_THREADS / 32) + (threadIdx.x >> 5);
-    if (e >= b.num_envs) return;
-    const PackedObs o = encode_obs(b, e);
-    const EnvState st = unpack_state(b.state[e]);
-    if (st.steps != 0) {   // a real transition (steps == 0 only right after a reset)
-        unsigned long long at = 0;
-        if (lane == 0) at = atomicAdd(r.pushed, 1ull);
-        at = __shfl_sync(FULL, at, 0);
-        const size_t slot = (size_t)(at % (unsigned long long)r.capacity);
-        if (lane < 6) {
-            r.vec[slot * 6 + lane] = r.stage_vec[(size_t)e * 6 + lane];
-            r.next_vec[slot * 6 + lane] = o.vec;
-        }
-        if (lane < WORDS) {
-            r.win[slot * WORDS + lane] = r.stage_win[(size_t)e * WORDS + lane];
-            r.next_win[slot * WORDS + lane] = o.word;
-        }
-        if (lane == 0) {
-            r.action[slot] = actions[e] & 3;
-            r.reward[slot] = (float)b.reward[e];
+    const int hl = threadIdx.x & 15, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (PUSH_THREADS / 16) + (threadIdx.x >> 4);
+    const bool valid = e < b.num_envs;
+    bool real = false;
+    if (valid) real = unpack_state(b.state[e]).steps != 0;   // a real transition (steps == 0 only right after a reset)
+    // slot claim for both envs of the warp
+    const unsigned real_halves = (__ballot_sync(FULL, real && hl == 0));          // bit 0 / bit 16
+    unsigned long long at = 0;
+    if (lane == 0 && real_halves) at = atomicAdd(r.pushed, (unsigned long long)__popc(real_halves));
+    // staged observation of the env (the `state` of its transition)
+    float sv = 0.f;
+    uint32_t sw0 = 0, sw1 = 0;
+    uint8_t act = 0;
+    float rew = 0.f;
+    if (real) {
+        if (hl < 6) sv = r.stage_vec[(size_t)e * 6 + hl];
+        sw0 = r.stage_win[(size_t)e * WORDS + hl];
+        if (hl < WORDS - 16) sw1 = r.stage_win[(size_t)e * WORDS + 16 + hl];
+        if (hl == 0) {
+            act = actions[e] & 3;
+            rew = (float)b.reward[e];
         }
     }
-    __syncwarp();
-    if (lane < 6) r.stage_vec[(size_t)e * 6 + lane] = o.vec;
-    if (lane < WORDS) r.stage_win[(size_t)e * WORDS + lane] = o.word;
+    const PackedObs o = encode_obs16(b, e, valid, hl);
+    at = __shfl_sync(FULL, at, 0);
+    if (real) {
+        const unsigned long long mine = at + ((lane >= 16 && (real_halves & 1u)) ? 1ull : 0ull);
+        const size_t slot = (size_t)(mine % (unsigned long long)r.capacity);
+        if (hl < 6) r.vec[slot * 6 + hl] = sv;
+        r.win[slot * WORDS + hl] = sw0;
+        if (hl < WORDS - 16) r.win[slot * WORDS + 16 + hl] = sw1;
+        store_obs16(o, hl, r.next_vec + slot * 6, r.next_win + slot * WORDS);
+        if (hl == 0) {
+            r.action[slot] = act;
+            r.reward[slot] = rew;
+        }
+    }
+    // (the staged observation was read into registers above, before anything re-stages it)
+    if (valid) store_obs16(o, hl, r.stage_vec + (size_t)e * 6, r.stage_win + (size_t)e * WORDS);
 }
 
 __device__ __forceinline__ void unpack_window(const uint32_t* __restrict__ words, float* __restrict__ out) {
@@ -234,7 +244,7 @@ extern "C" int maze_dqn_observe(maze_ctx* ctx, const maze_env_batch* b, const ma
     if (!ctx) return MAZE_E_NULL;
     if (int rc = maze_check_batch(ctx, b)) return rc;
     if (int rc = check_replay(ctx, r, true)) return rc;
-    const int per = DQN_THREADS / 32;
+    const int per = DQN_THREADS / 16;
     maze_dqn_observe_kernel<<<(b->num_envs + per - 1) / per, DQN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r);
     MAZE_CHECK(cudaGetLastError());
     return 0;
@@ -247,8 +257,8 @@ extern "C" int maze_dqn_push(maze_ctx* ctx, const maze_env_batch* b, const maze_
     if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_push: actions");
     if (r->capacity < b->num_envs)   // one launch claims up to num_envs slots: a smaller ring would hand one slot to several warps
         return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_push: replay capacity must be >= num_envs");
-    const int per = DQN_THREADS / 32;
-    maze_dqn_push_kernel<<<(b->num_envs + per - 1) / per, DQN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r, actions);
+    const int per = PUSH_THREADS / 16;
+    maze_dqn_push_kernel<<<(b->num_envs + per - 1) / per, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r, actions);
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

@@ -7,6 +7,7 @@
 // maze_direction_mask: one thread per env, four table bytes (lib/maze_handler.py:122-162,
 // simple_maze_env.py:41-50, toroidal_maze_env.py:57-70).
 #include "maze_env.cuh"
+#include "maze_window.cuh"
 
 namespace {
 
@@ -14,93 +15,49 @@ constexpr int OBS_THREADS = 256;
 constexpr int WIN = MAZE_WINDOW;
 constexpr int WIN_CELLS = WIN * WIN;
 
-// A CTA of 8 warps serves 8 consecutive envs.  Each warp gathers its env's 225 window blocks and writes
-// one byte (0 / 1) per output float into shared memory, laid out exactly like the output; then all 256
-// threads stream the 8 x 2 700 bytes out as 16-byte stores, four shared bytes -> one float4 (8 envs x
-// 675 floats start on a 16-byte boundary; one env's 2 700 bytes do not).  ncu of the first version
-// (one 4-byte store per value, div / mod per block): 1 080 warp instructions per env, 77 % issue-slot
-// busy, table rows missing L2 behind the streamed output -- hence the incremental indexing, the byte
-// staging and the evict_last policy on the table loads below.
-constexpr int WIN_ENVS = OBS_THREADS / 32;
+// A CTA of 256 threads serves 16 consecutive envs, 16 lanes each: lane r < 15 owns window row r and assembles its three
+// 15-bit masks in registers (window_row_masks: 15 table bytes + 15 visit words per lane; a 4 x 4 visit tile is one
+// 32-byte sector shared by the four lanes whose rows cross it), then writes them as bytes into shared memory, laid out
+// exactly like the output; then all 256 threads stream the 16 x 2 700 bytes out as 16-byte stores, four shared bytes ->
+// one float4 (16 envs x 675 floats start on a 16-byte boundary; one env's 2 700 bytes do not).  History (ncu): first
+// version 1 080 warp instructions per env (one 4-byte store per value, div / mod per block); round 1's warp-per-env
+// gather 757, issue slots 78 % busy at 0.48 of the HBM peak (profiles/r01j_window_after_details.txt); this one-lane-
+// per-row form does the gather in about a quarter of the instructions.
+constexpr int WIN_ENVS = OBS_THREADS / 16;
 constexpr int WIN_FLOATS = 3 * WIN_CELLS;
 
 #ifndef MAZE_WIN_MINB
-#define MAZE_WIN_MINB 5
+#define MAZE_WIN_MINB 4
 #endif
-// kTiled: 4 x 4-tiled visit index; kUnit: visit_cell_stride == 1 (env-major array, the -v1 default)
-template <bool kTiled, bool kUnit>
 __global__ void __launch_bounds__(OBS_THREADS, MAZE_WIN_MINB)
 maze_window_kernel(maze_env_batch b, float* __restrict__ window, double* __restrict__ agent_norm,
                    double* __restrict__ target_norm) {
     __shared__ __align__(16) uint8_t s_out[WIN_ENVS * WIN_FLOATS];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int hl = threadIdx.x & 15, w = threadIdx.x >> 4;
     const int e0 = blockIdx.x * WIN_ENVS, e = e0 + w;
-    uint8_t* so = s_out + w * WIN_FLOATS;
     if (e < b.num_envs) {
         const EnvState st = unpack_state(b.state[e]);
-        const int m = b.env_maze[e];
-        const int4 m0 = __ldg(reinterpret_cast<const int4*>(b.meta + (size_t)m * MAZE_META_WORDS));
-        const int H = m0.x, W = m0.y;
-        const bool tor = (__ldg(b.meta + (size_t)m * MAZE_META_WORDS + MAZE_META_FLAGS) & MAZE_FLAG_TOROIDAL) != 0;
-        const int start_idx = (m0.z & 0xffff) * W + (m0.z >> 16);
-        const int goal_idx = (m0.w & 0xffff) * W + (m0.w >> 16);
-        if (H < WIN || W < WIN) {   // no 15 x 15 crop exists (the reference cannot build one either)
-            for (int i = lane; i < WIN_FLOATS; i += 32) so[i] = 0;
-        } else {
-            int r0 = st.r - WIN / 2, c0 = st.c - WIN / 2;
-            if (!tor) {   // extract_submaze: clamped, and the reference uses len(maze) for both axes
-                r0 = min(max(r0, 0), H - WIN);
-                c0 = min(max(c0, 0), W - WIN);   // the reference clamps with len(maze) (maze_handler.py:21-29: square mazes only); W keeps a non-square slot in bounds
-            }
-            const uint8_t* tab = b.table + (size_t)m * b.slot;
-            const uint64_t pol_table = l2_policy<MAZE_TABLE_POLICY>();
-            const uint16_t* vbase = b.visits + (size_t)e * b.visit_env_stride;
-            const int wt = (W + 3) >> 2;
-            // Lane -> window block mapping: lanes 0-14 take the columns of an even window row, lanes 16-30 those of
-            // the odd row below it, eight row pairs per lane (lanes 15 / 31 and row 15 are idle: 225 of 256 slots).
-            // The column part of every index is then fixed per lane and the row part is a compile-time step, so the
-            // loop body is a handful of integer instructions around its two loads (the kernel is issue-bound).
-            // Table byte and visit word of all eight blocks are requested before any is used; the visit word is
-            // fetched whether or not the block is open (same sectors, one dependent round trip less).
-            constexpr int K = (WIN + 1) / 2;
-            const int half = lane >> 4, col = min(lane & 15, WIN - 1);
-            const bool col_ok = (lane & 15) < WIN;
-            int cc = c0 + col;
-            if (tor) cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);   // extract_submaze_toroid: (position + i - k) % maze_shape
-            const int cpart = kTiled ? (((cc >> 2) << 4) | (cc & 3)) : cc;
-            int idxs[K], tb[K];
-            unsigned vis[K];
+        const MazeView mz = load_maze(b, b.env_maze[e]);
+        unsigned m0, m1, m2;
+        window_row_masks(b, e, st, mz, hl, m0, m1, m2);
+        if (hl < WIN) {
+            uint8_t* sl = s_out + w * WIN_FLOATS + hl * WIN;   // block (row, col) of channel ch is output index 225 ch + 15 row + col
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                int rr = r0 + min(2 * k + half, WIN - 1);
-                if (tor) rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
-                idxs[k] = rr * W + cc;
-                tb[k] = pol_load_nc<MAZE_TABLE_POLICY>(tab + idxs[k], pol_table);
-                const int vi = kTiled ? ((((rr >> 2) * wt) << 4) | ((rr & 3) << 2)) + cpart : idxs[k];
-                vis[k] = __ldcs(kUnit ? vbase + vi : vbase + (size_t)vi * b.visit_cell_stride);
-            }
-            uint8_t* sl = so + half * WIN + col;   // block (row 2 k + half, col) is output index 30 k + half * 15 + col
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if (!col_ok || 2 * k + half >= WIN) continue;
-                const bool open = (tb[k] & MAZE_TAB_OPEN) != 0;
-                // non_visited (base_maze_env.py:148-149,183-184): open, not the start, no visit in this episode
-                const bool fresh = open && idxs[k] != start_idx && !((int)(vis[k] >> 8) == st.epoch && (vis[k] & 0xffu) != 0);
-                sl[2 * WIN * k] = open ? 0 : 1;                                          // maze == 0
-                sl[WIN_CELLS + 2 * WIN * k] = (open && idxs[k] != goal_idx) ? 1 : 0;     // maze == 1
-                sl[2 * WIN_CELLS + 2 * WIN * k] = fresh ? 1 : 0;
+            for (int j = 0; j < WIN; ++j) {
+                sl[j] = (uint8_t)((m0 >> j) & 1u);
+                sl[WIN_CELLS + j] = (uint8_t)((m1 >> j) & 1u);
+                sl[2 * WIN_CELLS + j] = (uint8_t)((m2 >> j) & 1u);
             }
         }
-        if (lane < 2) {
-            const int goal = m0.w;
-            const double shape = (double)(lane == 0 ? H : W);
-            if (agent_norm) agent_norm[(size_t)e * 2 + lane] = __ddiv_rn((double)(lane == 0 ? st.r : st.c), shape);
-            if (target_norm) target_norm[(size_t)e * 2 + lane] = __ddiv_rn((double)(lane == 0 ? (goal & 0xffff) : (goal >> 16)), shape);
+        if (hl < 2) {
+            const double shape = (double)(hl == 0 ? mz.H : mz.W);
+            if (agent_norm) agent_norm[(size_t)e * 2 + hl] = __ddiv_rn((double)(hl == 0 ? st.r : st.c), shape);
+            if (target_norm) target_norm[(size_t)e * 2 + hl] = __ddiv_rn((double)(hl == 0 ? (mz.goal & 0xffff) : (mz.goal >> 16)), shape);
         }
     }
     __syncthreads();
     const int n_float = min(WIN_ENVS, b.num_envs - e0) * WIN_FLOATS;
-    float* out = window + (size_t)e0 * WIN_FLOATS;   // 16-byte aligned: e0 is a multiple of 8
+    float* out = window + (size_t)e0 * WIN_FLOATS;   // 16-byte aligned: e0 is a multiple of 16
     for (int q = threadIdx.x; 4 * q < n_float; q += OBS_THREADS) {
         const int f = 4 * q;
         const unsigned v = *reinterpret_cast<const unsigned*>(s_out + f);   // four values, one byte each
@@ -244,17 +201,8 @@ extern "C" int maze_window(maze_ctx* ctx, const maze_env_batch* b, float* window
     if (!window) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_window: window");
     if (((uintptr_t)window & 15) || ((uintptr_t)agent_norm & 7) || ((uintptr_t)target_norm & 7))
         return maze_fail_arg(ctx, MAZE_E_ALIGN, "maze_window pointer alignment");
-    const int per_cta = OBS_THREADS / 32;
-    const int grid = (b->num_envs + per_cta - 1) / per_cta;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool unit = b->visit_cell_stride == 1;
-    if (b->visit_tiled) {
-        if (unit) maze_window_kernel<true, true><<<grid, OBS_THREADS, 0, st>>>(*b, window, agent_norm, target_norm);
-        else maze_window_kernel<true, false><<<grid, OBS_THREADS, 0, st>>>(*b, window, agent_norm, target_norm);
-    } else {
-        if (unit) maze_window_kernel<false, true><<<grid, OBS_THREADS, 0, st>>>(*b, window, agent_norm, target_norm);
-        else maze_window_kernel<false, false><<<grid, OBS_THREADS, 0, st>>>(*b, window, agent_norm, target_norm);
-    }
+    const int grid = (b->num_envs + WIN_ENVS - 1) / WIN_ENVS;
+    maze_window_kernel<<<grid, OBS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, window, agent_norm, target_norm);
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,85 @@
+// One window row of one env: the three 15-bit masks of lib/maze_handler.py:82-99 ([maze == 0, maze == 1 (goal
+// excluded), non_visited]) for window row `row` (0..14) of the 15 x 15 crop around the agent (extract_submaze :4-54
+// clamped on bordered mazes, extract_submaze_toroid :56-80 wrapped on the torus).  Bit j = window column j.
+// One lane per row: 15 table bytes and 15 visit words are loaded first, then folded into the masks in registers.
+// Shared by the bit-packed replay encode (maze_dqn.cu) and the float window of the -v1 observation (maze_obs.cu).
+#pragma once
+#include "maze_env.cuh"
+
+__device__ __forceinline__ void window_row_masks(const maze_env_batch& b, int e, const EnvState& st, const MazeView& mz, int row,
+                                                 unsigned& m0, unsigned& m1, unsigned& m2) {
+    constexpr int WIN = MAZE_WINDOW;
+    m0 = m1 = m2 = 0u;
+    const int H = mz.H, W = mz.W;
+    if (H < WIN || W < WIN || row >= WIN) return;   // no 15 x 15 crop exists (the reference cannot build one either)
+    const int start_idx = (mz.start & 0xffff) * W + (mz.start >> 16);
+    const int goal_idx = (mz.goal & 0xffff) * W + (mz.goal >> 16);
+    int r0 = st.r - WIN / 2, c0 = st.c - WIN / 2;
+    if (!mz.tor) {
+        r0 = min(max(r0, 0), H - WIN);
+        c0 = min(max(c0, 0), W - WIN);   // the reference clamps with len(maze) (maze_handler.py:21-29: square mazes only); W keeps a non-square slot in bounds
+    }
+    int rr = r0 + row;
+    if (mz.tor) rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
+    const uint8_t* trow = mz.tab + rr * W;
+    const uint16_t* vbase = b.visits + (size_t)e * b.visit_env_stride;
+    const int wt = (W + 3) >> 2;
+    if (!mz.tor && b.visit_tiled && b.visit_cell_stride == 1) {
+        // Fast path (bordered mazes, the tiled env-major visit array of the -v1 default): the row's 15 table bytes come
+        // as five aligned 32-bit words, its visit words as one 8-byte load per 4 x 4 tile the row crosses -- 10 loads per
+        // lane instead of 30, and a third of the L1 sector look-ups, which is what bounded the one-load-per-block form
+        // (ncu profiles/r02i_obs_details.txt: 10.5 sectors per request, long-scoreboard stalls).
+        const int first = rr * W + c0, off = first & 3;
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(mz.tab + (first - off));   // slots are 16-byte aligned and padded
+        const int tc0 = c0 >> 2;
+        const unsigned long long* vt = reinterpret_cast<const unsigned long long*>(vbase + ((((rr >> 2) * wt) << 4) | ((rr & 3) << 2)));
+        uint32_t tword[5];
+        unsigned long long vword[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            tword[k] = (4 * k - off < WIN) ? __ldg(tw + k) : 0u;
+            vword[k] = (tc0 + k < wt) ? vt[(size_t)(tc0 + k) * 4] : 0ull;   // tile (rr >> 2, tc0 + k): 16 entries = 4 x 8 bytes further
+        }
+        unsigned openm = 0, seen = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int jt = 4 * k + q - off;               // window column of table byte q of word k
+                if (jt >= 0 && jt < WIN) openm |= ((tword[k] >> (8 * q)) & MAZE_TAB_OPEN) << jt;
+                const int jv = 4 * (tc0 + k) + q - c0;        // window column of visit entry q of tile k
+                const unsigned v = (unsigned)(vword[k] >> (16 * q)) & 0xffffu;
+                if (jv >= 0 && jv < WIN) seen |= (((int)(v >> 8) == st.epoch && (v & 0xffu) != 0) ? 1u : 0u) << jv;
+            }
+        const unsigned all = (1u << WIN) - 1u;
+        const int gj = goal_idx - first, sj = start_idx - first;   // goal / start inside this row of the window?
+        const unsigned goal_bit = (gj >= 0 && gj < WIN) ? 1u << gj : 0u, start_bit = (sj >= 0 && sj < WIN) ? 1u << sj : 0u;
+        m0 = ~openm & all;
+        m1 = openm & ~goal_bit;
+        m2 = openm & ~start_bit & ~seen;
+        return;
+    }
+    const int vrow = b.visit_tiled ? ((((rr >> 2) * wt) << 4) | ((rr & 3) << 2)) : rr * W;
+    int tb[WIN];
+    unsigned vis[WIN];
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) {   // all loads of the row first
+        int cc = c0 + j;
+        if (mz.tor) cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
+        tb[j] = __ldg(trow + cc);
+        const int vi = b.visit_tiled ? vrow + (((cc >> 2) << 4) | (cc & 3)) : vrow + cc;
+        vis[j] = vbase[(size_t)vi * b.visit_cell_stride];
+    }
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) {
+        int cc = c0 + j;
+        if (mz.tor) cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
+        const int idx = rr * W + cc;
+        const bool open = (tb[j] & MAZE_TAB_OPEN) != 0;
+        // non_visited (base_maze_env.py:148-149,183-184): open, not the start, no visit in this episode
+        const bool fresh = open && idx != start_idx && !((int)(vis[j] >> 8) == st.epoch && (vis[j] & 0xffu) != 0);
+        m0 |= (open ? 0u : 1u) << j;
+        m1 |= ((open && idx != goal_idx) ? 1u : 0u) << j;
+        m2 |= (fresh ? 1u : 0u) << j;
+    }
+}
