@@ -68,3 +68,35 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
                 assert "/root/reference" not in src
+
+
+def test_packed_record_decoder_runs_on_the_host():
+    """maze_step_decode_host is plain C (no GPU): records built here by the documented bit layout decode to the wide arrays
+    by the reference's rules -- best dir = agent - (wrapped) neighbour, reward from the LUT the record names."""
+    from maze_b200 import cabi
+    rng = np.random.default_rng(0)
+    n, S = 5000, 21
+    r, c = rng.integers(0, S, n), rng.integers(0, S, n)
+    code = rng.integers(0, 5, n)
+    term, trunc = rng.integers(0, 2, n), rng.integers(0, 2, n)
+    kind = rng.integers(0, 4, n)
+    index = np.where(kind == 2, rng.integers(0, 3, n), np.where(kind == 3, rng.integers(0, 3, n), rng.integers(0, 256, n)))
+    rec = (r | (c << 8) | (code << cabi.REC_CODE_SHIFT) | (term << cabi.REC_TERM_SHIFT) | (trunc << cabi.REC_TRUNC_SHIFT)
+           | (kind << cabi.REC_KIND_SHIFT) | (index << cabi.REC_INDEX_SHIFT)).astype(np.uint32)
+    tor = rng.integers(0, 2, n).astype(np.uint8)
+    shape = np.full((n, 2), S, dtype=np.int32)
+    d = cabi.decode_records(rec, shape, tor)
+    np.testing.assert_array_equal(d["agent"], np.stack([r, c], 1))
+    np.testing.assert_array_equal(d["terminated"], term.astype(bool))
+    np.testing.assert_array_equal(d["truncated"], trunc.astype(bool))
+    table = cabi.reward_table()
+    np.testing.assert_array_equal(d["reward"].view(np.uint64), table[kind, index].view(np.uint64))
+    assert table[3, 0] == 0.0 and table[3, 1] == 1.0 and table[3, 2] == -1.0 and table[2, 2] == 1 * 0.5 - 0.05
+    dr, dc = np.array([1, -1, 0, 0, 0]), np.array([0, 0, 1, -1, 0])
+    nr, nc = r + dr[code], c + dc[code]
+    wrap = tor.astype(bool)
+    nr, nc = np.where(wrap, nr % S, nr), np.where(wrap, nc % S, nc)
+    np.testing.assert_array_equal(d["best_dir"], np.stack([r - nr, c - nc], 1))
+    # bordered mazes need neither shapes nor topology
+    d2 = cabi.decode_records(rec)
+    np.testing.assert_array_equal(d2["best_dir"], np.stack([-dr[code], -dc[code]], 1))

@@ -65,9 +65,12 @@ def test_reduce_is_identity_without_a_process_group():
         mdist.reduce_statistics(torch.zeros(4, dtype=torch.float64))
 
 
-def test_reference_arm_of_the_bench_runs_without_a_gpu():
+@pytest.mark.parametrize("force_port", [False, True])
+def test_reference_arm_of_the_bench_runs_without_a_gpu(force_port):
     """`bench.py --impl reference` is the CPU arm the driver runs beside ours: it must work on a box
-    without a GPU, print exactly one JSON line with the contract keys, and honour its time budget."""
+    without a GPU, print exactly one JSON line with the contract keys, and honour its time budget.  With baseline/_ref
+    present (tools/install_reference.py) it times the unmodified reference's own SimpleMazeEnv (kind "reference");
+    without it -- or with MAZE_REF_FORCE_PORT -- the oracle's port (kind "port")."""
     import json
     import os
     import subprocess
@@ -75,6 +78,10 @@ def test_reference_arm_of_the_bench_runs_without_a_gpu():
     import time
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, MAZE_REF_BUDGET_S="2")
+    if force_port:
+        env["MAZE_REF_FORCE_PORT"] = "1"
+    have_ref = os.path.isfile(os.path.join(root, "baseline", "_ref", "gymnasium_env", "envs", "simple_maze_env.py"))
+    want_kind = "reference" if have_ref and not force_port else "port"
     t0 = time.time()
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
                          capture_output=True, text=True, env=env, timeout=300)
@@ -83,7 +90,8 @@ def test_reference_arm_of_the_bench_runs_without_a_gpu():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["value"] > 0 and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert set(d["config"]) == {"workload", "envs_per_gpu", "mazes_per_gpu", "l2", "parallelism"}      # the same keys as this repo's arm
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["steps"] == 3 and d["warmup"] == 1 and d["gpu_launches"] == 0
     assert time.time() - t0 < 120
