@@ -639,7 +639,7 @@ def run_ddqn(args, rank, local_rank, world):
     device, barrier, max_over_ranks = _dist_setup(local_rank, world)
     B = args.envs_per_gpu if args.envs_per_gpu_set else 8192
     n = args.batch or B
-    loop = DDQNLoop(B, n, SHAPE[0], 1 << 20, rank, world, device)
+    loop = DDQNLoop(B, n, SHAPE[0], 1 << 20, rank, world, device, overlap=not args.no_overlap)
     sampler = ClockSampler(local_rank)
     sampler.start()
     for _ in range(max(args.warmup, (n + B - 1) // B + 2)):
@@ -666,7 +666,11 @@ def run_ddqn(args, rank, local_rank, world):
                                    "optimiser step, one optimiser step per env step, net of agents/ddqn_agent.py:18-52 (dropout off)",
                        "envs_per_gpu": B, "batch_per_gpu": n, "parallelism": f"data parallel over {world} GPU(s): envs and replay sharded, one NCCL all-reduce "
                                    "(sum) of the flat fp32 gradient (8.7 MB) per optimiser step"},
-            "samples_per_s": world * n * n_opt / (ms * 1e-3), "optimizer_steps_per_s": n_opt / (ms * 1e-3), "allreduce_share": ar_ms / ms,
+            "samples_per_s": world * n * n_opt / (ms * 1e-3), "optimizer_steps_per_s": n_opt / (ms * 1e-3),
+            "allreduce": ("separate: the whole gradient is reduced after the backward pass (timed: allreduce_share)" if args.no_overlap or world == 1 else
+                          "overlapped: grads[MAZE_NET_OFF_W1:] are reduced on a side stream while the backward-data GEMM and the conv gradient run "
+                          "(maze_dqn_backward's fc_ready_event); run with --no-overlap for the separate, timed variant"),
+            "allreduce_share": (ar_ms / ms) if (args.no_overlap and world > 1) else None,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None, "peak_source": peak_src,
                          "flop_per_step_per_gpu": loop.flop_per_iteration(),
                          "note": "whole loop per GPU (policy forward on B envs + forward on 3 n and backward on n samples per optimiser step; env step, "
@@ -704,6 +708,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--workload", default="configs1", choices=["configs1", "toroidal-regen", "curriculum-dq", "ddqn"])
     ap.add_argument("--batch", type=int, default=0, help="ddqn: replay batch per GPU per optimiser step (default: envs per GPU)")
+    ap.add_argument("--no-overlap", action="store_true", help="ddqn: all-reduce the whole gradient after the backward pass and time it (allreduce_share)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

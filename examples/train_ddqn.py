@@ -35,8 +35,8 @@ class DDQNLoop:
     """One rank's share of config 5."""
 
     def __init__(self, envs: int, batch: int, shape: int = 81, memory: int = 1 << 20, rank: int = 0, world: int = 1, device="cuda",
-                 lr: float = 1e-4, gamma: float = 0.9, target_every: int = 50, seed: int = 1):
-        self.B, self.n, self.rank, self.world = envs, batch, rank, world
+                 lr: float = 1e-4, gamma: float = 0.9, target_every: int = 50, seed: int = 1, overlap: bool = True):
+        self.B, self.n, self.rank, self.world, self.overlap = envs, batch, rank, world, overlap
         self.lr, self.gamma, self.target_every = lr, gamma, target_every
         self.device = torch.device(device)
         self.env = mb.MazeVectorEnv(envs, shape=(shape, shape), enrich=True, on_win="regenerate", algorithms="r-prim", seed=seed,
@@ -61,16 +61,20 @@ class DDQNLoop:
         self.iters += 1
         if self.iters * self.B >= self.n:                              # len(memory) >= batch_size, without a device sync
             batch = mem.sample_packed(self.n)
-            net.backward(*batch, gamma=self.gamma)
-            if self.world > 1:
-                if time_allreduce:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                dist.all_reduce(net.grads)                             # the DQN gradient all-reduce: 8.7 MB of fp32
-                if time_allreduce:
-                    e1.record()
-                    self.ar_events.append((e0, e1))
-            net.adamw(self.lr, grad_scale=1.0 / self.world)
+            if self.world > 1 and self.overlap:
+                # the fc gradients are all-reduced on a side stream while the tail of the backward pass still runs
+                net.train_step_overlapped(*batch, gamma=self.gamma, lr=self.lr, world=self.world)
+            else:
+                net.backward(*batch, gamma=self.gamma)
+                if self.world > 1:
+                    if time_allreduce:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    dist.all_reduce(net.grads)                         # the DQN gradient all-reduce: 8.7 MB of fp32
+                    if time_allreduce:
+                        e1.record()
+                        self.ar_events.append((e0, e1))
+                net.adamw(self.lr, grad_scale=1.0 / self.world)
             self.opt_steps += 1
         if self.iters % self.target_every == 0:
             net.update_target()
@@ -87,13 +91,14 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="replay batch per GPU per optimiser step")
     ap.add_argument("--shape", type=int, default=81)
     ap.add_argument("--memory", type=int, default=1 << 20)
+    ap.add_argument("--no-overlap", action="store_true", help="all-reduce the whole gradient after the backward pass (and time it)")
     args = ap.parse_args()
     rank, local, world = mb.dist.env_from_torchrun()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    loop = DDQNLoop(args.envs, args.batch, args.shape, args.memory, rank, world, device)
+    loop = DDQNLoop(args.envs, args.batch, args.shape, args.memory, rank, world, device, overlap=not args.no_overlap)
     warmup = max(5, min(20, args.iters // 4))
     for _ in range(warmup):
         loop.iterate()

@@ -449,10 +449,13 @@ int maze_dqn_features(maze_ctx* ctx, const maze_dqn_net* net, int which, const f
 
 /* optimize_model up to loss.backward() (ddqn_agent.py:113-144) on a batch of n transitions (n a multiple of 8):
  * adds d loss / d params into net->grads (so that ranks can be summed before the optimiser runs), writes the loss
- * to net->loss and, if qsa_out is not NULL, q(s, a) [n].  action [n] uint8, reward [n] float32. */
+ * to net->loss and, if qsa_out is not NULL, q(s, a) [n].  action [n] uint8, reward [n] float32.
+ * fc_ready_event (optional cudaEvent_t): recorded on `stream` once every gradient except the conv layer's -- the flat
+ * buffer from MAZE_NET_OFF_W1 on, 99.96 % of it -- is complete, so that a gradient all-reduce can overlap the rest of
+ * the backward pass (the backward-data GEMM into the conv features and the conv weight gradient). */
 int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const float* vec, const uint32_t* win, const float* next_vec,
                       const uint32_t* next_win, const uint8_t* action, const float* reward, int n, float gamma,
-                      float* qsa_out, void* stream);
+                      float* qsa_out, void* fc_ready_event, void* stream);
 
 /* param.grad.clamp_(-clamp, clamp) (ddqn_agent.py:146-147; clamp <= 0 disables) on grads * grad_scale, then one
  * torch.optim.AdamW step (`step` counts from 1), then zeroes the gradient accumulators and refreshes the source

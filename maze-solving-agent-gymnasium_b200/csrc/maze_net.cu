@@ -40,6 +40,7 @@ struct GemmArgs {
     const bf16* aux;      // forward activation [M, ldaux]     (EPI_MASK: derivative of `act` taken at it)
     int ldaux;
     int act;
+    int splits;           // CTAs along K per output tile (EPI_RED_F32)
 };
 
 template <int BN>
@@ -61,18 +62,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr uint32_t ACC_COLS = 2 * BN;   // two accumulator stages: the epilogue of tile i overlaps the main loop of tile i + 1
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bars[2 * STAGES + 1];
+    __shared__ uint64_t bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_slot;
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms are 1024-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; tile t = (split, n block, m block) with the m block
+    // fastest, so CTAs that run side by side share their B (weight) tile in L2.
+    const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN, splits = g.splits;
+    const int num_tiles = tiles_m * tiles_n * splits;
     const int nkb_total = (g.K + BK - 1) / BK;
-    const int kb_begin = (int)((long long)nkb_total * blockIdx.z / gridDim.z);
-    const int kb_end = (int)((long long)nkb_total * (blockIdx.z + 1) / gridDim.z);
-    const int nkb = kb_end - kb_begin;
-    if (nkb <= 0) return;   // uniform over the CTA (the launcher never asks for more splits than k-blocks)
-    const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[STAGES]), accum_bar = tc::smem_u32(&bars[2 * STAGES]);
+    const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[STAGES]);
+    const uint32_t acc_full0 = tc::smem_u32(&bars[2 * STAGES]), acc_empty0 = tc::smem_u32(&bars[2 * STAGES + 2]);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
@@ -81,11 +83,14 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc::mbar_init(full0 + 8 * s, 1);
             tc::mbar_init(empty0 + 8 * s, 1);
         }
-        tc::mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(acc_full0 + 8 * a, 1);    // one tcgen05.commit
+            tc::mbar_init(acc_empty0 + 8 * a, 4);   // one arrival per epilogue warp
+        }
         tc::mbar_fence_init();
     }
     if (warp == 1) {
-        tc::tmem_alloc(tc::smem_u32(&tmem_slot), BN);
+        tc::tmem_alloc(tc::smem_u32(&tmem_slot), ACC_COLS);
         tc::tmem_relinquish();
     }
     tc::tc_fence_before();
@@ -93,115 +98,146 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
+    auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& nkb) {
+        const int mb = t % tiles_m, rest = t / tiles_m;
+        const int nb = rest % tiles_n, sp = rest / tiles_n;
+        m0 = mb * BM;
+        n0 = nb * BN;
+        kb_begin = (int)((long long)nkb_total * sp / splits);
+        nkb = (int)((long long)nkb_total * (sp + 1) / splits) - kb_begin;   // >= 1: the launcher keeps splits <= k-blocks
+    };
+
     if (warp == 0) {
         if (lane == 0) {   // TMA producer
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                tc::mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                tc::mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
-                const uint32_t a_dst = base + (uint32_t)s * Cfg::STAGE_BYTES;
-                if constexpr (!MN) {
-                    tc::tma_load_2d(a_dst, &tmA, full0 + 8 * s, (kb_begin + i) * BK, m0);
-                    tc::tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full0 + 8 * s, (kb_begin + i) * BK, n0);
-                } else {
+            uint32_t it = 0;   // k-block counter over all tiles of this CTA: ring position and phase
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m0, n0, kb_begin, nkb;
+                tile_coords(t, m0, n0, kb_begin, nkb);
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    tc::mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    tc::mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
+                    const uint32_t a_dst = base + s * Cfg::STAGE_BYTES;
+                    if constexpr (!MN) {
+                        tc::tma_load_2d(a_dst, &tmA, full0 + 8 * s, (kb_begin + i) * BK, m0);
+                        tc::tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full0 + 8 * s, (kb_begin + i) * BK, n0);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < BM / 64; ++j) tc::tma_load_2d(a_dst + j * 8192, &tmA, full0 + 8 * s, m0 + 64 * j, (kb_begin + i) * BK);
+                        for (int j = 0; j < BM / 64; ++j) tc::tma_load_2d(a_dst + j * 8192, &tmA, full0 + 8 * s, m0 + 64 * j, (kb_begin + i) * BK);
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tc::tma_load_2d(a_dst + Cfg::A_BYTES + j * 8192, &tmB, full0 + 8 * s, n0 + 64 * j, (kb_begin + i) * BK);
+                        for (int j = 0; j < BN / 64; ++j)
+                            tc::tma_load_2d(a_dst + Cfg::A_BYTES + j * 8192, &tmB, full0 + 8 * s, n0 + 64 * j, (kb_begin + i) * BK);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {   // MMA issuer
             constexpr uint32_t idesc = tc::idesc_bf16(BM, BN) | (MN ? (1u << 15) | (1u << 16) : 0u);   // bits 15 / 16: A / B are MN-major
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                tc::mbar_wait(full0 + 8 * s, ph);
+            uint32_t it = 0, local = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+                int m0, n0, kb_begin, nkb;
+                tile_coords(t, m0, n0, kb_begin, nkb);
+                const uint32_t acc = local & 1u;
+                tc::mbar_wait(acc_empty0 + 8 * acc, ((local >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator stage
                 tc::tc_fence_after();
-                const uint32_t a_addr = base + (uint32_t)s * Cfg::STAGE_BYTES;
-                const uint64_t da = tc::smem_desc(a_addr, MN ? 8192 : 0, 1024, tc::SWIZZLE_128B);
-                const uint64_t db = tc::smem_desc(a_addr + Cfg::A_BYTES, MN ? 8192 : 0, 1024, tc::SWIZZLE_128B);
-                // next UMMA (K = 16): K-major 32 bytes further inside the 128-byte swizzle row, MN-major 16 rows = 2048 bytes further
-                constexpr uint32_t kstep = MN ? (2048u >> 4) : (32u >> 4);
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    tc::mbar_wait(full0 + 8 * s, ph);
+                    tc::tc_fence_after();
+                    const uint32_t a_addr = base + s * Cfg::STAGE_BYTES;
+                    const uint64_t da = tc::smem_desc(a_addr, MN ? 8192 : 0, 1024, tc::SWIZZLE_128B);
+                    const uint64_t db = tc::smem_desc(a_addr + Cfg::A_BYTES, MN ? 8192 : 0, 1024, tc::SWIZZLE_128B);
+                    // next UMMA (K = 16): K-major 32 bytes further inside the 128-byte swizzle row, MN-major 16 rows = 2048 bytes further
+                    constexpr uint32_t kstep = MN ? (2048u >> 4) : (32u >> 4);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                    tc::umma_bf16(tmem_base, da + kstep * k, db + kstep * k, idesc, (uint32_t)((i | k) != 0));
-                tc::umma_commit(empty0 + 8 * s);   // frees the stage once these MMAs have read it
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc::umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, (uint32_t)((i | k) != 0));
+                    tc::umma_commit(empty0 + 8 * s);   // frees the stage once these MMAs have read it
+                }
+                tc::umma_commit(acc_full0 + 8 * acc);
             }
-            tc::umma_commit(accum_bar);
         }
     } else {   // epilogue: warp w may read TMEM lanes 32 (w % 4) .. + 31
         const int q = warp & 3;
-        tc::mbar_wait(accum_bar, 0);
-        tc::tc_fence_after();
-        const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < g.M;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (n0 + c0 >= g.N) break;
-            uint32_t v[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tc::tmem_ld_wait();
-            const int col0 = n0 + c0;
-            if constexpr (EPI == EPI_RED_F32) {
-                float* dst = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col0;
+        uint32_t local = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+            int m0, n0, kb_begin, nkb;
+            tile_coords(t, m0, n0, kb_begin, nkb);
+            const uint32_t acc = local & 1u;
+            tc::mbar_wait(acc_full0 + 8 * acc, (local >> 1) & 1u);
+            tc::tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < g.M;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= g.N) break;
+                uint32_t v[32];
+                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, v);
+                tc::tmem_ld_wait();
+                const int col0 = n0 + c0;
+                if constexpr (EPI == EPI_RED_F32) {
+                    float* dst = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (row_ok && col0 + j + 4 <= g.N)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
-                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                                     : "memory");
-                }
-            } else {
-                uint32_t packed[16];
-                if constexpr (EPI == EPI_BIAS_ACT) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
-                        if (g.bias) {
-                            x0 += col0 + j < g.N ? __ldg(g.bias + col0 + j) : 0.f;
-                            x1 += col0 + j + 1 < g.N ? __ldg(g.bias + col0 + j + 1) : 0.f;
-                        }
-                        if (g.act == ACT_LRELU) {
-                            x0 = x0 > 0.f ? x0 : LRELU_SLOPE * x0;
-                            x1 = x1 > 0.f ? x1 : LRELU_SLOPE * x1;
-                        } else if (g.act == ACT_RELU) {
-                            x0 = fmaxf(x0, 0.f);
-                            x1 = fmaxf(x1, 0.f);
-                        }
-                        packed[j >> 1] = tc::pack_bf16x2(x0, x1);
+                    for (int j = 0; j < 32; j += 4) {
+                        if (row_ok && col0 + j + 4 <= g.N)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                         : "memory");
                     }
-                } else {   // EPI_MASK: dL/d(pre-activation) = dL/d(activation) * act'(pre), sign taken from the stored activation
-                    const bf16* arow = g.aux + (size_t)row * g.ldaux + col0;
-                    const float neg = g.act == ACT_LRELU ? LRELU_SLOPE : 0.f;
+                } else {
+                    uint32_t packed[16];
+                    if constexpr (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
+                            if (g.bias) {
+                                x0 += col0 + j < g.N ? __ldg(g.bias + col0 + j) : 0.f;
+                                x1 += col0 + j + 1 < g.N ? __ldg(g.bias + col0 + j + 1) : 0.f;
+                            }
+                            if (g.act == ACT_LRELU) {
+                                x0 = x0 > 0.f ? x0 : LRELU_SLOPE * x0;
+                                x1 = x1 > 0.f ? x1 : LRELU_SLOPE * x1;
+                            } else if (g.act == ACT_RELU) {
+                                x0 = fmaxf(x0, 0.f);
+                                x1 = fmaxf(x1, 0.f);
+                            }
+                            packed[j >> 1] = tc::pack_bf16x2(x0, x1);
+                        }
+                    } else {   // EPI_MASK: dL/d(pre-activation) = dL/d(activation) * act'(pre), sign taken from the stored activation
+                        const bf16* arow = g.aux + (size_t)row * g.ldaux + col0;
+                        const float neg = g.act == ACT_LRELU ? LRELU_SLOPE : 0.f;
+#pragma unroll
+                        for (int j8 = 0; j8 < 32; j8 += 8) {
+                            uint4 h = make_uint4(0, 0, 0, 0);
+                            if (row_ok && col0 + j8 + 8 <= g.N) h = __ldg(reinterpret_cast<const uint4*>(arow + j8));
+                            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                // bf16 sign/zero test on the raw bits: > 0 <=> sign clear and magnitude non-zero
+                                const uint32_t lo = hw[u] & 0xffffu, hi = hw[u] >> 16;
+                                const float f0 = (lo != 0 && lo < 0x8000u) ? 1.f : neg, f1 = (hi != 0 && hi < 0x8000u) ? 1.f : neg;
+                                packed[(j8 >> 1) + u] = tc::pack_bf16x2(__uint_as_float(v[j8 + 2 * u]) * f0, __uint_as_float(v[j8 + 2 * u + 1]) * f1);
+                            }
+                        }
+                    }
+                    bf16* dst = reinterpret_cast<bf16*>(g.C) + (size_t)row * g.ldc + col0;
 #pragma unroll
                     for (int j8 = 0; j8 < 32; j8 += 8) {
-                        uint4 h = make_uint4(0, 0, 0, 0);
-                        if (row_ok && col0 + j8 + 8 <= g.N) h = __ldg(reinterpret_cast<const uint4*>(arow + j8));
-                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            // bf16 sign/zero test on the raw bits: > 0 <=> sign clear and magnitude non-zero
-                            const uint32_t lo = hw[t] & 0xffffu, hi = hw[t] >> 16;
-                            const float f0 = (lo != 0 && lo < 0x8000u) ? 1.f : neg, f1 = (hi != 0 && hi < 0x8000u) ? 1.f : neg;
-                            packed[(j8 >> 1) + t] = tc::pack_bf16x2(__uint_as_float(v[j8 + 2 * t]) * f0, __uint_as_float(v[j8 + 2 * t + 1]) * f1);
-                        }
+                        if (row_ok && col0 + j8 + 8 <= g.N)
+                            *reinterpret_cast<uint4*>(dst + j8) = make_uint4(packed[j8 >> 1], packed[(j8 >> 1) + 1], packed[(j8 >> 1) + 2], packed[(j8 >> 1) + 3]);
                     }
                 }
-                bf16* dst = reinterpret_cast<bf16*>(g.C) + (size_t)row * g.ldc + col0;
-#pragma unroll
-                for (int j8 = 0; j8 < 32; j8 += 8) {
-                    if (row_ok && col0 + j8 + 8 <= g.N)
-                        *reinterpret_cast<uint4*>(dst + j8) = make_uint4(packed[j8 >> 1], packed[(j8 >> 1) + 1], packed[(j8 >> 1) + 2], packed[(j8 >> 1) + 3]);
-                }
             }
+            // every value of this accumulator stage is in registers: hand the stage back to the MMA issuer
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty0 + 8 * acc);
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, ACC_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -253,8 +289,11 @@ int launch_gemm_t(maze_ctx* ctx, const bf16* A, int lda, const bf16* B, int ldb,
     const int nkb = (g.K + BK - 1) / BK;
     if (splits < 1) splits = 1;
     if (splits > nkb) splits = nkb;
-    const dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
-    net_gemm_kernel<BN, EPI, MN><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, st>>>(ta, tb, g);
+    GemmArgs ga = g;
+    ga.splits = splits;
+    const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * splits;
+    const int grid = num_tiles < ctx->num_sms ? num_tiles : ctx->num_sms;   // persistent: one CTA per SM walks the tiles
+    net_gemm_kernel<BN, EPI, MN><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, st>>>(ta, tb, ga);
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1053,7 +1092,7 @@ extern "C" int maze_dqn_forward(maze_ctx* ctx, const maze_dqn_net* net, int whic
 
 extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const float* vec, const uint32_t* win, const float* next_vec,
                                  const uint32_t* next_win, const uint8_t* action, const float* reward, int n, float gamma, float* qsa_out,
-                                 void* stream) {
+                                 void* fc_ready_event, void* stream) {
     if (!ctx) return MAZE_E_NULL;
     if (int rc = check_net(ctx, net, true)) return rc;
     if (!vec || !win || !next_vec || !next_win || !action || !reward) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_backward pointer");
@@ -1105,6 +1144,9 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
     g = GemmArgs{};
     g.M = NET_H1; g.N = NET_IN; g.K = n; g.C = gr + MAZE_NET_OFF_W1; g.ldc = NET_IN;
     if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh1, NET_H1, w.X, NET_IN, g, splits, st, true)) return rc;
+    // every gradient but the conv layer's (the first MAZE_NET_OFF_W1 floats of the flat buffer) is complete here: a caller
+    // that all-reduces gradients can start on grads[MAZE_NET_OFF_W1:] while the backward-data GEMM and the conv gradient run
+    if (fc_ready_event) MAZE_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(fc_ready_event), st));
     g = GemmArgs{};
     g.M = n; g.N = NET_CONV_OUT; g.K = NET_H1; g.C = w.dX; g.ldc = NET_IN; g.act = ACT_NONE;
     if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, 256, w.dh1, NET_H1, w1t, NET_H1, g, 1, st)) return rc;

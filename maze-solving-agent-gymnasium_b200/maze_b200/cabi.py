@@ -131,7 +131,7 @@ SIGNATURES = {
     "maze_dqn_forward": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "maze_dqn_features": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
-    "maze_dqn_backward": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet)] + [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "maze_dqn_backward": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet)] + [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maze_dqn_adamw": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet)] + [C.c_float] * 5 + [C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "maze_dqn_sample_packed": (C.c_int, [C.c_void_p, C.POINTER(MazeReplay), C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 7),
     "maze_dqn_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -127,12 +127,15 @@ class DQNNet:
         self.ctx.check(rc, "maze_dqn_features")
         return (X, idx) if save_idx else X
 
-    def backward(self, vec, win, next_vec, next_win, action, reward, gamma: float, qsa_out: torch.Tensor | None = None):
-        """Accumulate d loss / d params into self.grads; the loss lands in self.loss (no sync)."""
+    def backward(self, vec, win, next_vec, next_win, action, reward, gamma: float, qsa_out: torch.Tensor | None = None,
+                 fc_ready: torch.cuda.Event | None = None):
+        """Accumulate d loss / d params into self.grads; the loss lands in self.loss (no sync).  fc_ready: an event that
+        is recorded as soon as self.grads[NET_OFF_W1:] (everything but the conv layer) is final."""
         n = vec.shape[0]
+        ev = None if fc_ready is None else C.c_void_p(fc_ready.cuda_event)
         rc = cabi.lib().maze_dqn_backward(self.ctx.handle, C.byref(self._c), cabi.ptr(vec), cabi.ptr(win), cabi.ptr(next_vec),
                                           cabi.ptr(next_win), cabi.ptr(action), cabi.ptr(reward), n, float(gamma), cabi.ptr(qsa_out),
-                                          cabi.current_stream(self.device))
+                                          ev, cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_dqn_backward")
         return self.loss
 
@@ -149,6 +152,26 @@ class DQNNet:
         self.backward(vec, win, next_vec, next_win, action, reward, gamma)
         if all_reduce is not None and world > 1:
             all_reduce(self.grads)
+        self.adamw(lr, grad_scale=1.0 / world, **adam)
+        return self.loss
+
+    def train_step_overlapped(self, vec, win, next_vec, next_win, action, reward, gamma: float, lr: float, world: int, group=None, **adam):
+        """train_step for world > 1 with the gradient all-reduce hidden behind the tail of the backward pass: the fc
+        gradients (99.96 % of the buffer) are reduced on a side stream from the moment they are final, while the
+        backward-data GEMM and the conv weight gradient still run; the 896 conv floats follow at the end."""
+        import torch.distributed as dist
+        if getattr(self, "_fc_ready", None) is None:
+            self._fc_ready = torch.cuda.Event()
+            self._fc_ready.record(torch.cuda.current_stream(self.device))    # materialises the cudaEvent_t
+            self._side = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        self.backward(vec, win, next_vec, next_win, action, reward, gamma, fc_ready=self._fc_ready)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._fc_ready)
+            work = dist.all_reduce(self.grads[cabi.NET_OFF_W1:], group=group, async_op=True)
+        dist.all_reduce(self.grads[:cabi.NET_OFF_W1], group=group)
+        work.wait()                       # the current (main) stream waits for the side all-reduce; the host does not
+        main.wait_stream(self._side)
         self.adamw(lr, grad_scale=1.0 / world, **adam)
         return self.loss
 
