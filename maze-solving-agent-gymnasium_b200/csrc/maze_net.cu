@@ -479,14 +479,34 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
 constexpr int HEAD_THREADS = 256;
 constexpr int NET_H2 = 512, NET_H1 = 1024;
 
+// A warp owns one sample; lane l holds the 16 columns  k * 128 + 4 l + j  (k, j = 0..3) of its 512-wide rows: global
+// loads are 8 bytes per lane and 256 contiguous bytes per warp, shared-memory weight reads are float4 at a 16-byte lane
+// stride (conflict-free; the first version's 16 consecutive columns per lane made every weight read a 16-way bank
+// conflict: ncu profiles r02n, 4.6 M conflicts, short-scoreboard stalls).
+__device__ __forceinline__ int head_col(int lane, int i) { return (i >> 2) * 128 + lane * 4 + (i & 3); }
+
 __device__ __forceinline__ void head_load16(const bf16* row, int lane, float (&h)[16]) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(row + lane * 16)), b = __ldg(reinterpret_cast<const uint4*>(row + lane * 16 + 8));
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        h[2 * i] = __uint_as_float(w[i] << 16);
-        h[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    for (int k = 0; k < 4; ++k) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(row + k * 128 + lane * 4));
+        h[4 * k + 0] = __uint_as_float(w.x << 16);
+        h[4 * k + 1] = __uint_as_float(w.x & 0xffff0000u);
+        h[4 * k + 2] = __uint_as_float(w.y << 16);
+        h[4 * k + 3] = __uint_as_float(w.y & 0xffff0000u);
     }
+}
+
+__device__ __forceinline__ float head_dot(const float (&h)[16], const float* w_row, int lane) {   // w_row: 512 floats in shared memory
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(w_row + k * 128 + lane * 4);
+        acc = fmaf(h[4 * k + 0], w.x, acc);
+        acc = fmaf(h[4 * k + 1], w.y, acc);
+        acc = fmaf(h[4 * k + 2], w.z, acc);
+        acc = fmaf(h[4 * k + 3], w.w, acc);
+    }
+    return acc;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -497,20 +517,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __global__ void __launch_bounds__(HEAD_THREADS)
 net_head_q_kernel(const bf16* __restrict__ h2, int n, const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ q) {
-    __shared__ float sw[4 * NET_H2];
+    __shared__ __align__(16) float sw[4 * NET_H2];
     for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS) sw[i] = w3[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     for (int s = blockIdx.x * (HEAD_THREADS / 32) + (threadIdx.x >> 5); s < n; s += gridDim.x * (HEAD_THREADS / 32)) {
         float h[16];
         head_load16(h2 + (size_t)s * NET_H2, lane, h);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[a] = fmaf(h[i], sw[a * NET_H2 + lane * 16 + i], acc[a]);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) acc[a] = warp_sum(acc[a]);
+        for (int a = 0; a < 4; ++a) acc[a] = warp_sum(head_dot(h, sw + a * NET_H2, lane));
         if (lane < 4) q[(size_t)s * 4 + lane] = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + b3[lane];
     }
 }
@@ -523,7 +539,7 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
                      const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ tw3, const float* __restrict__ tb3,
                      const uint8_t* __restrict__ action, const float* __restrict__ reward, float gamma, bf16* __restrict__ dh2,
                      float* __restrict__ gw3, float* __restrict__ gb3, float* __restrict__ loss, float* __restrict__ qsa_out) {
-    __shared__ float sw[4 * NET_H2], stw[4 * NET_H2], sgw[4 * NET_H2];
+    __shared__ __align__(16) float sw[4 * NET_H2], stw[4 * NET_H2], sgw[4 * NET_H2];
     __shared__ float sgb[4], sloss;
     for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS) {
         sw[i] = w3[i];
@@ -546,39 +562,38 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
         head_load16(h2_s + (size_t)s * NET_H2, lane, h);
         head_load16(h2_sn + (size_t)s * NET_H2, lane, hn);
         head_load16(h2_tn + (size_t)s * NET_H2, lane, ht);
+        const int act = action[s] & 3;
+        const float rew = reward[s];
         float qs[4], qn[4], qt[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            float x = 0.f, y = 0.f, z = 0.f;
+            qs[a] = head_dot(h, sw + a * NET_H2, lane);
+            qn[a] = head_dot(hn, sw + a * NET_H2, lane);
+            qt[a] = head_dot(ht, stw + a * NET_H2, lane);
+        }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                x = fmaf(h[i], sw[a * NET_H2 + lane * 16 + i], x);
-                y = fmaf(hn[i], sw[a * NET_H2 + lane * 16 + i], y);
-                z = fmaf(ht[i], stw[a * NET_H2 + lane * 16 + i], z);
-            }
-            qs[a] = warp_sum(x) + b3[a];
-            qn[a] = warp_sum(y) + b3[a];
-            qt[a] = warp_sum(z) + tb3[a];
+        for (int a = 0; a < 4; ++a) {   // twelve independent butterfly reductions, interleaved by the compiler
+            qs[a] = warp_sum(qs[a]) + b3[a];
+            qn[a] = warp_sum(qn[a]) + b3[a];
+            qt[a] = warp_sum(qt[a]) + tb3[a];
         }
         int best = 0;   // .max(1)[1]: first maximum
 #pragma unroll
         for (int a = 1; a < 4; ++a)
             if (qn[a] > qn[best]) best = a;
-        const int act = action[s] & 3;
         const float qsa = act == 0 ? qs[0] : act == 1 ? qs[1] : act == 2 ? qs[2] : qs[3];
         const float qtb = best == 0 ? qt[0] : best == 1 ? qt[1] : best == 2 ? qt[2] : qt[3];
-        const float target = qtb * gamma + reward[s];
+        const float target = qtb * gamma + rew;
         const float d = qsa - target;
         const float gq = 2.f * d * inv_n;   // d mean((q - y)^2) / d q
-        uint32_t out[8];
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-            const float w0 = sw[act * NET_H2 + lane * 16 + i], w1 = sw[act * NET_H2 + lane * 16 + i + 1];
-            out[i >> 1] = tc::pack_bf16x2(h[i] > 0.f ? gq * w0 : 0.f, h[i + 1] > 0.f ? gq * w1 : 0.f);   // ReLU'
+        for (int k = 0; k < 4; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(sw + act * NET_H2 + k * 128 + lane * 4);
+            uint2 out;   // ReLU'
+            out.x = tc::pack_bf16x2(h[4 * k + 0] > 0.f ? gq * w.x : 0.f, h[4 * k + 1] > 0.f ? gq * w.y : 0.f);
+            out.y = tc::pack_bf16x2(h[4 * k + 2] > 0.f ? gq * w.z : 0.f, h[4 * k + 3] > 0.f ? gq * w.w : 0.f);
+            *reinterpret_cast<uint2*>(dh2 + (size_t)s * NET_H2 + k * 128 + lane * 4) = out;
         }
-        uint4* dst = reinterpret_cast<uint4*>(dh2 + (size_t)s * NET_H2 + lane * 16);
-        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
             if (act == a) {
@@ -595,7 +610,7 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (gacc[a][i] != 0.f) atomicAdd(&sgw[a * NET_H2 + lane * 16 + i], gacc[a][i]);
+            if (gacc[a][i] != 0.f) atomicAdd(&sgw[a * NET_H2 + head_col(lane, i)], gacc[a][i]);
     if (lane < 4 && gb_acc != 0.f) atomicAdd(&sgb[lane], gb_acc);
     if (lane == 0) atomicAdd(&sloss, loss_acc);
     __syncthreads();
@@ -734,15 +749,22 @@ net_conv_bwd_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ poo
 // lives in TMEM lane 32 (r / 16) + r % 16).
 constexpr int CB_THREADS = 256;
 constexpr uint32_t CB_A_BYTES = 64 * 256 * 2, CB_B_BYTES = 32 * 256 * 2;
-constexpr size_t CB_SMEM = CB_A_BYTES + CB_B_BYTES + 128;   // 48 KB: four CTAs per SM overlap each other's build / MMA phases
+constexpr size_t CB_SMEM = CB_A_BYTES + CB_B_BYTES + 128;   // 48 KB (+ 9 KB static staging): three CTAs per SM overlap each other's build / MMA phases
 constexpr int CB_B_UNITS = 27 * 28;                          // (tap, window row 0..13, half row)
 
-__global__ void __launch_bounds__(CB_THREADS, 4)
+__global__ void __launch_bounds__(CB_THREADS, 3)
 net_conv_bwd_tc_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ pool_idx, const uint32_t* __restrict__ win, int n,
                        float* __restrict__ gconv_w, float* __restrict__ gconv_b) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
+    // One sample's gradient row (1 568 bf16) and pool choices (1 568 bytes), double-buffered: fetched from global memory
+    // with coalesced 16-byte loads one sample ahead.  Reading them straight from global with this kernel's (channel,
+    // pooled position) thread mapping made every 1- and 2-byte load touch 32 sectors -- L1 tag look-ups, not bytes,
+    // bounded the first version (87 us per 8 192 samples, profiles/r02m_net_launches_summary.txt).
+    __shared__ __align__(16) bf16 s_g[2][NET_CONV_OUT];
+    __shared__ __align__(16) uint8_t s_i[2][NET_CONV_OUT];
+    __shared__ uint32_t s_w[2][MAZE_WINDOW_WORDS];   // and its packed window
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* const A = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);
     uint8_t* const B = A + CB_A_BYTES;
@@ -781,15 +803,39 @@ net_conv_bwd_tc_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ 
         b_sh8[j] = 8 * h + dx;
         b_off[j] = u < CB_B_UNITS ? (uint32_t)yh * 512u + (uint32_t)((kk >> 3) * 128 + (kk & 7) * 16) : 0xffffffffu;
     }
+    auto fetch = [&](int smp, uint4& gq, uint4& iq, uint32_t& wq) {   // this thread's share of the sample's gradient row / pool choices / window
+        gq = iq = make_uint4(0, 0, 0, 0);
+        wq = 0;
+        if (smp < n) {
+            if (tid < NET_CONV_OUT / 8) gq = __ldg(reinterpret_cast<const uint4*>(dX + (size_t)smp * NET_IN) + tid);
+            if (tid < NET_CONV_OUT / 16) iq = __ldg(reinterpret_cast<const uint4*>(pool_idx + (size_t)smp * NET_CONV_OUT) + tid);
+            if (tid >= 224 && tid < 224 + MAZE_WINDOW_WORDS) wq = __ldg(win + (size_t)smp * MAZE_WINDOW_WORDS + (tid - 224));
+        }
+    };
+    auto stash = [&](int buf, const uint4& gq, const uint4& iq, uint32_t wq) {
+        if (tid < NET_CONV_OUT / 8) reinterpret_cast<uint4*>(s_g[buf])[tid] = gq;
+        if (tid < NET_CONV_OUT / 16) reinterpret_cast<uint4*>(s_i[buf])[tid] = iq;
+        if (tid >= 224 && tid < 224 + MAZE_WINDOW_WORDS) s_w[buf][tid - 224] = wq;
+    };
+    {
+        uint4 gq, iq;
+        uint32_t wq;
+        fetch(blockIdx.x, gq, iq, wq);
+        stash(0, gq, iq, wq);
+    }
+    __syncthreads();
     uint32_t it = 0;
     for (int s = blockIdx.x; s < n; s += gridDim.x, ++it) {
-        // global loads first (they do not touch the operand buffers the previous sample's MMAs may still be reading)
+        const int buf = (int)(it & 1u);
+        uint4 next_g, next_i;
+        uint32_t next_w;
+        fetch(s + (int)gridDim.x, next_g, next_i, next_w);   // in flight while this sample is built
+        // everything that does not touch the operand buffers (the previous sample's MMAs may still be reading them) first
         uint32_t bits8[3];
-        const uint32_t* words = win + (size_t)s * MAZE_WINDOW_WORDS;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             bits8[j] = 0;
-            if (b_on[j]) bits8[j] = (((((__ldg(words + b_word[j]) >> b_shift[j]) & 0x7fffu) << 1) >> b_sh8[j])) & 0xffu;
+            if (b_on[j]) bits8[j] = (((((s_w[buf][b_word[j]] >> b_shift[j]) & 0x7fffu) << 1) >> b_sh8[j])) & 0xffu;
         }
         uint32_t top[2][4], bot[2][4];
 #pragma unroll
@@ -800,9 +846,9 @@ net_conv_bwd_tc_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ 
             for (int j = 0; j < 4; ++j) {
                 uint32_t word = 0, b = 0;
                 if (u < 14 && 4 * h + j < 7) {
-                    const size_t at = (size_t)o * 49 + py * 7 + 4 * h + j;
-                    b = pool_idx[(size_t)s * NET_CONV_OUT + at];
-                    float gv = __bfloat162float(dX[(size_t)s * NET_IN + at]);
+                    const int at = o * 49 + py * 7 + 4 * h + j;
+                    b = s_i[buf][at];
+                    float gv = __bfloat162float(s_g[buf][at]);
                     if (!(b & 4u)) gv *= LRELU_SLOPE;
                     const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(gv));
                     word = (b & 1u) ? hb << 16 : hb;       // columns 2 px and 2 px + 1 share a word
@@ -833,6 +879,7 @@ net_conv_bwd_tc_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ 
                 *reinterpret_cast<uint4*>(B + b_off[j]) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
+        stash(buf ^ 1, next_g, next_i, next_w);   // the other stage: its last readers passed the barrier of the previous iteration
         tc::fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -1157,7 +1204,7 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
         MAZE_CHECK(cudaGetLastError());
     } else {
         MAZE_CHECK(cudaFuncSetAttribute(net_conv_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
-        const int grid = n < ctx->num_sms * 4 ? n : ctx->num_sms * 4;
+        const int grid = n < ctx->num_sms * 3 ? n : ctx->num_sms * 3;   // 48 KB of operands + 9 KB of staging per CTA: three fit an SM
         net_conv_bwd_tc_kernel<<<grid, CB_THREADS, CB_SMEM, st>>>(w.dX, w.idx, win, n, gr + MAZE_NET_OFF_CONV_W, gr + MAZE_NET_OFF_CONV_B);
         MAZE_CHECK(cudaGetLastError());
     }
