@@ -407,6 +407,18 @@ def run_ours(args, rank, local_rank, world):
 
     e2e_wide, d2h_wide, (obs, rew, term, trunc, _) = time_e2e(env.step_host)
     e2e_packed, d2h_packed, records = time_e2e(env.step_host_packed)
+
+    # The floor of that path on this box: the same bytes over PCIe with no kernel in between (4 MB in, 16 MB out per step
+    # and rank, all ranks at once).  e2e.value close to this number means the step is bound by the host link, not the GPU.
+    pin_out = torch.empty(B, dtype=torch.int32, pin_memory=True)
+    d_in = torch.empty(B, dtype=torch.uint8, device=device)
+
+    def copies_only(actions):
+        d_in.copy_(actions, non_blocking=True)
+        pin_out.copy_(env.batch.packed, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        return None
+    transfer_only, _, _ = time_e2e(copies_only)
     # the records decode to exactly what the wide path returns: one more step taken with both outputs switched on,
     # decoded record against the device's wide buffers
     t0 = time.perf_counter()
@@ -466,6 +478,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_packed, "unit": UNIT, "wire": "packed", "h2d_bytes_per_step": env.h2d_bytes_per_step(),
                     "d2h_bytes_per_step": d2h_packed, "steps": e2e_steps,
                     "wide": {"value": e2e_wide, "d2h_bytes_per_step": d2h_wide},
+                    "transfer_only_value": transfer_only,
                     "host_decode_s_per_step": decode_s,
                     "note": "MazeVectorEnv.step_host_packed: actions in pinned host memory -> device, maze_step writing ONE uint32 record per env "
                             "(row, col, best-next code, terminated, truncated, reward kind + index; include/maze_b200.h MAZE_REC_*), one copy to "
@@ -473,7 +486,8 @@ def run_ours(args, rank, local_rank, world):
                             "steps whose launch changed a maze (maze_env_batch.target_dirty).  Records decode to the wide arrays bit for bit "
                             "(cabi.decode_records, asserted in this run); decoding is left to the consumer and is not inside the timed region "
                             "(host_decode_s_per_step: the library's single-threaded C loop over all envs).  `wide` is round 1's format: "
-                            "26 bytes per env in six arrays"},
+                            "26 bytes per env in six arrays.  transfer_only_value: the same host<->device copies with no kernel between them, "
+                            "all ranks at once -- the floor the host link sets for this path on this box"},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "secondary": secondary_metrics(extra),
