@@ -320,16 +320,26 @@ int launch_gemm(maze_ctx* ctx, int epi, int bn, const bf16* A, int lda, const bf
 
 // ------------------------------------------------------------------------------------------------------
 // Convolution features.  Per sample, shared memory holds the image matrix
-//   R[(y', x), kk]   y' = 0..17 (image row y' - 1; rows -1, 15, 16 are zero), x = 0..15 (column 15 is padding),
-//                    kk = channel * 3 + dx' (dx' = 0..2 <-> column x + dx' - 1), 9 of 16 K slots used
-// in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices: the two K halves of an
-// 8-row group 128 bytes apart, groups 256 bytes apart).  Output position p = y * 16 + x of dy' uses R row
-// p + 16 dy', so the three vertical taps are three MMAs whose A descriptors start 512 bytes apart; the B
-// operands are the three [32 out-channels, 16] weight slices.  Tile t (positions 128 t .. 128 t + 127 = image
-// rows 8 t .. 8 t + 7) accumulates in TMEM columns 32 t .. 32 t + 31.
+//   R[(y', x), kk]   y' = 0..33 (image row y' - 1; only y' = 1..15 are ever non-zero), x = 0..15 (column 15 is
+//                    padding), kk = channel * 3 + dx' (dx' = 0..2 <-> column x + dx' - 1), 9 of 16 K slots used
+// in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices: the two K halves of an 8-row
+// group 128 bytes apart, groups 256 bytes apart), with the 16 columns of an image row stored EVEN COLUMNS FIRST:
+// row index = 16 y' + 8 (x & 1) + (x >> 1).  Then the conv outputs of one max-pool class -- the positions
+// (2 py + dy_c, 2 px + dx_c) of all pooled cells (py, px) -- under vertical tap dy' are the R rows
+// 16 (2 py + dy_c + dy') + 8 dx_c + px: eight consecutive rows per py, 32 rows (1 024 bytes) from one py to the
+// next, i.e. ONE UMMA A operand (M = 128: py = 0..15, px = 0..7; stride-dimension offset 1 024) starting at byte
+// 256 (2 (dy_c + dy') + dx_c).  Twelve MMAs per sample (4 pool classes x 3 vertical taps, N = 32 channels, K = 16)
+// leave D[(py, px), 32 class + channel] in 128 TMEM columns: the four candidates of a pooled cell sit in the SAME TMEM
+// lane, so the 2 x 2 max-pool is three max instructions per channel in registers -- no shuffles, and only the two
+// warps that own py < 8 have an epilogue at all (the first version pooled a [position, channel] accumulator by
+// exchanging values between lanes: 2 080 warp instructions of epilogue per sample against ~600 here).
+// TWO samples share every MMA: sample B's image matrix starts 16 image rows (8 192 bytes) after sample A's, which is
+// exactly eight py steps, so rows 0-63 of the M = 128 operand are A's pooled cells (py = 0..7) and rows 64-127 are B's.
+// (The two y' rows a sample would own beyond its sixteen are only read by its dummy row py = 7.)  Warps 0-1 run A's
+// epilogue from TMEM lanes 0-63, warps 2-3 run B's from lanes 64-127.
 constexpr int FEAT_THREADS = 128;
-constexpr int FEAT_R_ROWS = 288;                   // 18 x 16
-constexpr int FEAT_R_BYTES = FEAT_R_ROWS * 32;     // 9216
+constexpr int FEAT_R_ROWS = 34 * 16;               // y' = 0..15 sample A, 16..31 sample B, 32..33 zero
+constexpr int FEAT_R_BYTES = FEAT_R_ROWS * 32;     // 17 408
 constexpr int FEAT_W_BYTES = 3 * 32 * 32;          // three [32, 16] bf16 slices
 constexpr int NET_CONV_OUT = 32 * 49;              // 1568
 constexpr int NET_IN = 1600;                       // 1568 + 6, padded to a multiple of 64
@@ -344,8 +354,8 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
                     const float* __restrict__ conv_b, bf16* __restrict__ X, uint8_t* __restrict__ pool_idx) {
     __shared__ __align__(128) uint8_t sR[FEAT_R_BYTES];
     __shared__ __align__(128) uint8_t sW[FEAT_W_BYTES];
-    __shared__ __align__(16) bf16 sfeat[NET_CONV_OUT];
-    __shared__ __align__(16) uint8_t sidx[SAVE_IDX ? NET_CONV_OUT : 16];
+    __shared__ __align__(16) bf16 sfeat[2][NET_CONV_OUT];
+    __shared__ __align__(16) uint8_t sidx[2][SAVE_IDX ? NET_CONV_OUT : 16];
     __shared__ float sbias[32];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -355,9 +365,10 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
         tc::mbar_fence_init();
     }
     if (warp == 0) {
-        tc::tmem_alloc(tc::smem_u32(&tmem_slot), 64);
+        tc::tmem_alloc(tc::smem_u32(&tmem_slot), 128);
         tc::tmem_relinquish();
     }
+    for (int i = tid * 16; i < FEAT_R_BYTES; i += FEAT_THREADS * 16) *reinterpret_cast<uint4*>(sR + i) = make_uint4(0, 0, 0, 0);
     // weight slices: sW[dy][o][kk] = conv_w[o][c][dy][dx], kk = c * 3 + dx (Conv2d.weight is [32, 3, 3, 3])
     for (int i = tid; i < 3 * 32 * 16; i += FEAT_THREADS) {
         const int dy = i / 512, o = (i >> 4) & 31, kk = i & 15;
@@ -373,13 +384,17 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
     const uint32_t bar_a = tc::smem_u32(&bar), r_base = tc::smem_u32(sR), w_base = tc::smem_u32(sW);
     uint32_t phase = 0;
 
-    for (int s = blockIdx.x; s < n; s += gridDim.x) {
-        // ---- build R from the packed window (word ch * 8 + k: window rows 2 k in bits 0-14, 2 k + 1 in bits 16-30)
-        const uint32_t* words = win + (size_t)s * MAZE_WINDOW_WORDS;
-        for (int r = tid; r < FEAT_R_ROWS; r += FEAT_THREADS) {
-            const int iy = (r >> 4) - 1, x = r & 15;
+    for (int s0 = 2 * blockIdx.x; s0 < n; s0 += 2 * gridDim.x) {
+        // ---- build both image matrices from the packed windows (word ch * 8 + k: window rows 2 k in bits 0-14, 2 k + 1 in
+        //      bits 16-30): 2 x 256 rows, four per thread
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = tid + FEAT_THREADS * k;          // 0..511: sample r >> 8, y' = (r >> 4) & 15, x = r & 15
+            const int smp = s0 + (r >> 8);
+            const int iy = ((r >> 4) & 15) - 1, x = r & 15;
             uint32_t v9 = 0;
-            if (iy >= 0 && iy < MAZE_WINDOW) {
+            if (iy >= 0 && smp < n) {
+                const uint32_t* words = win + (size_t)smp * MAZE_WINDOW_WORDS;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const uint32_t rowbits = (__ldg(words + c * 8 + (iy >> 1)) >> ((iy & 1) * 16)) & 0x7fffu;
@@ -392,8 +407,9 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
                 const uint32_t b2 = (v9 >> (2 * j)) & 3u;
                 w[j] = (b2 & 1u) * 0x3F80u + (b2 >> 1) * 0x3F800000u;
             }
-            *reinterpret_cast<uint4*>(sR + r_offset(r, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(sR + r_offset(r, 1)) = make_uint4(w[4] & 0xffffu, 0, 0, 0);
+            const int row = (r & ~15) + ((x & 1) << 3) + (x >> 1);   // even columns first
+            *reinterpret_cast<uint4*>(sR + r_offset(row, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(sR + r_offset(row, 1)) = make_uint4(w[4] & 0xffffu, 0, 0, 0);
         }
         tc::fence_proxy_async_smem();
         __syncthreads();
@@ -401,77 +417,80 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
             tc::tc_fence_after();
             constexpr uint32_t idesc = tc::idesc_bf16(128, 32);
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
+            for (int cls = 0; cls < 4; ++cls)
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
-                    const uint64_t da = tc::smem_desc(r_base + (uint32_t)(t * 16 + dy * 2) * 256u, 128, 256, tc::SWIZZLE_NONE);
+                    const uint64_t da = tc::smem_desc(r_base + (uint32_t)(2 * ((cls >> 1) + dy) + (cls & 1)) * 256u, 128, 1024, tc::SWIZZLE_NONE);
                     const uint64_t db = tc::smem_desc(w_base + (uint32_t)dy * 1024u, 128, 256, tc::SWIZZLE_NONE);
-                    tc::umma_bf16(tmem_base + (uint32_t)t * 32u, da, db, idesc, (uint32_t)(dy != 0));
+                    tc::umma_bf16(tmem_base + (uint32_t)cls * 32u, da, db, idesc, (uint32_t)(dy != 0));
                 }
             tc::umma_commit(bar_a);
         }
         tc::mbar_wait(bar_a, phase);
         phase ^= 1u;
         tc::tc_fence_after();
-        // ---- epilogue: bias, 2 x 2 max-pool (first maximum in scan order wins), LeakyReLU
-        const bool odd = lane & 1, upper = (lane >> 4) & 1;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            uint32_t v[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * 32u, v);
-            tc::tmem_ld_wait();
-            // x pair: even lanes keep channels 0-15, odd lanes channels 16-31
-            float a[16];
-            uint32_t xbits = 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float lo = __uint_as_float(v[j]), hi = __uint_as_float(v[j + 16]);
-                const float send = odd ? lo : hi, keep = odd ? hi : lo;
-                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                const float left = odd ? recv : keep, right = odd ? keep : recv;
-                a[j] = fmaxf(left, right);
-                xbits |= (uint32_t)(right > left) << j;
-            }
-            // y pair (lanes l, l ^ 16): lanes 0-15 keep the first 8 of their 16 channels, lanes 16-31 the last 8
-            const uint32_t other_xbits = __shfl_xor_sync(0xffffffffu, xbits, 16);
-            const int py = t * 4 + warp, px = (lane & 15) >> 1;
+        // ---- epilogue: warp pair (warp >> 1) owns sample s0 + (warp >> 1); its lanes are the pooled cells py = 4 (warp & 1) +
+        //      lane / 8, px = lane % 8.  2 x 2 max-pool over the four class blocks (first maximum in scan order wins), bias,
+        //      LeakyReLU.
+        const int half = warp >> 1;
+        if (s0 + half < n) {
+            const int py = (warp & 1) * 4 + (lane >> 3), px = lane & 7;
             const bool valid = py < 7 && px < 7;
+            float m[32];
+            uint32_t v[32];
+            [[maybe_unused]] uint32_t c1 = 0, c2 = 0;   // bit ch of c1 / c2: low / high bit of the winning class
+            tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+            tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float send = upper ? a[j] : a[j + 8], keep = upper ? a[j + 8] : a[j];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-                const float top = upper ? recv : keep, bottom = upper ? keep : recv;
-                const int jj = upper ? j + 8 : j;                       // index into the 16 channels both lanes hold
-                const int ch = (odd ? 16 : 0) + jj;
-                const bool down = bottom > top;
-                float m = fmaxf(top, bottom) + sbias[ch];
-                if (valid) {
+            for (int ch = 0; ch < 32; ++ch) m[ch] = __uint_as_float(v[ch]);
+#pragma unroll
+            for (int cls = 1; cls < 4; ++cls) {
+                tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cls * 32u, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int ch = 0; ch < 32; ++ch) {
+                    const float x = __uint_as_float(v[ch]);
                     if constexpr (SAVE_IDX) {
-                        const uint32_t xb_top = ((upper ? other_xbits : xbits) >> jj) & 1u, xb_bot = ((upper ? xbits : other_xbits) >> jj) & 1u;
-                        sidx[ch * 49 + py * 7 + px] = (uint8_t)((down ? 2u + xb_bot : xb_top) | (m > 0.f ? 4u : 0u));
+                        const bool take = x > m[ch];
+                        if (cls & 1) c1 = take ? (c1 | (1u << ch)) : c1; else c1 = take ? (c1 & ~(1u << ch)) : c1;
+                        if (cls & 2) c2 = take ? (c2 | (1u << ch)) : c2;
                     }
-                    m = m > 0.f ? m : LRELU_SLOPE * m;
-                    sfeat[ch * 49 + py * 7 + px] = __float2bfloat16(m);
+                    m[ch] = fmaxf(m[ch], x);
+                }
+            }
+            if (valid) {
+                const int q = py * 7 + px;
+#pragma unroll
+                for (int ch = 0; ch < 32; ++ch) {
+                    float x = m[ch] + sbias[ch];
+                    if constexpr (SAVE_IDX) sidx[half][ch * 49 + q] = (uint8_t)(((c1 >> ch) & 1u) | (((c2 >> ch) & 1u) << 1) | (x > 0.f ? 4u : 0u));
+                    x = x > 0.f ? x : LRELU_SLOPE * x;
+                    sfeat[half][ch * 49 + q] = __float2bfloat16(x);
                 }
             }
         }
         tc::tc_fence_before();
         __syncthreads();
-        // ---- write the feature row: 1568 conv features, 6 state floats, zero padding up to 1600
-        bf16* xrow = X + (size_t)s * NET_IN;
-        for (int i = tid; i < NET_CONV_OUT / 8; i += FEAT_THREADS)
-            reinterpret_cast<uint4*>(xrow)[i] = reinterpret_cast<const uint4*>(sfeat)[i];
-        if (tid < 32) xrow[NET_CONV_OUT + tid] = __float2bfloat16(tid < 6 ? __ldg(vec + (size_t)s * 6 + tid) : 0.f);
-        if constexpr (SAVE_IDX) {
-            uint8_t* irow = pool_idx + (size_t)s * NET_CONV_OUT;
-            for (int i = tid; i < NET_CONV_OUT / 16; i += FEAT_THREADS)
-                reinterpret_cast<uint4*>(irow)[i] = reinterpret_cast<const uint4*>(sidx)[i];
+        // ---- write the feature rows: 1568 conv features, 6 state floats, zero padding up to 1600
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int smp = s0 + h;
+            if (smp >= n) break;
+            bf16* xrow = X + (size_t)smp * NET_IN;
+            for (int i = tid; i < NET_CONV_OUT / 8; i += FEAT_THREADS)
+                reinterpret_cast<uint4*>(xrow)[i] = reinterpret_cast<const uint4*>(sfeat[h])[i];
+            if (tid < 32) xrow[NET_CONV_OUT + tid] = __float2bfloat16(tid < 6 ? __ldg(vec + (size_t)smp * 6 + tid) : 0.f);
+            if constexpr (SAVE_IDX) {
+                uint8_t* irow = pool_idx + (size_t)smp * NET_CONV_OUT;
+                for (int i = tid; i < NET_CONV_OUT / 16; i += FEAT_THREADS)
+                    reinterpret_cast<uint4*>(irow)[i] = reinterpret_cast<const uint4*>(sidx[h])[i];
+            }
         }
         // the next iteration rewrites sfeat / sidx only after its own __syncthreads
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1043,7 +1062,8 @@ int check_net(maze_ctx* ctx, const maze_dqn_net* net, bool train) {
 }
 
 int features(maze_ctx* ctx, bool save_idx, const float* vec, const uint32_t* win, int n, const float* params, bf16* X, uint8_t* idx, cudaStream_t st) {
-    const int grid = n < ctx->num_sms * 6 ? n : ctx->num_sms * 6;
+    const int pairs = (n + 1) / 2;   // two samples per iteration
+    const int grid = pairs < ctx->num_sms * 4 ? pairs : ctx->num_sms * 4;   // 128 TMEM columns per CTA: four CTAs per SM
     if (save_idx)
         net_features_kernel<true><<<grid, FEAT_THREADS, 0, st>>>(vec, win, n, params + MAZE_NET_OFF_CONV_W, params + MAZE_NET_OFF_CONV_B, X, idx);
     else
