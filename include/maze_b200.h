@@ -148,6 +148,14 @@ typedef struct maze_env_batch {
                               so maze_step rewrites `target` only then, and a host mirror of the outputs can skip
                               the device-to-host copy of `target` on all other steps                       */
     uint32_t* packed;      /* optional [B] (may be NULL): packed step records, written under MAZE_STEP_PACKED        */
+    uint32_t* visit_bits;  /* optional (may be NULL): one bit per block, "visited in the current episode", bit (r, c) of
+                              env e = bit c & 31 of word e * visit_bits_stride + r * visit_bits_pitch + (c >> 5).  Kept
+                              beside the counters by every stepping kernel (set on a legal move, cleared when an episode
+                              starts); the -v1 window and the replay encode read their non_visited channel from it: a
+                              15 x 15 window is 15 consecutive bitmap rows (180 contiguous bytes at 81 x 81) instead of
+                              up to 25 scattered 32-byte sectors of counters                                          */
+    int32_t   visit_bits_pitch;   /* words per bitmap row: ceil(max W / 32)                                          */
+    int32_t   visit_bits_stride;  /* words per env: max H * pitch rounded up to a multiple of 4                       */
 } maze_env_batch;
 
 /* sizeof of the ABI structs as this library was compiled (a binding checks its own layout against it):

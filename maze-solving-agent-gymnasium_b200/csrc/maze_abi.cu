@@ -26,6 +26,9 @@ int maze_check_batch(maze_ctx* ctx, const maze_env_batch* b) {
         return maze_fail_arg(ctx, MAZE_E_RANGE, "num_envs / num_mazes / slot (must be even)");
     if (b->visit_slot < b->slot || (b->visit_tiled != 0 && b->visit_tiled != 1))
         return maze_fail_arg(ctx, MAZE_E_RANGE, "visit_slot (>= slot) / visit_tiled (0 or 1)");
+    if (b->visit_bits && (b->visit_bits_pitch < 1 || b->visit_bits_stride < b->visit_bits_pitch || (b->visit_bits_stride & 3) ||
+                          ((uintptr_t)b->visit_bits & 15)))
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "visit_bits: pitch >= 1, stride a multiple of 4 words, 16-byte aligned");
     if (b->visit_cell_stride <= 0 || b->visit_env_stride <= 0)
         return maze_fail_arg(ctx, MAZE_E_RANGE, "visit strides (cell-major: B, 1; env-major: 1, slot)");
     if (((uintptr_t)b->meta & 15) || ((uintptr_t)b->state & 7) || ((uintptr_t)b->agent & 7) ||

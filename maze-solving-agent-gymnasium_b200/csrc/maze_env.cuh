@@ -100,6 +100,16 @@ __device__ __forceinline__ int visit_index(const maze_env_batch& b, int r, int c
     return r * W + c;
 }
 
+// "Visited in this episode" bitmap (maze_env_batch.visit_bits; optional).
+__device__ __forceinline__ void visit_bit_set(const maze_env_batch& b, int e, int r, int c) {
+    if (b.visit_bits) atomicOr(b.visit_bits + (size_t)e * b.visit_bits_stride + r * b.visit_bits_pitch + (c >> 5), 1u << (c & 31));
+}
+__device__ __forceinline__ void visit_bits_clear(const maze_env_batch& b, int e) {   // an episode starts
+    if (!b.visit_bits) return;
+    uint4* p = reinterpret_cast<uint4*>(b.visit_bits + (size_t)e * b.visit_bits_stride);
+    for (int i = 0; i < (b.visit_bits_stride >> 2); ++i) p[i] = make_uint4(0, 0, 0, 0);
+}
+
 // Zero the visit counters of the lanes in `need` (epoch wrap-around: once per 255 episodes per
 // env; envs sharing a maze wrap together, so the lanes of a warp usually clear side by side).
 // Must be called by all 32 lanes.
@@ -179,6 +189,7 @@ __device__ __forceinline__ StepResult env_transition(const maze_env_batch& b, in
             out.reward = __ldg(luts.revisit + cnt);   // :194
         }
         visit_store(vp, (unsigned)((st.epoch << 8) | (cnt < 255 ? cnt + 1 : 255)), pol);   // :196
+        visit_bit_set(b, e, nr, nc);
         st.r = nr;
         st.c = nc;
         st.tab = tb;

@@ -222,6 +222,7 @@ maze_q_rollout_kernel(maze_env_batch b, maze_q_agent ag, int k_steps, uint32_t m
             }
             bool wrapped;
             begin_episode(st, mz.start, __ldg(mz.tab + (mz.start & 0xffff) * mz.W + (mz.start >> 16)), wrapped);
+            visit_bits_clear(b, e);
             if (wrapped)
                 for (int i = 0; i < b.visit_slot; ++i) *VISIT_AT(b, e, i) = 0;
             cur.slot = q_find_or_insert(ag, q_key(st, mz.goal, agent_id));

@@ -124,6 +124,7 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
 
         if (do_reset[k]) {
             begin_episode(st, npos[k], tb[k], wrapped);
+            visit_bits_clear(b, e);
         } else if (valid[k]) {
             if (moved[k]) {
                 const int cnt = ((int)(vis[k] >> 8) == st.epoch) ? (int)(vis[k] & 0xff) : 0;
@@ -143,6 +144,7 @@ maze_step_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, uint32_t
                 }
 #ifndef MAZE_EXP_NOVISIT
                 visit_store(VISIT_AT(b, e, vidx[k]), (unsigned)((st.epoch << 8) | (cnt < 255 ? cnt + 1 : 255)), pol);   // :196
+                visit_bit_set(b, e, npos[k] & 0xffff, npos[k] >> 16);
 #endif
                 st.r = npos[k] & 0xffff;
                 st.c = npos[k] >> 16;
@@ -238,6 +240,7 @@ maze_reset_kernel(maze_env_batch b, const uint8_t* __restrict__ mask) {
         const int start = m0.z;
         const int sidx = (start & 0xffff) * W + (start >> 16);
         begin_episode(s, start, __ldg(b.table + (size_t)m * b.slot + sidx), wrapped);
+        visit_bits_clear(b, ee);
     }
     const unsigned need = __ballot_sync(0xffffffffu, wrapped);
     if (need) warp_clear_visits(need, b, ee);
@@ -279,6 +282,7 @@ maze_step_many_kernel(maze_env_batch b, const uint8_t* __restrict__ actions, int
             }
             bool wrapped;
             begin_episode(st, mz.start, __ldg(mz.tab + (mz.start & 0xffff) * mz.W + (mz.start >> 16)), wrapped);
+            visit_bits_clear(b, e);
             if (wrapped)
                 for (int i = 0; i < b.visit_slot; ++i) *VISIT_AT(b, e, i) = 0;
             reward = 0.0; term = 0; trunc = 0;

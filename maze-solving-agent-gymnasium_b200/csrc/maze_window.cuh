@@ -24,6 +24,34 @@ __device__ __forceinline__ void window_row_masks(const maze_env_batch& b, int e,
     const uint8_t* trow = mz.tab + rr * W;
     const uint16_t* vbase = b.visits + (size_t)e * b.visit_env_stride;
     const int wt = (W + 3) >> 2;
+    if (b.visit_bits && !mz.tor) {
+        // Bitmap path (bordered mazes): the row's "visited" bits are 15 consecutive bits of one bitmap row -- two words -- and
+        // its table bytes five aligned 32-bit words: 7 loads per lane, and the 15 lanes of an env read 15 consecutive bitmap
+        // rows (180 contiguous bytes at 81 x 81: three 64-byte DRAM atoms where the counter tiles cost up to 25 sectors).
+        const int first = rr * W + c0, off = first & 3;
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(mz.tab + (first - off));   // slots are 16-byte aligned and padded
+        const uint32_t* brow = b.visit_bits + (size_t)e * b.visit_bits_stride + rr * b.visit_bits_pitch + (c0 >> 5);
+        uint32_t tword[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) tword[k] = (4 * k - off < WIN) ? __ldg(tw + k) : 0u;
+        const uint32_t b_lo = brow[0], b_hi = ((c0 & 31) + WIN > 32) ? brow[1] : 0u;
+        const unsigned seen = __funnelshift_r(b_lo, b_hi, c0 & 31) & ((1u << WIN) - 1u);
+        unsigned openm = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int jt = 4 * k + q - off;               // window column of table byte q of word k
+                if (jt >= 0 && jt < WIN) openm |= ((tword[k] >> (8 * q)) & MAZE_TAB_OPEN) << jt;
+            }
+        const unsigned all = (1u << WIN) - 1u;
+        const int gj = goal_idx - first, sj = start_idx - first;   // goal / start inside this row of the window?
+        const unsigned goal_bit = (gj >= 0 && gj < WIN) ? 1u << gj : 0u, start_bit = (sj >= 0 && sj < WIN) ? 1u << sj : 0u;
+        m0 = ~openm & all;
+        m1 = openm & ~goal_bit;
+        m2 = openm & ~start_bit & ~seen;
+        return;
+    }
     if (!mz.tor && b.visit_tiled && b.visit_cell_stride == 1) {
         // Fast path (bordered mazes, the tiled env-major visit array of the -v1 default): the row's 15 table bytes come
         // as five aligned 32-bit words, its visit words as one 8-byte load per 4 x 4 tile the row crosses -- 10 loads per
@@ -67,8 +95,13 @@ __device__ __forceinline__ void window_row_masks(const maze_env_batch& b, int e,
         int cc = c0 + j;
         if (mz.tor) cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
         tb[j] = __ldg(trow + cc);
-        const int vi = b.visit_tiled ? vrow + (((cc >> 2) << 4) | (cc & 3)) : vrow + cc;
-        vis[j] = vbase[(size_t)vi * b.visit_cell_stride];
+        if (b.visit_bits) {   // wrapped window on the torus: one bitmap word per block (the word is shared by up to 15 columns: L1)
+            const uint32_t wv = b.visit_bits[(size_t)e * b.visit_bits_stride + rr * b.visit_bits_pitch + (cc >> 5)];
+            vis[j] = ((wv >> (cc & 31)) & 1u) ? (unsigned)((st.epoch << 8) | 1) : 0u;   // in the counters' terms: seen this episode
+        } else {
+            const int vi = b.visit_tiled ? vrow + (((cc >> 2) << 4) | (cc & 3)) : vrow + cc;
+            vis[j] = vbase[(size_t)vi * b.visit_cell_stride];
+        }
     }
 #pragma unroll
     for (int j = 0; j < WIN; ++j) {

@@ -39,6 +39,7 @@ class MazeEnvBatch(C.Structure):
         ("visit_cell_stride", C.c_int64), ("visit_env_stride", C.c_int64),
         ("visit_tiled", C.c_int32), ("visit_slot", C.c_int32),
         ("target_dirty", C.c_void_p), ("packed", C.c_void_p),
+        ("visit_bits", C.c_void_p), ("visit_bits_pitch", C.c_int32), ("visit_bits_stride", C.c_int32),
     ]
 
 

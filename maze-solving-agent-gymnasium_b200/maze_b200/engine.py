@@ -216,10 +216,12 @@ class MazeBatch:
     """B environments over a MazePool; the SoA buffers of `maze_env_batch`."""
 
     def __init__(self, pool: MazePool, num_envs: int, env_maze=None, stats: bool = False, pool_stride: int = 1,
-                 queue: bool = False, visit_layout: str = "cell"):
+                 queue: bool = False, visit_layout: str = "cell", visit_bits: bool = False):
         """visit_layout: "cell" = [slot, B] (best for the -v0 step: envs sharing a block share lines),
         "env" = [B, slot] (best when the 15x15 window is read every step: rows are contiguous),
-        "tile" = env-major with 4x4 block tiles per 32-byte sector (a walking agent stays in a sector)."""
+        "tile" = env-major with 4x4 block tiles per 32-byte sector (a walking agent stays in a sector).
+        visit_bits: also keep the one-bit-per-block "visited this episode" map (1 KB per env at 81 x 81) that the -v1
+        window and the replay encode read their non_visited channel from."""
         if visit_layout not in ("cell", "env", "tile"):
             raise ValueError("visit_layout must be 'cell', 'env' or 'tile'")
         self.visit_layout = visit_layout
@@ -254,11 +256,14 @@ class MazeBatch:
         self.queue_count = torch.zeros(1, dtype=torch.int32, device=d) if queue else None
         self.target_dirty = torch.zeros(1, dtype=torch.int32, device=d)   # set by launches that write `target`
         self.packed = torch.zeros(B, dtype=torch.int32, device=d)         # packed step records (cabi.STEP_PACKED)
+        self.visit_bits_pitch = (mw + 31) // 32
+        self.visit_bits_stride = _round_up(mh * self.visit_bits_pitch, 4)
+        self.visit_bits = torch.zeros((B, self.visit_bits_stride), dtype=torch.int32, device=d) if visit_bits else None
         self.pool_stride = int(pool_stride)
         self._c = self._make_struct()
 
     _CKPT = ("env_maze", "state", "visits", "agent", "target", "best_dir", "reward", "terminated", "truncated",
-             "ep_return", "stats", "stats_return", "queue", "queue_count", "target_dirty")
+             "ep_return", "stats", "stats_return", "queue", "queue_count", "target_dirty", "visit_bits")
 
     def state_dict(self):
         """Everything a later step depends on (the visit counters included: [slot, B] int16, by far the largest
@@ -291,7 +296,9 @@ class MazeBatch:
             visit_cell_stride=self.num_envs if self.visit_layout == "cell" else 1,
             visit_env_stride=1 if self.visit_layout == "cell" else self.visit_slot,
             visit_tiled=1 if self.visit_layout == "tile" else 0, visit_slot=self.visit_slot,
-            target_dirty=self.target_dirty.data_ptr(), packed=self.packed.data_ptr())
+            target_dirty=self.target_dirty.data_ptr(), packed=self.packed.data_ptr(),
+            visit_bits=None if self.visit_bits is None else self.visit_bits.data_ptr(),
+            visit_bits_pitch=self.visit_bits_pitch, visit_bits_stride=self.visit_bits_stride)
 
     def view_struct(self, lo: int, hi: int) -> cabi.MazeEnvBatch:
         """maze_env_batch over the envs [lo, hi) of this batch: the same buffers with every per-env pointer advanced by
@@ -307,6 +314,8 @@ class MazeBatch:
             if base:
                 setattr(c, name, base + lo * per_env_bytes)
         c.visits = self._c.visits + lo * self._c.visit_env_stride * 2
+        if self._c.visit_bits:
+            c.visit_bits = self._c.visit_bits + lo * self.visit_bits_stride * 4
         return c
 
     def step_view(self, view: cabi.MazeEnvBatch, actions_ptr, mode: int, stream):

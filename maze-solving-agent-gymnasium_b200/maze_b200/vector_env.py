@@ -123,22 +123,32 @@ class MazeVectorEnv(_VectorBase):
             per = max(1, self.num_envs // pool.num_mazes)
             env_maze = (torch.arange(self.num_envs, device=self.device, dtype=torch.int32) // per).clamp_(max=pool.num_mazes - 1)
         self.batch = MazeBatch(pool, self.num_envs, env_maze=env_maze, stats=stats, queue=(on_win == "regenerate"),
-                               visit_layout=visit_layout or ("tile" if self.enrich else "cell"))
+                               visit_layout=visit_layout or ("tile" if self.enrich else "cell"), visit_bits=self.enrich)
         self._mode = ((cabi.STEP_AUTORESET if self.autoreset else 0)
                       | (cabi.STEP_WIN_NEXT if on_win == "next" else 0)
                       | (cabi.STEP_WIN_QUEUE if on_win == "regenerate" else 0))
-        self.single_action_space = _ActionSpace(4)
-        self.action_space = _ActionSpace(4, self.num_envs, seed)
-        self.single_observation_space = None
-        self.observation_space = None
+        # spaces: gymnasium's when it is installed, the package's own stand-ins (maze_b200/_gym.py) otherwise, so that
+        # single_observation_space / observation_space are never None.  They describe the PRODUCED observations
+        # (base_maze_env.py:116-122; -v1: simple_maze_env.py:151-158), not the reference's declared ones, which disagree
+        # with what its envs return.
+        sp = _gymshim.spaces
+        hi = max(self.pool.max_shape)
+        if self.enrich:
+            single = {"agent": sp.Box(0.0, 1.0, shape=(2,), dtype=np.float64), "target": sp.Box(0.0, 1.0, shape=(2,), dtype=np.float64),
+                      "best dir": sp.Box(-hi, hi, shape=(2,), dtype=np.int32),
+                      "window": sp.Box(0.0, 1.0, shape=(3, cabi.WINDOW, cabi.WINDOW), dtype=np.float32)}
+        else:
+            single = {"agent": sp.Box(0, hi, shape=(2,), dtype=np.int32), "target": sp.Box(0, hi, shape=(2,), dtype=np.int32),
+                      "best dir": sp.Box(-hi, hi, shape=(2,), dtype=np.int32)}
+        self.single_observation_space = sp.Dict(single)
+        self.observation_space = sp.Dict({k: sp.Box(v.low if np.isscalar(v.low) else float(np.min(v.low)), v.high if np.isscalar(v.high) else float(np.max(v.high)),
+                                                    shape=(self.num_envs,) + tuple(v.shape), dtype=v.dtype) for k, v in single.items()})
         if _gym is not None:  # pragma: no cover
-            sp = _gym.spaces
-            hi = max(self.pool.max_shape)
             self.single_action_space = sp.Discrete(4)
             self.action_space = sp.MultiDiscrete([4] * self.num_envs)
-            self.single_observation_space = sp.Dict({
-                "agent": sp.Box(0, hi, shape=(2,), dtype=np.int32), "target": sp.Box(0, hi, shape=(2,), dtype=np.int32),
-                "best dir": sp.Box(-hi, hi, shape=(2,), dtype=np.int32)})
+        else:
+            self.single_action_space = _ActionSpace(4)
+            self.action_space = _ActionSpace(4, self.num_envs, seed)
         # pinned staging for the host-buffer path
         self._h_actions = None
         self._d_actions = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)

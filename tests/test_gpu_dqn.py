@@ -12,7 +12,7 @@ from conftest import load_golden  # noqa: E402
 from oracle.env_port import ClosedFormEnv  # noqa: E402
 
 
-def _setup(B_per_maze=4):
+def _setup(B_per_maze=4, visit_bits=False):
     import maze_b200 as mb
     z, meta = load_golden("bestdir")
     rows = [m for m in meta if m["shape"] >= 15][:6]
@@ -21,7 +21,7 @@ def _setup(B_per_maze=4):
                                   [m["toroidal"] for m in mazes])
     B = B_per_maze * len(mazes)
     env_maze = np.arange(B) % len(mazes)
-    batch = mb.MazeBatch(pool, B, env_maze=torch.from_numpy(env_maze.astype(np.int32)).cuda(), visit_layout="env")
+    batch = mb.MazeBatch(pool, B, env_maze=torch.from_numpy(env_maze.astype(np.int32)).cuda(), visit_layout="env", visit_bits=visit_bits)
     envs = [ClosedFormEnv(mazes[k]["grid"], mazes[k]["start"], mazes[k]["goal"], mazes[k]["toroidal"], enrich=True) for k in env_maze]
     return mb, batch, envs
 
@@ -31,9 +31,10 @@ def _state_of(obs):
     return vec, np.asarray(obs["window"], dtype=np.float32)
 
 
-def test_replay_holds_exactly_the_oracle_transitions_and_samples_unpack():
+@pytest.mark.parametrize("visit_bits", [False, True])
+def test_replay_holds_exactly_the_oracle_transitions_and_samples_unpack(visit_bits):
     from maze_b200.dqn import DeviceReplay, unpack_windows
-    mb, batch, envs = _setup()
+    mb, batch, envs = _setup(visit_bits=visit_bits)
     B, T = batch.num_envs, 120
     mem = DeviceReplay(batch, capacity=B * T, seed=3)
     batch.reset()

@@ -220,3 +220,24 @@ def test_step_host_refreshes_target_only_when_a_maze_changed():
     wins = env.episode_statistics()["wins"]
     assert wins > 0 and 0 < copies_with_target < 400     # targets did change, and most steps skipped the copy
     assert env.d2h_bytes_per_step() < B * 34
+
+
+@pytest.mark.parametrize("enrich", [False, True])
+def test_vector_env_declares_spaces_that_match_its_observations(enrich):
+    """The north star asks for a gymnasium VectorEnv: single_observation_space / observation_space / action spaces exist
+    (gymnasium's classes when it is installed, the package's stand-ins otherwise) and describe what reset / step produce."""
+    import maze_b200 as mb
+    env = mb.MazeVectorEnv(64, shape=(21, 21), num_mazes=4, enrich=enrich, seed=1)
+    obs, _ = env.reset()
+    assert env.single_observation_space is not None and env.observation_space is not None
+    assert set(env.single_observation_space.keys()) == set(obs.keys())
+    for k, v in obs.items():
+        single, batched = env.single_observation_space[k], env.observation_space[k]
+        assert tuple(batched.shape) == tuple(v.shape) == (64,) + tuple(single.shape), k
+        assert np.dtype(single.dtype) == np.dtype(str(v.dtype).replace("torch.", "")), (k, single.dtype, v.dtype)
+        lo, hi = float(v.min()), float(v.max())
+        assert lo >= float(np.min(single.low)) and hi <= float(np.max(single.high)), k
+    a = env.action_space.sample()
+    assert len(a) == 64 and env.single_action_space.n == 4
+    obs, rew, term, trunc, _ = env.step(a)
+    assert rew.shape == (64,) and term.dtype == torch.bool and trunc.dtype == torch.bool

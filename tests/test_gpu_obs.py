@@ -9,13 +9,13 @@ pytestmark = pytest.mark.gpu
 from conftest import load_golden  # noqa: E402
 
 
-def _replay(meta, z, visit_layout, on_step):
+def _replay(meta, z, visit_layout, on_step, visit_bits=False):
     import maze_b200 as mb
     pool = mb.MazePool.from_grids([z[f"m{m['id']}_grid"] for m in meta], [m["start"] for m in meta],
                                   [m["goal"] for m in meta], [m["topology"] == "torus" for m in meta])
     pairs = [(k, m, j) for k, m in enumerate(meta) for j in m["tapes"]]
     env_maze = torch.tensor([k for k, _, _ in pairs], dtype=torch.int32, device="cuda")
-    batch = mb.MazeBatch(pool, len(pairs), env_maze=env_maze, visit_layout=visit_layout)
+    batch = mb.MazeBatch(pool, len(pairs), env_maze=env_maze, visit_layout=visit_layout, visit_bits=visit_bits)
     tapes = [z[f"m{m['id']}_t{j}_action"] for _, m, j in pairs]
     T = max(len(t) for t in tapes)
     acts = np.zeros((T, len(pairs)), dtype=np.uint8)
@@ -30,8 +30,12 @@ def _replay(meta, z, visit_layout, on_step):
 
 
 @pytest.mark.parametrize("name", ["steps", "steps81"])
-@pytest.mark.parametrize("visit_layout", ["env", "cell", "tile"])
+@pytest.mark.parametrize("visit_layout", ["env", "cell", "tile", "cell+bits", "tile+bits"])
 def test_window_matches_reference_traces(name, visit_layout):
+    """"+bits": the non_visited channel comes from the one-bit-per-block visited map (maze_env_batch.visit_bits, the -v1
+    default of MazeVectorEnv) instead of the visit counters."""
+    visit_bits = visit_layout.endswith("+bits")
+    visit_layout = visit_layout.split("+")[0]
     z, meta = load_golden(name)
     meta = [m for m in meta if m["enrich"]]
     assert len(meta) >= (5 if name == "steps" else 1)
@@ -49,7 +53,7 @@ def test_window_matches_reference_traces(name, visit_layout):
             np.testing.assert_array_equal(tn[e].view(np.uint64), z[pre + "target"][t].view(np.uint64))
             checked[0] += 1
 
-    _replay(meta, z, visit_layout, on_step)
+    _replay(meta, z, visit_layout, on_step, visit_bits=visit_bits)
     assert checked[0] > (2000 if name == "steps" else 400)
 
 
@@ -74,8 +78,10 @@ def test_direction_mask_matches_reference_traces(golden_steps):
     assert checked[0] > 5000
 
 
-def test_window_against_oracle_with_autoreset():
-    """Window after autoresets and revisits, both topologies, vs the closed-form oracle."""
+@pytest.mark.parametrize("visit_bits", [False, True])
+def test_window_against_oracle_with_autoreset(visit_bits):
+    """Window after autoresets and revisits, both topologies, vs the closed-form oracle (with the visited bitmap: it must be
+    cleared by every episode start)."""
     from oracle.env_port import ClosedFormEnv
     import maze_b200 as mb
     z, meta = load_golden("bestdir")
@@ -84,7 +90,7 @@ def test_window_against_oracle_with_autoreset():
     pool = mb.MazePool.from_grids([m["grid"] for m in mazes], [m["start"] for m in mazes], [m["goal"] for m in mazes],
                                   [m["toroidal"] for m in mazes])
     B = len(mazes)
-    batch = mb.MazeBatch(pool, B, visit_layout="env")
+    batch = mb.MazeBatch(pool, B, visit_layout="env", visit_bits=visit_bits)
     envs = [ClosedFormEnv(m["grid"], m["start"], m["goal"], m["toroidal"], enrich=True) for m in mazes]
     batch.reset()
     obs = [e.reset()[0] for e in envs]

@@ -212,8 +212,8 @@ def test_step_many_equals_repeated_steps(visit_layout, chunk):
     mode = mb.cabi.STEP_AUTORESET | mb.cabi.STEP_WIN_NEXT
     rng = np.random.default_rng(3)
     acts = torch.from_numpy(rng.integers(0, 4, (3 * K, B)).astype(np.uint8)).cuda()
-    one = mb.MazeBatch(pool, B, env_maze=env_maze.clone(), stats=True, pool_stride=5, visit_layout=visit_layout)
-    many = mb.MazeBatch(pool, B, env_maze=env_maze.clone(), stats=True, pool_stride=5, visit_layout=visit_layout)
+    one = mb.MazeBatch(pool, B, env_maze=env_maze.clone(), stats=True, pool_stride=5, visit_layout=visit_layout, visit_bits=True)
+    many = mb.MazeBatch(pool, B, env_maze=env_maze.clone(), stats=True, pool_stride=5, visit_layout=visit_layout, visit_bits=True)
     one.reset(); many.reset()
     for burst in range(3):
         tape = acts[burst * K:(burst + 1) * K]
@@ -225,7 +225,7 @@ def test_step_many_equals_repeated_steps(visit_layout, chunk):
         tr = many.step_many(tape, mode, trace=True, chunk_envs=chunk)
         for k in ref:
             assert torch.equal(tr[k], torch.stack(ref[k])), (burst, k)
-        for k in ("state", "env_maze", "agent", "target", "best_dir", "reward", "terminated", "truncated", "visits", "ep_return", "stats"):
+        for k in ("state", "env_maze", "agent", "target", "best_dir", "reward", "terminated", "truncated", "visits", "ep_return", "stats", "visit_bits"):
             assert torch.equal(getattr(many, k), getattr(one, k)), (burst, k)
         assert abs(float(many.stats_return.item()) - float(one.stats_return.item())) < 1e-6
     assert int(one.stats[0].item()) > 0
