@@ -471,6 +471,13 @@ int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const float* vec, 
 int maze_dqn_adamw(maze_ctx* ctx, const maze_dqn_net* net, float lr, float beta1, float beta2, float eps, float weight_decay,
                    int64_t step, float grad_scale, float clamp, void* stream);
 
+/* In-situ launch times of maze_dqn_backward: while enabled, every launch of a backward call is followed by a CUDA event
+ * on the caller's stream; _read waits for the last call's events and returns the `count` per-launch durations (ms) in
+ * launch order with their labels (label_bytes per entry, NUL-terminated; labels may be NULL).  This is how bench.py
+ * measures the dominant kernel's duration inside the step (ncu's replays are serialised and cold-cache). */
+int maze_dqn_net_profile(maze_ctx* ctx, int enable);
+int maze_dqn_net_profile_read(maze_ctx* ctx, float* ms, char* labels, int label_bytes, int cap, int* count);
+
 /* memory.sample(n) that keeps the windows packed: the same draw as maze_dqn_sample (same seed / draw -> same
  * transitions), 212 bytes per transition instead of 5.5 KB.  action [n] uint8. */
 int maze_dqn_sample_packed(maze_ctx* ctx, const maze_replay* r, int n, uint64_t seed, uint64_t draw, float* vec, uint32_t* win,
@@ -481,7 +488,8 @@ int maze_dqn_sample_packed(maze_ctx* ctx, const maze_replay* r, int n, uint64_t 
  * (act 0 none, 1 LeakyReLU(0.01), 2 ReLU; bias may be NULL); 1: C bf16 = acc * act'(aux) with aux [M, ldaux] bf16 the
  * stored activation; 2: C fp32 += acc (atomic, `splits` CTAs along K); 3: as 2 with TRANSPOSED operands, A [K, M] and
  * B [K, N] row-major, i.e. C += A^T . B (the weight gradients, straight from [batch, features] activations; M a multiple
- * of 8).  tile_n 128 or 256. */
+ * of 8).  tile_n 128 or 256 (one CTA per 128 x tile_n tile), or 512: CTA pairs (tcgen05 cta_group::2) on 256 x 256 tiles,
+ * epilogues 0 and 1 only. */
 int maze_dqn_gemm_bf16(maze_ctx* ctx, const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc, int M, int N, int K,
                        int epilogue, int act, const float* bias, const uint16_t* aux, int ldaux, int tile_n, int splits, void* stream);
 

@@ -113,6 +113,7 @@ extern "C" void maze_ctx_destroy(maze_ctx* ctx) {
     cudaFree(ctx->d_lut_invalid);
     cudaFree(ctx->d_counter);
     cudaFree(ctx->d_scratch);
+    maze_net_profile_free(ctx);
     delete ctx;
 }
 

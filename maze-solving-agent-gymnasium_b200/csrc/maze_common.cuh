@@ -22,9 +22,11 @@ struct maze_ctx {
     int    step_ept;        // envs per thread of maze_step (tunable: MAZE_STEP_EPT)
     void*  d_scratch;       // library-owned scratch (candidate wall planes of scored generation), grown on demand
     size_t scratch_bytes;
+    void*  net_profile;     // maze_net.cu: in-situ launch timing (events), created on first use
     char   err[512];
 };
 
+void maze_net_profile_free(maze_ctx* ctx);   // maze_net.cu
 int maze_fail_cuda(maze_ctx* ctx, cudaError_t e, const char* what);
 int maze_fail_arg(maze_ctx* ctx, int code, const char* what);
 int maze_check_batch(maze_ctx* ctx, const maze_env_batch* b);

@@ -57,6 +57,80 @@ struct GemmCfg {
 //              of 64 K-rows x 64 M (N)-elements; inside a box the 8-row swizzle atoms follow each other along K
 //              (stride-dimension offset 1024), the boxes along M / N (leading-dimension offset 8192); one UMMA of
 //              K = 16 starts 16 rows = 2048 bytes further.  No transposed copies of the activations are needed.
+// The bf16 epilogues of one accumulator tile for one thread (= one output row; 32 columns per TMEM load).  The main loop
+// saturates L2 -> SM bandwidth, so a global load issued from here waits microseconds: the bias slice of the tile is staged
+// in shared memory by the caller (`sb`, zero beyond N, or nullptr), and the stored activations of EPI_MASK are fetched one
+// 32-column chunk ahead of their use.  (With per-element __ldg of the bias the fc1 forward GEMM took 90 us instead of 50.)
+template <int EPI, int BN>
+__device__ __forceinline__ void epi_bf16_tile(const GemmArgs& g, uint32_t taddr, int row, int n0, const float* sb) {
+    const bool row_ok = row < g.M;
+    bf16* crow = reinterpret_cast<bf16*>(g.C) + (size_t)row * g.ldc + n0;
+    const bf16* arow = g.aux + (size_t)row * g.ldaux + n0;
+    const float neg = g.act == ACT_LRELU ? LRELU_SLOPE : 0.f;
+    uint4 h[4], hn[4];
+    auto load_aux = [&](uint4 (&dst)[4], int c0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dst[u] = make_uint4(0, 0, 0, 0);
+            if (row_ok && n0 + c0 + 8 * u + 8 <= g.N) dst[u] = __ldg(reinterpret_cast<const uint4*>(arow + c0 + 8 * u));
+        }
+    };
+    if constexpr (EPI == EPI_MASK) load_aux(h, 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= g.N) break;
+        uint32_t v[32];
+        tc::tmem_ld32(taddr + (uint32_t)c0, v);
+        if constexpr (EPI == EPI_MASK) {
+            if (c0 + 32 < BN) load_aux(hn, c0 + 32);
+        }
+        tc::tmem_ld_wait();
+        uint32_t packed[16];
+        if constexpr (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sb) b = *reinterpret_cast<const float4*>(sb + c0 + j);
+                float x[4] = {__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y, __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (g.act == ACT_LRELU) x[u] = x[u] > 0.f ? x[u] : LRELU_SLOPE * x[u];
+                    else if (g.act == ACT_RELU) x[u] = fmaxf(x[u], 0.f);
+                }
+                packed[j >> 1] = tc::pack_bf16x2(x[0], x[1]);
+                packed[(j >> 1) + 1] = tc::pack_bf16x2(x[2], x[3]);
+            }
+        } else {   // EPI_MASK: dL/d(pre-activation) = dL/d(activation) * act'(pre), sign taken from the stored activation
+#pragma unroll
+            for (int u8 = 0; u8 < 4; ++u8) {
+                const uint32_t hw[4] = {h[u8].x, h[u8].y, h[u8].z, h[u8].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    // bf16 sign/zero test on the raw bits: > 0 <=> sign clear and magnitude non-zero
+                    const uint32_t lo = hw[u] & 0xffffu, hi = hw[u] >> 16;
+                    const float f0 = (lo != 0 && lo < 0x8000u) ? 1.f : neg, f1 = (hi != 0 && hi < 0x8000u) ? 1.f : neg;
+                    packed[4 * u8 + u] = tc::pack_bf16x2(__uint_as_float(v[8 * u8 + 2 * u]) * f0, __uint_as_float(v[8 * u8 + 2 * u + 1]) * f1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) h[u] = hn[u];
+        }
+#pragma unroll
+        for (int j8 = 0; j8 < 32; j8 += 8) {
+            if (row_ok && n0 + c0 + j8 + 8 <= g.N)
+                *reinterpret_cast<uint4*>(crow + c0 + j8) = make_uint4(packed[j8 >> 1], packed[(j8 >> 1) + 1], packed[(j8 >> 1) + 2], packed[(j8 >> 1) + 3]);
+        }
+    }
+}
+
+// The tile's slice of the bias vector -> shared memory, by the four epilogue warps (128 threads, named barrier 1).  Two
+// buffers, indexed like the accumulator stages: a warp can be at most one tile ahead of the slowest one.
+template <int BN>
+__device__ __forceinline__ void stage_bias(const GemmArgs& g, float* sb, int n0, int et) {
+    for (int i = et; i < BN; i += 128) sb[i] = n0 + i < g.N ? __ldg(g.bias + n0 + i) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
@@ -66,6 +140,7 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_bias[2][BN];   // the tile's bias slice, per accumulator stage
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms are 1024-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; tile t = (split, n block, m block) with the m block
@@ -161,22 +236,25 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else {   // epilogue: warp w may read TMEM lanes 32 (w % 4) .. + 31
         const int q = warp & 3;
+        const bool has_bias = EPI == EPI_BIAS_ACT && g.bias != nullptr;
         uint32_t local = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
             int m0, n0, kb_begin, nkb;
             tile_coords(t, m0, n0, kb_begin, nkb);
             const uint32_t acc = local & 1u;
+            if (has_bias) stage_bias<BN>(g, s_bias[acc], n0, (warp - 2) * 32 + lane);   // overlaps the tile's main loop
             tc::mbar_wait(acc_full0 + 8 * acc, (local >> 1) & 1u);
             tc::tc_fence_after();
             const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < g.M;
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (n0 + c0 >= g.N) break;
-                uint32_t v[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, v);
-                tc::tmem_ld_wait();
-                const int col0 = n0 + c0;
-                if constexpr (EPI == EPI_RED_F32) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            if constexpr (EPI == EPI_RED_F32) {
+                const bool row_ok = row < g.M;
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if (n0 + c0 >= g.N) break;
+                    uint32_t v[32];
+                    tc::tmem_ld32(taddr + (uint32_t)c0, v);
+                    tc::tmem_ld_wait();
+                    const int col0 = n0 + c0;
                     float* dst = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -185,49 +263,9 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                          "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
                                          : "memory");
                     }
-                } else {
-                    uint32_t packed[16];
-                    if constexpr (EPI == EPI_BIAS_ACT) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
-                            if (g.bias) {
-                                x0 += col0 + j < g.N ? __ldg(g.bias + col0 + j) : 0.f;
-                                x1 += col0 + j + 1 < g.N ? __ldg(g.bias + col0 + j + 1) : 0.f;
-                            }
-                            if (g.act == ACT_LRELU) {
-                                x0 = x0 > 0.f ? x0 : LRELU_SLOPE * x0;
-                                x1 = x1 > 0.f ? x1 : LRELU_SLOPE * x1;
-                            } else if (g.act == ACT_RELU) {
-                                x0 = fmaxf(x0, 0.f);
-                                x1 = fmaxf(x1, 0.f);
-                            }
-                            packed[j >> 1] = tc::pack_bf16x2(x0, x1);
-                        }
-                    } else {   // EPI_MASK: dL/d(pre-activation) = dL/d(activation) * act'(pre), sign taken from the stored activation
-                        const bf16* arow = g.aux + (size_t)row * g.ldaux + col0;
-                        const float neg = g.act == ACT_LRELU ? LRELU_SLOPE : 0.f;
-#pragma unroll
-                        for (int j8 = 0; j8 < 32; j8 += 8) {
-                            uint4 h = make_uint4(0, 0, 0, 0);
-                            if (row_ok && col0 + j8 + 8 <= g.N) h = __ldg(reinterpret_cast<const uint4*>(arow + j8));
-                            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                // bf16 sign/zero test on the raw bits: > 0 <=> sign clear and magnitude non-zero
-                                const uint32_t lo = hw[u] & 0xffffu, hi = hw[u] >> 16;
-                                const float f0 = (lo != 0 && lo < 0x8000u) ? 1.f : neg, f1 = (hi != 0 && hi < 0x8000u) ? 1.f : neg;
-                                packed[(j8 >> 1) + u] = tc::pack_bf16x2(__uint_as_float(v[j8 + 2 * u]) * f0, __uint_as_float(v[j8 + 2 * u + 1]) * f1);
-                            }
-                        }
-                    }
-                    bf16* dst = reinterpret_cast<bf16*>(g.C) + (size_t)row * g.ldc + col0;
-#pragma unroll
-                    for (int j8 = 0; j8 < 32; j8 += 8) {
-                        if (row_ok && col0 + j8 + 8 <= g.N)
-                            *reinterpret_cast<uint4*>(dst + j8) = make_uint4(packed[j8 >> 1], packed[(j8 >> 1) + 1], packed[(j8 >> 1) + 2], packed[(j8 >> 1) + 3]);
-                    }
                 }
+            } else {
+                epi_bf16_tile<EPI, BN>(g, taddr, row, n0, has_bias ? s_bias[acc] : nullptr);
             }
             // every value of this accumulator stage is in registers: hand the stage back to the MMA issuer
             tc::tc_fence_before();
@@ -238,6 +276,124 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem_base, ACC_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The same GEMM on CTA PAIRS (tcgen05 cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, compute one
+// 256 x 256 output tile.  Each CTA loads its own 128 rows of A and HALF of the B tile (128 of the 256 N rows); the leader
+// CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes each CTA's
+// 128 rows of the accumulator into that CTA's own TMEM.  Per 128 x 256 outputs an SM now pulls 32 KB per k-block from L2
+// instead of 48 KB: the single-CTA kernel is bound by L2 -> SM bandwidth once its operands are not L2-warm (ncu
+// profiles/r02r: 630 MB through the crossbar in 90 us, tensor pipe 33 %).  Protocol: the "full" barrier of a stage lives
+// in the leader (it expects the bytes of both CTAs; both CTAs' TMA loads complete on it through its shared::cluster
+// address); "empty" and "accumulator full" barriers exist in both CTAs and are released by multicast tcgen05.commit;
+// "accumulator empty" lives in the leader and collects the arrivals of all eight epilogue warps of the pair.
+// K-major operands, BN = 256, no split-K (the forward and backward-data GEMMs).
+constexpr int PAIR_STAGES = 6;
+constexpr uint32_t PAIR_A_BYTES = 128 * BK * 2, PAIR_B_BYTES = 128 * BK * 2, PAIR_STAGE_BYTES = PAIR_A_BYTES + PAIR_B_BYTES;
+constexpr size_t PAIR_SMEM = (size_t)PAIR_STAGES * PAIR_STAGE_BYTES + 1024;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+net_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    constexpr int BN = 256;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2 * PAIR_STAGES + 4];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_bias[2][BN];
+    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int tiles_m = (g.M + 255) / 256, tiles_n = (g.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int nkb = (g.K + BK - 1) / BK;
+    const uint32_t full0 = tc::smem_u32(&bars[0]), empty0 = tc::smem_u32(&bars[PAIR_STAGES]);
+    const uint32_t acc_full0 = tc::smem_u32(&bars[2 * PAIR_STAGES]), acc_empty0 = tc::smem_u32(&bars[2 * PAIR_STAGES + 2]);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+        for (int s = 0; s < PAIR_STAGES; ++s) {
+            tc::mbar_init(full0 + 8 * s, 1);
+            tc::mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(acc_full0 + 8 * a, 1);
+            tc::mbar_init(acc_empty0 + 8 * a, 8);   // four epilogue warps in each CTA of the pair
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc_pair(tc::smem_u32(&tmem_slot), 512);
+        tc::tmem_relinquish_pair();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync();   // both CTAs' barriers are initialised before anything arrives on them from the peer
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // TMA producer (both CTAs)
+            uint32_t it = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                const int m0 = (t % tiles_m) * 256 + (int)rank * 128, n0 = (t / tiles_m) * BN + (int)rank * 128;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const uint32_t s = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
+                    tc::mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    if (leader) tc::mbar_expect_tx(full0 + 8 * s, 2 * PAIR_STAGE_BYTES);
+                    const uint32_t full_leader = tc::mapa(full0 + 8 * s, 0);
+                    const uint32_t a_dst = base + s * PAIR_STAGE_BYTES;
+                    tc::tma_load_2d_pair(a_dst, &tmA, full_leader, i * BK, m0);
+                    tc::tma_load_2d_pair(a_dst + PAIR_A_BYTES, &tmB, full_leader, i * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {   // MMA issuer: the leader CTA only
+            constexpr uint32_t idesc = tc::idesc_bf16(256, BN);
+            uint32_t it = 0, local = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
+                const uint32_t acc = local & 1u;
+                tc::mbar_wait(acc_empty0 + 8 * acc, ((local >> 1) & 1u) ^ 1u);
+                tc::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const uint32_t s = it % PAIR_STAGES, ph = (it / PAIR_STAGES) & 1u;
+                    tc::mbar_wait(full0 + 8 * s, ph);
+                    tc::tc_fence_after();
+                    const uint32_t a_addr = base + s * PAIR_STAGE_BYTES;
+                    const uint64_t da = tc::smem_desc(a_addr, 0, 1024, tc::SWIZZLE_128B);
+                    const uint64_t db = tc::smem_desc(a_addr + PAIR_A_BYTES, 0, 1024, tc::SWIZZLE_128B);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) tc::umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (uint32_t)((i | k) != 0));
+                    tc::umma_commit_pair(empty0 + 8 * s, 3);   // frees the stage in both CTAs
+                }
+                tc::umma_commit_pair(acc_full0 + 8 * acc, 3);
+            }
+        }
+    } else {   // epilogue (both CTAs): this CTA's 128 rows of the tile
+        const int q = warp & 3;
+        const bool has_bias = EPI == EPI_BIAS_ACT && g.bias != nullptr;
+        uint32_t local = 0;
+        for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
+            const int m0 = (t % tiles_m) * 256 + (int)rank * 128, n0 = (t / tiles_m) * BN;
+            const uint32_t acc = local & 1u;
+            if (has_bias) stage_bias<BN>(g, s_bias[acc], n0, (warp - 2) * 32 + lane);
+            tc::mbar_wait(acc_full0 + 8 * acc, (local >> 1) & 1u);
+            tc::tc_fence_after();
+            epi_bf16_tile<EPI, BN>(g, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, m0 + q * 32 + lane, n0, has_bias ? s_bias[acc] : nullptr);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(acc_empty0 + 8 * acc, 0));   // the leader's barrier collects both CTAs
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync();   // the peer may still be reading this CTA's shared memory (MMA) or arriving on its barriers
+    if (warp == 1) tc::tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -298,10 +454,29 @@ int launch_gemm_t(maze_ctx* ctx, const bf16* A, int lda, const bf16* B, int ldb,
     return 0;
 }
 
+template <int EPI>
+int launch_gemm_pair(maze_ctx* ctx, const bf16* A, int lda, const bf16* B, int ldb, const GemmArgs& g, cudaStream_t st) {
+    CUtensorMap ta, tb;
+    if (int rc = make_map(ctx, &ta, A, g.M, g.K, lda, 128)) return rc;
+    if (int rc = make_map(ctx, &tb, B, g.N, g.K, ldb, 128)) return rc;
+    MAZE_CHECK(cudaFuncSetAttribute(net_gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
+    const int num_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
+    int pairs = ctx->num_sms / 2;
+    if (num_tiles < pairs) pairs = num_tiles;
+    net_gemm_pair_kernel<EPI><<<2 * pairs, GEMM_THREADS, PAIR_SMEM, st>>>(ta, tb, g);
+    MAZE_CHECK(cudaGetLastError());
+    return 0;
+}
+
 int launch_gemm(maze_ctx* ctx, int epi, int bn, const bf16* A, int lda, const bf16* B, int ldb, const GemmArgs& g, int splits, cudaStream_t st,
                 bool mn_major = false) {
     if (g.M < 1 || g.N < 1 || g.K < 1 || (g.N % 8) != 0) return maze_fail_arg(ctx, MAZE_E_RANGE, "GEMM shape (N must be a multiple of 8)");
     if (epi != EPI_RED_F32 && splits > 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "split-K needs the accumulate epilogue");
+    if (bn == 512) {   // CTA pairs, 256 x 256 tiles
+        if (mn_major || epi == EPI_RED_F32) return maze_fail_arg(ctx, MAZE_E_RANGE, "the CTA-pair GEMM has the bf16 epilogues and K-major operands only");
+        if (epi == EPI_BIAS_ACT) return launch_gemm_pair<EPI_BIAS_ACT>(ctx, A, lda, B, ldb, g, st);
+        return launch_gemm_pair<EPI_MASK>(ctx, A, lda, B, ldb, g, st);
+    }
     if (mn_major) {
         if (epi != EPI_RED_F32) return maze_fail_arg(ctx, MAZE_E_RANGE, "the MN-major (A^T . B) GEMM only has the accumulate epilogue");
         if ((g.M % 8) != 0) return maze_fail_arg(ctx, MAZE_E_RANGE, "MN-major GEMM: M must be a multiple of 8");
@@ -1061,6 +1236,45 @@ int check_net(maze_ctx* ctx, const maze_dqn_net* net, bool train) {
     return 0;
 }
 
+// Rows per forward chunk of maze_dqn_backward (MAZE_NET_CHUNK_ROWS; a multiple of 256; 0 = the whole batch at once).
+int fc_chunk_rows() {
+    static const int rows = [] {
+        const char* e = getenv("MAZE_NET_CHUNK_ROWS");
+        int v = e && *e ? atoi(e) : 0;
+        if (v <= 0) v = 1 << 30;
+        return (v + 255) / 256 * 256;
+    }();
+    return rows;
+}
+
+// In-situ kernel times: while enabled (maze_dqn_net_profile), maze_dqn_backward records a CUDA event on its stream after
+// every launch; maze_dqn_net_profile_read turns the last call's events into per-launch durations.  These are the times
+// the kernels take INSIDE the train step (warm L2, real clocks), which ncu's serialised cold-cache replays do not show.
+struct NetProfile {
+    static constexpr int CAP = 96;
+    bool on = false;
+    int count = 0;
+    cudaEvent_t ev[CAP] = {};
+    const char* label[CAP] = {};
+};
+
+inline void prof_reset(maze_ctx* ctx, cudaStream_t st) {
+    NetProfile* pr = static_cast<NetProfile*>(ctx->net_profile);
+    if (!pr || !pr->on) return;
+    pr->count = 0;
+    if (!pr->ev[0]) for (auto& e : pr->ev) cudaEventCreate(&e);
+    pr->label[0] = "begin";
+    cudaEventRecord(pr->ev[0], st);
+    pr->count = 1;
+}
+
+inline void prof_mark(maze_ctx* ctx, cudaStream_t st, const char* label) {
+    NetProfile* pr = static_cast<NetProfile*>(ctx->net_profile);
+    if (!pr || !pr->on || pr->count == 0 || pr->count >= NetProfile::CAP) return;
+    pr->label[pr->count] = label;
+    cudaEventRecord(pr->ev[pr->count++], st);
+}
+
 int features(maze_ctx* ctx, bool save_idx, const float* vec, const uint32_t* win, int n, const float* params, bf16* X, uint8_t* idx, cudaStream_t st) {
     const int pairs = (n + 1) / 2;   // two samples per iteration
     const int grid = pairs < ctx->num_sms * 4 ? pairs : ctx->num_sms * 4;   // 128 TMEM columns per CTA: four CTAs per SM
@@ -1069,17 +1283,28 @@ int features(maze_ctx* ctx, bool save_idx, const float* vec, const uint32_t* win
     else
         net_features_kernel<false><<<grid, FEAT_THREADS, 0, st>>>(vec, win, n, params + MAZE_NET_OFF_CONV_W, params + MAZE_NET_OFF_CONV_B, X, idx);
     MAZE_CHECK(cudaGetLastError());
+    prof_mark(ctx, st, save_idx ? "features (conv + pool, saves argmax)" : "features (conv + pool)");
     return 0;
+}
+
+// Tile choice of the four K-major GEMMs of the net: CTA pairs (256 x 256) once there are at least two row blocks;
+// MAZE_NET_NO_PAIRS=1 keeps the single-CTA kernel (A/B measurements).
+int fc_tile(int rows) {
+    static const bool no_pairs = [] { const char* e = getenv("MAZE_NET_NO_PAIRS"); return e && *e && *e != '0'; }();
+    return rows > 128 && !no_pairs ? 512 : 256;
 }
 
 // X [rows, 1600] -> h1 [rows, 1024] -> h2 [rows, 512] with one net's weights
 int mlp_forward(maze_ctx* ctx, const bf16* X, int rows, const bf16* w1b, const bf16* w2b, const float* params, bf16* h1, bf16* h2, cudaStream_t st) {
     GemmArgs g{};
     g.M = rows; g.N = NET_H1; g.K = NET_IN; g.C = h1; g.ldc = NET_H1; g.bias = params + MAZE_NET_OFF_B1; g.act = ACT_LRELU;
-    if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, 256, X, NET_IN, w1b, NET_IN, g, 1, st)) return rc;
+    if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, fc_tile(rows), X, NET_IN, w1b, NET_IN, g, 1, st)) return rc;
+    prof_mark(ctx, st, "fc1 forward GEMM");
     g = GemmArgs{};
     g.M = rows; g.N = NET_H2; g.K = NET_H1; g.C = h2; g.ldc = NET_H2; g.bias = params + MAZE_NET_OFF_B2; g.act = ACT_RELU;
-    return launch_gemm(ctx, EPI_BIAS_ACT, 256, h1, NET_H1, w2b, NET_H1, g, 1, st);
+    if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, fc_tile(rows), h1, NET_H1, w2b, NET_H1, g, 1, st)) return rc;
+    prof_mark(ctx, st, "fc2 forward GEMM");
+    return 0;
 }
 
 [[maybe_unused]] int transpose(maze_ctx* ctx, const bf16* in, int R, int C, int ld_in, bf16* out, int ld_out, float* colsum, cudaStream_t st) {
@@ -1101,7 +1326,8 @@ extern "C" int maze_dqn_gemm_bf16(maze_ctx* ctx, const uint16_t* A, int lda, con
                                   int epilogue, int act, const float* bias, const uint16_t* aux, int ldaux, int tile_n, int splits, void* stream) {
     if (!ctx) return MAZE_E_NULL;
     if (!A || !B || !C) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_gemm_bf16 pointer");
-    if (epilogue < 0 || epilogue > 3 || act < 0 || act > 2 || (tile_n != 128 && tile_n != 256)) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_gemm_bf16 epilogue / act / tile_n");
+    if (epilogue < 0 || epilogue > 3 || act < 0 || act > 2 || (tile_n != 128 && tile_n != 256 && tile_n != 512))
+        return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_gemm_bf16 epilogue / act / tile_n");
     const bool mn = epilogue == 3;   // C fp32 += A^T . B with A [K, M], B [K, N]
     if (mn) epilogue = EPI_RED_F32;
     if (epilogue == EPI_MASK && !aux) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_gemm_bf16: aux");
@@ -1171,52 +1397,64 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
     float* gr = net->grads;
     const bf16 *w1b = reinterpret_cast<const bf16*>(net->w1_bf16), *w2b = reinterpret_cast<const bf16*>(net->w2_bf16);
     const bf16 *w1t = reinterpret_cast<const bf16*>(net->w1t_bf16), *w2t = reinterpret_cast<const bf16*>(net->w2t_bf16);
+    prof_reset(ctx, st);
     MAZE_CHECK(cudaMemsetAsync(net->loss, 0, sizeof(float), st));
-    // forward: source net on states and next states, target net on next states
-    if (int rc = features(ctx, true, vec, win, n, p, w.X, w.idx, st)) return rc;
-    if (int rc = features(ctx, false, next_vec, next_win, n, p, w.X + np * NET_IN, nullptr, st)) return rc;
-    if (np == (size_t)n) {
-        if (int rc = mlp_forward(ctx, w.X, 2 * n, w1b, w2b, p, w.h1, w.h2, st)) return rc;
-    } else {
-        if (int rc = mlp_forward(ctx, w.X, n, w1b, w2b, p, w.h1, w.h2, st)) return rc;
-        if (int rc = mlp_forward(ctx, w.X + np * NET_IN, n, w1b, w2b, p, w.h1 + np * NET_H1, w.h2 + np * NET_H2, st)) return rc;
+    // forward: source net on states and next states, target net on next states.  Done in row chunks -- features, fc1, fc2 of
+    // one chunk back to back -- so that a chunk's X (3.2 KB a row) and h1 (2 KB a row) are still in L2 when the next GEMM
+    // reads them: with whole-batch passes (n = 8192: 52 MB of X, 33 MB of h1) the GEMMs ran at their cold-cache time in
+    // situ, twice the L2-warm one (tools/net_selftest.py profile).
+    bf16* Xt = w.dX;   // the target net has its own conv weights, so its own features; dX is free until the backward-data GEMM
+    const bf16 *tw1b = reinterpret_cast<const bf16*>(net->tw1_bf16), *tw2b = reinterpret_cast<const bf16*>(net->tw2_bf16);
+    const int chunk = fc_chunk_rows();
+    for (int r0 = 0; r0 < n; r0 += chunk) {
+        const int rows = n - r0 < chunk ? n - r0 : chunk;
+        const float *v0 = vec + (size_t)r0 * 6, *v1 = next_vec + (size_t)r0 * 6;
+        const uint32_t *w0 = win + (size_t)r0 * MAZE_WINDOW_WORDS, *w1 = next_win + (size_t)r0 * MAZE_WINDOW_WORDS;
+        const size_t a = (size_t)r0, b = np + (size_t)r0;
+        if (int rc = features(ctx, true, v0, w0, rows, p, w.X + a * NET_IN, w.idx + a * NET_CONV_OUT, st)) return rc;
+        if (int rc = mlp_forward(ctx, w.X + a * NET_IN, rows, w1b, w2b, p, w.h1 + a * NET_H1, w.h2 + a * NET_H2, st)) return rc;
+        if (int rc = features(ctx, false, v1, w1, rows, p, w.X + b * NET_IN, nullptr, st)) return rc;
+        if (int rc = mlp_forward(ctx, w.X + b * NET_IN, rows, w1b, w2b, p, w.h1 + b * NET_H1, w.h2 + b * NET_H2, st)) return rc;
+        if (int rc = features(ctx, false, v1, w1, rows, net->target, Xt + a * NET_IN, nullptr, st)) return rc;
+        if (int rc = mlp_forward(ctx, Xt + a * NET_IN, rows, tw1b, tw2b, net->target, w.h1t_tn + a * NET_H1, w.h2_tn + a * NET_H2, st)) return rc;
     }
-    // the target net has its own conv weights: its features differ from the source net's
-    bf16* Xt = w.dX;   // dX is free until the backward-data GEMM
-    if (int rc = features(ctx, false, next_vec, next_win, n, net->target, Xt, nullptr, st)) return rc;
-    if (int rc = mlp_forward(ctx, Xt, n, reinterpret_cast<const bf16*>(net->tw1_bf16), reinterpret_cast<const bf16*>(net->tw2_bf16), net->target,
-                             w.h1t_tn, w.h2_tn, st))
-        return rc;
     {
         const int grid = (n + 7) / 8 < ctx->num_sms ? (n + 7) / 8 : ctx->num_sms;   // one CTA per SM: the fc3 gradient is merged with one atomic per CTA and entry
         net_head_loss_kernel<<<grid, HEAD_THREADS, 0, st>>>(w.h2, w.h2 + np * NET_H2, w.h2_tn, n, p + MAZE_NET_OFF_W3, p + MAZE_NET_OFF_B3,
                                                            net->target + MAZE_NET_OFF_W3, net->target + MAZE_NET_OFF_B3, action, reward, gamma,
                                                            w.dh2, gr + MAZE_NET_OFF_W3, gr + MAZE_NET_OFF_B3, net->loss, qsa_out);
         MAZE_CHECK(cudaGetLastError());
+        prof_mark(ctx, st, "head: Q, double-Q target, loss, dQ, fc3 gradients");
     }
     // fc2: dW2 = dh2^T . h1 (MN-major operands: straight from the [n, features] activations), db2 = colsum(dh2),
     //      dh1 = (dh2 . W2) * LeakyReLU'(h1)
     const int splits = n >= 4096 ? 4 : (n >= 1024 ? 2 : 1);
     net_colsum_kernel<<<dim3(NET_H2 / 64, (n + 511) / 512), 256, 0, st>>>(w.dh2, n, NET_H2, NET_H2, gr + MAZE_NET_OFF_B2);
     MAZE_CHECK(cudaGetLastError());
+    prof_mark(ctx, st, "fc2 bias gradient (column sums)");
     GemmArgs g{};
     g.M = NET_H2; g.N = NET_H1; g.K = n; g.C = gr + MAZE_NET_OFF_W2; g.ldc = NET_H1;
     if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh2, NET_H2, w.h1, NET_H1, g, splits * 2, st, true)) return rc;
+    prof_mark(ctx, st, "fc2 weight gradient GEMM (split-K)");
     g = GemmArgs{};
     g.M = n; g.N = NET_H1; g.K = NET_H2; g.C = w.dh1; g.ldc = NET_H1; g.aux = w.h1; g.ldaux = NET_H1; g.act = ACT_LRELU;
-    if (int rc = launch_gemm(ctx, EPI_MASK, 256, w.dh2, NET_H2, w2t, NET_H2, g, 1, st)) return rc;
+    if (int rc = launch_gemm(ctx, EPI_MASK, fc_tile(n), w.dh2, NET_H2, w2t, NET_H2, g, 1, st)) return rc;
+    prof_mark(ctx, st, "fc2 backward-data GEMM (masked)");
     // fc1: dW1 = dh1^T . X, db1 = colsum(dh1), dX = dh1 . W1
     net_colsum_kernel<<<dim3(NET_H1 / 64, (n + 511) / 512), 256, 0, st>>>(w.dh1, n, NET_H1, NET_H1, gr + MAZE_NET_OFF_B1);
     MAZE_CHECK(cudaGetLastError());
+    prof_mark(ctx, st, "fc1 bias gradient (column sums)");
     g = GemmArgs{};
     g.M = NET_H1; g.N = NET_IN; g.K = n; g.C = gr + MAZE_NET_OFF_W1; g.ldc = NET_IN;
     if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh1, NET_H1, w.X, NET_IN, g, splits, st, true)) return rc;
+    prof_mark(ctx, st, "fc1 weight gradient GEMM (split-K)");
     // every gradient but the conv layer's (the first MAZE_NET_OFF_W1 floats of the flat buffer) is complete here: a caller
     // that all-reduces gradients can start on grads[MAZE_NET_OFF_W1:] while the backward-data GEMM and the conv gradient run
     if (fc_ready_event) MAZE_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(fc_ready_event), st));
     g = GemmArgs{};
     g.M = n; g.N = NET_CONV_OUT; g.K = NET_H1; g.C = w.dX; g.ldc = NET_IN; g.act = ACT_NONE;
-    if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, 256, w.dh1, NET_H1, w1t, NET_H1, g, 1, st)) return rc;
+    if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, fc_tile(n), w.dh1, NET_H1, w1t, NET_H1, g, 1, st)) return rc;
+    prof_mark(ctx, st, "fc1 backward-data GEMM");
     static const bool conv_bwd_cuda_cores = getenv("MAZE_NET_CONV_BWD_CUDA_CORES") != nullptr;   // A/B switch for the CUDA-core version
     if (conv_bwd_cuda_cores) {
         const int grid = n < ctx->num_sms * 4 ? n : ctx->num_sms * 4;
@@ -1227,6 +1465,43 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
         const int grid = n < ctx->num_sms * 3 ? n : ctx->num_sms * 3;   // 48 KB of operands + 9 KB of staging per CTA: three fit an SM
         net_conv_bwd_tc_kernel<<<grid, CB_THREADS, CB_SMEM, st>>>(w.dX, w.idx, win, n, gr + MAZE_NET_OFF_CONV_W, gr + MAZE_NET_OFF_CONV_B);
         MAZE_CHECK(cudaGetLastError());
+    }
+    prof_mark(ctx, st, "conv gradient (un-pool + implicit GEMM)");
+    return 0;
+}
+
+void maze_net_profile_free(maze_ctx* ctx) {   // called by maze_ctx_destroy
+    NetProfile* pr = static_cast<NetProfile*>(ctx->net_profile);
+    if (!pr) return;
+    for (auto& e : pr->ev)
+        if (e) cudaEventDestroy(e);
+    delete pr;
+    ctx->net_profile = nullptr;
+}
+
+extern "C" int maze_dqn_net_profile(maze_ctx* ctx, int enable) {
+    if (!ctx) return MAZE_E_NULL;
+    if (!ctx->net_profile) ctx->net_profile = new NetProfile();
+    NetProfile* pr = static_cast<NetProfile*>(ctx->net_profile);
+    pr->on = enable != 0;
+    pr->count = 0;
+    return 0;
+}
+
+extern "C" int maze_dqn_net_profile_read(maze_ctx* ctx, float* ms, char* labels, int label_bytes, int cap, int* count) {
+    if (!ctx) return MAZE_E_NULL;
+    if (!ms || !count || cap < 0 || (labels && label_bytes < 1)) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_net_profile_read arguments");
+    NetProfile* pr = static_cast<NetProfile*>(ctx->net_profile);
+    *count = 0;
+    if (!pr || pr->count < 2) return 0;
+    MAZE_CHECK(cudaEventSynchronize(pr->ev[pr->count - 1]));
+    for (int i = 1; i < pr->count && i - 1 < cap; ++i) {
+        MAZE_CHECK(cudaEventElapsedTime(&ms[i - 1], pr->ev[i - 1], pr->ev[i]));
+        if (labels) {
+            strncpy(labels + (size_t)(i - 1) * label_bytes, pr->label[i], (size_t)label_bytes - 1);
+            labels[(size_t)(i - 1) * label_bytes + label_bytes - 1] = 0;
+        }
+        *count = i;
     }
     return 0;
 }

@@ -139,6 +139,20 @@ class DQNNet:
         self.ctx.check(rc, "maze_dqn_backward")
         return self.loss
 
+    def profile(self, enable: bool):
+        """Switch the in-situ launch timing of backward() on or off (one CUDA event after every launch)."""
+        self.ctx.check(cabi.lib().maze_dqn_net_profile(self.ctx.handle, int(bool(enable))), "maze_dqn_net_profile")
+
+    def profile_read(self):
+        """[(label, ms)] of the last backward() call, in launch order (waits for it to finish)."""
+        cap, nb = 96, 64
+        ms = (C.c_float * cap)()
+        labels = C.create_string_buffer(cap * nb)
+        count = C.c_int(0)
+        rc = cabi.lib().maze_dqn_net_profile_read(self.ctx.handle, ms, labels, nb, cap, C.byref(count))
+        self.ctx.check(rc, "maze_dqn_net_profile_read")
+        return [(labels.raw[i * nb:(i + 1) * nb].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(count.value)]
+
     def adamw(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, grad_scale: float = 1.0,
               clamp: float = 1.0):
         self.step_count += 1

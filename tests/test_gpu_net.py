@@ -55,7 +55,10 @@ def _no_tf32():
 
 
 @pytest.mark.parametrize("M,N,K,tile,act", [(128, 256, 64, 256, 0), (130, 264, 200, 256, 1), (72, 8, 40, 128, 2), (1000, 1568, 1024, 256, 0),
-                                            (384, 1024, 512, 128, 1)])
+                                            (384, 1024, 512, 128, 1),
+                                            # tile 512: CTA pairs (cta_group::2), 256 x 256 tiles
+                                            (256, 256, 64, 512, 0), (512, 512, 448, 512, 1), (1000, 1568, 1024, 512, 2), (8192, 1024, 1600, 512, 1),
+                                            (130, 264, 200, 512, 0)])
 def test_gemm_bias_activation(M, N, K, tile, act):
     from maze_b200.dqn_net import gemm_bf16
     torch.manual_seed(M + N + K)

@@ -200,7 +200,8 @@ def run_case(case):
     elif case == "perf":
         from maze_b200.dqn_net import DQNNet, gemm_bf16
         out = {}
-        for (M, N, K, tn) in ((8192, 1024, 1600, 256), (16384, 1024, 1600, 256), (16384, 512, 1024, 256), (8192, 1024, 1600, 128), (8192, 8192, 8192, 256)):
+        for (M, N, K, tn) in ((8192, 1024, 1600, 256), (16384, 1024, 1600, 256), (16384, 512, 1024, 256), (8192, 1024, 1600, 128), (8192, 8192, 8192, 256),
+                              (8192, 1024, 1600, 512), (16384, 1024, 1600, 512), (16384, 512, 1024, 512), (8192, 8192, 8192, 512)):
             A = torch.randn(M, K, device="cuda").bfloat16()
             B = torch.randn(N, K, device="cuda").bfloat16()
             Cc = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
@@ -247,6 +248,44 @@ def run_case(case):
                   f"({5 * fwd_flop * n / ms_t / 1e9:.1f} TFLOP/s, {n / ms_t * 1e3:.3g} samples/s)", flush=True)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(out, open(os.path.join(ROOT, "gpurun_out", "net_perf.json"), "w"), indent=1)
+    elif case == "profile":   # in-situ launch times of the backward pass (CUDA events between the launches)
+        from maze_b200.dqn_net import DQNNet
+        n = int(os.environ.get("NET_BATCH", "8192"))
+        net = DQNNet("cuda", max_batch=n, seed=6)
+        b = make_batch(n, seed=30)
+        net.profile(True)
+        acc = {}
+        order = []
+        reps = 20
+        for it in range(reps + 5):
+            net.forward(b["vec"], b["pwin"])
+            net.train_step(b["vec"], b["pwin"], b["nvec"], b["pnwin"], b["action"], b["reward"], gamma=0.9, lr=1e-4)
+            rows = net.profile_read()
+            if it >= 5:
+                for i, (label, ms) in enumerate(rows):
+                    key = (i, label)
+                    if key not in acc:
+                        acc[key] = []
+                        order.append(key)
+                    acc[key].append(ms)
+        net.profile(False)
+        total = 0.0
+        lines = []
+        by_label = {}
+        for key in order:
+            v = sorted(acc[key])
+            med = v[len(v) // 2]
+            total += med
+            by_label.setdefault(key[1], [0.0, 0])
+            by_label[key[1]][0] += med
+            by_label[key[1]][1] += 1
+        for label, (ms, cnt) in by_label.items():
+            lines.append(f"{ms * 1e3:9.1f} us  {cnt:3d} x  {label}")
+        lines.append(f"{total * 1e3:9.1f} us  backward pass, sum of medians over {reps} steps (n = {n}, pairs {'off' if os.environ.get('MAZE_NET_NO_PAIRS') else 'on'}, chunk rows {os.environ.get('MAZE_NET_CHUNK_ROWS', 'default')})")
+        print("\n".join(lines), flush=True)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        tag = ("nopairs" if os.environ.get("MAZE_NET_NO_PAIRS") else "pairs") + "_chunk" + os.environ.get("MAZE_NET_CHUNK_ROWS", "default")
+        open(os.path.join(ROOT, "gpurun_out", f"net_insitu_{tag}_n{n}.txt"), "w").write("\n".join(lines) + "\n")
     elif case == "trainloop":   # a short loop for the ncu launch list
         from maze_b200.dqn_net import DQNNet
         n = int(os.environ.get("NET_BATCH", "8192"))
