@@ -32,6 +32,28 @@ enum { EPI_BIAS_ACT = 0, EPI_MASK = 1, EPI_RED_F32 = 2 };
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
 constexpr float LRELU_SLOPE = 0.01f;   // nn.LeakyReLU() default (ddqn_agent.py:28,38)
 
+// Every kernel of the train step can be launched with programmatic stream serialization (MAZE_NET_PDL=1): its CTAs may
+// become resident, set up barriers / TMEM / shared memory, and then sit in tc::pdl_wait() until the previous kernel of the
+// stream has finished, so that launch latency and prologue overlap the predecessor's tail.  Measured on the train step it
+// buys nothing (0.489 ms with, 0.483 ms without; the policy forward got slower, 0.093 vs 0.082 ms: early-resident CTAs
+// take shared memory and TMEM from the kernel that is still running), so it is off by default; without the attribute
+// griddepcontrol.wait / launch_dependents are no-ops.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool pdl = [] { const char* e = getenv("MAZE_NET_PDL"); return e && *e && *e != '0'; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct GemmArgs {
     int M, N, K;          // C[M, N] = A[M, K] . B[N, K]^T
     void* C;              // bf16 (EPI_BIAS_ACT, EPI_MASK) or fp32 accumulators (EPI_RED_F32)
@@ -57,14 +79,19 @@ struct GemmCfg {
 //              of 64 K-rows x 64 M (N)-elements; inside a box the 8-row swizzle atoms follow each other along K
 //              (stride-dimension offset 1024), the boxes along M / N (leading-dimension offset 8192); one UMMA of
 //              K = 16 starts 16 rows = 2048 bytes further.  No transposed copies of the activations are needed.
-// The bf16 epilogues of one accumulator tile for one thread (= one output row; 32 columns per TMEM load).  The main loop
-// saturates L2 -> SM bandwidth, so a global load issued from here waits microseconds: the bias slice of the tile is staged
-// in shared memory by the caller (`sb`, zero beyond N, or nullptr), and the stored activations of EPI_MASK are fetched one
-// 32-column chunk ahead of their use.  (With per-element __ldg of the bias the fc1 forward GEMM took 90 us instead of 50.)
+// The bf16 epilogues of one accumulator tile for one warp (32 rows; lane = row; 32 columns per TMEM load).  The main loop
+// saturates L2 -> SM bandwidth, so a global load issued from here waits microseconds, and a store of one 16-byte piece per
+// lane touches 32 lines per instruction.  Hence: the bias slice of the tile is staged in shared memory by the caller
+// (`sb`, zero beyond N, or nullptr); the stored activations of EPI_MASK are fetched one 32-column chunk ahead of their
+// use; and the output leaves through a TMA store -- 64 columns x 32 rows are packed to bf16, written to the warp's own
+// 4 KB staging tile in the 128-byte swizzle the tensor map expects (conflict-free: lane r writes piece p at p ^ (r & 7)),
+// and one lane issues cp.async.bulk.tensor (rows >= M / columns >= N are clipped by the TMA unit).
+// (Per-element __ldg of the bias: fc1 forward 90 us instead of 50; per-lane 16-byte stores: fc2 backward-data 25 us.)
 template <int EPI, int BN>
-__device__ __forceinline__ void epi_bf16_tile(const GemmArgs& g, uint32_t taddr, int row, int n0, const float* sb) {
+__device__ __forceinline__ void epi_bf16_tile(const GemmArgs& g, const CUtensorMap* tmC, uint32_t taddr, int row0, int lane, int n0, const float* sb,
+                                              uint8_t* stage) {
+    const int row = row0 + lane;
     const bool row_ok = row < g.M;
-    bf16* crow = reinterpret_cast<bf16*>(g.C) + (size_t)row * g.ldc + n0;
     const bf16* arow = g.aux + (size_t)row * g.ldaux + n0;
     const float neg = g.act == ACT_LRELU ? LRELU_SLOPE : 0.f;
     uint4 h[4], hn[4];
@@ -77,48 +104,58 @@ __device__ __forceinline__ void epi_bf16_tile(const GemmArgs& g, uint32_t taddr,
     };
     if constexpr (EPI == EPI_MASK) load_aux(h, 0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += 64) {
         if (n0 + c0 >= g.N) break;
-        uint32_t v[32];
-        tc::tmem_ld32(taddr + (uint32_t)c0, v);
-        if constexpr (EPI == EPI_MASK) {
-            if (c0 + 32 < BN) load_aux(hn, c0 + 32);
-        }
-        tc::tmem_ld_wait();
-        uint32_t packed[16];
-        if constexpr (EPI == EPI_BIAS_ACT) {
+        uint32_t packed[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (sb) b = *reinterpret_cast<const float4*>(sb + c0 + j);
-                float x[4] = {__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y, __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (g.act == ACT_LRELU) x[u] = x[u] > 0.f ? x[u] : LRELU_SLOPE * x[u];
-                    else if (g.act == ACT_RELU) x[u] = fmaxf(x[u], 0.f);
-                }
-                packed[j >> 1] = tc::pack_bf16x2(x[0], x[1]);
-                packed[(j >> 1) + 1] = tc::pack_bf16x2(x[2], x[3]);
+        for (int half = 0; half < 2; ++half) {
+            const int cc = c0 + 32 * half;
+            uint32_t v[32];
+            tc::tmem_ld32(taddr + (uint32_t)cc, v);
+            if constexpr (EPI == EPI_MASK) {
+                if (cc + 32 < BN) load_aux(hn, cc + 32);
             }
-        } else {   // EPI_MASK: dL/d(pre-activation) = dL/d(activation) * act'(pre), sign taken from the stored activation
+            tc::tmem_ld_wait();
+            if constexpr (EPI == EPI_BIAS_ACT) {
 #pragma unroll
-            for (int u8 = 0; u8 < 4; ++u8) {
-                const uint32_t hw[4] = {h[u8].x, h[u8].y, h[u8].z, h[u8].w};
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (sb) b = *reinterpret_cast<const float4*>(sb + cc + j);
+                    float x[4] = {__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y, __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // bf16 sign/zero test on the raw bits: > 0 <=> sign clear and magnitude non-zero
-                    const uint32_t lo = hw[u] & 0xffffu, hi = hw[u] >> 16;
-                    const float f0 = (lo != 0 && lo < 0x8000u) ? 1.f : neg, f1 = (hi != 0 && hi < 0x8000u) ? 1.f : neg;
-                    packed[4 * u8 + u] = tc::pack_bf16x2(__uint_as_float(v[8 * u8 + 2 * u]) * f0, __uint_as_float(v[8 * u8 + 2 * u + 1]) * f1);
+                    for (int u = 0; u < 4; ++u) {
+                        if (g.act == ACT_LRELU) x[u] = x[u] > 0.f ? x[u] : LRELU_SLOPE * x[u];
+                        else if (g.act == ACT_RELU) x[u] = fmaxf(x[u], 0.f);
+                    }
+                    packed[16 * half + (j >> 1)] = tc::pack_bf16x2(x[0], x[1]);
+                    packed[16 * half + (j >> 1) + 1] = tc::pack_bf16x2(x[2], x[3]);
                 }
+            } else {   // EPI_MASK: dL/d(pre-activation) = dL/d(activation) * act'(pre), sign taken from the stored activation
+#pragma unroll
+                for (int u8 = 0; u8 < 4; ++u8) {
+                    const uint32_t hw[4] = {h[u8].x, h[u8].y, h[u8].z, h[u8].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        // bf16 sign/zero test on the raw bits: > 0 <=> sign clear and magnitude non-zero
+                        const uint32_t lo = hw[u] & 0xffffu, hi = hw[u] >> 16;
+                        const float f0 = (lo != 0 && lo < 0x8000u) ? 1.f : neg, f1 = (hi != 0 && hi < 0x8000u) ? 1.f : neg;
+                        packed[16 * half + 4 * u8 + u] = tc::pack_bf16x2(__uint_as_float(v[8 * u8 + 2 * u]) * f0, __uint_as_float(v[8 * u8 + 2 * u + 1]) * f1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) h[u] = hn[u];
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) h[u] = hn[u];
         }
+        if (lane == 0) tc::tma_store_wait_read();   // the previous store has read the staging tile
+        __syncwarp();
 #pragma unroll
-        for (int j8 = 0; j8 < 32; j8 += 8) {
-            if (row_ok && n0 + c0 + j8 + 8 <= g.N)
-                *reinterpret_cast<uint4*>(crow + c0 + j8) = make_uint4(packed[j8 >> 1], packed[(j8 >> 1) + 1], packed[(j8 >> 1) + 2], packed[(j8 >> 1) + 3]);
+        for (int pc = 0; pc < 8; ++pc)
+            *reinterpret_cast<uint4*>(stage + lane * 128 + ((pc ^ (lane & 7)) << 4)) = make_uint4(packed[4 * pc], packed[4 * pc + 1], packed[4 * pc + 2], packed[4 * pc + 3]);
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tc::tma_store_2d(tmC, tc::smem_u32(stage), n0 + c0, row0);
+            tc::tma_store_commit();
         }
     }
 }
@@ -133,7 +170,8 @@ __device__ __forceinline__ void stage_bias(const GemmArgs& g, float* sb, int n0,
 
 template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                const GemmArgs g) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t ACC_COLS = 2 * BN;   // two accumulator stages: the epilogue of tile i overlaps the main loop of tile i + 1
@@ -141,6 +179,7 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ uint64_t bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_bias[2][BN];   // the tile's bias slice, per accumulator stage
+    __shared__ __align__(1024) uint8_t s_stage[EPI == EPI_RED_F32 ? 1 : 4][EPI == EPI_RED_F32 ? 1024 : 4096];   // per epilogue warp: 32 rows x 64 bf16, swizzled
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms are 1024-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; tile t = (split, n block, m block) with the m block
@@ -171,6 +210,8 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    tc::pdl_wait();   // nothing above touches global memory
+    tc::pdl_launch();
     const uint32_t tmem_base = tmem_slot;
 
     auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& nkb) {
@@ -265,13 +306,14 @@ net_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             } else {
-                epi_bf16_tile<EPI, BN>(g, taddr, row, n0, has_bias ? s_bias[acc] : nullptr);
+                epi_bf16_tile<EPI, BN>(g, &tmC, taddr, m0 + q * 32, lane, n0, has_bias ? s_bias[acc] : nullptr, s_stage[warp - 2]);
             }
             // every value of this accumulator stage is in registers: hand the stage back to the MMA issuer
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty0 + 8 * acc);
         }
+        if (EPI != EPI_RED_F32 && lane == 0) tc::tma_store_wait_all();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -295,12 +337,14 @@ constexpr size_t PAIR_SMEM = (size_t)PAIR_STAGES * PAIR_STAGE_BYTES + 1024;
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-net_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+net_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                     const GemmArgs g) {
     constexpr int BN = 256;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[2 * PAIR_STAGES + 4];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_bias[2][BN];
+    __shared__ __align__(1024) uint8_t s_stage[4][4096];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
@@ -333,6 +377,8 @@ net_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     tc::cluster_sync();   // both CTAs' barriers are initialised before anything arrives on them from the peer
     tc::tc_fence_after();
+    tc::pdl_wait();
+    tc::pdl_launch();
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
@@ -384,11 +430,13 @@ net_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (has_bias) stage_bias<BN>(g, s_bias[acc], n0, (warp - 2) * 32 + lane);
             tc::mbar_wait(acc_full0 + 8 * acc, (local >> 1) & 1u);
             tc::tc_fence_after();
-            epi_bf16_tile<EPI, BN>(g, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, m0 + q * 32 + lane, n0, has_bias ? s_bias[acc] : nullptr);
+            epi_bf16_tile<EPI, BN>(g, &tmC, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, m0 + q * 32, lane, n0, has_bias ? s_bias[acc] : nullptr,
+                                   s_stage[warp - 2]);
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(tc::mapa(acc_empty0 + 8 * acc, 0));   // the leader's barrier collects both CTAs
         }
+        if (lane == 0) tc::tma_store_wait_all();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -441,6 +489,10 @@ int launch_gemm_t(maze_ctx* ctx, const bf16* A, int lda, const bf16* B, int ldb,
         if (int rc = make_map(ctx, &ta, A, g.K, g.M, lda, 64)) return rc;
         if (int rc = make_map(ctx, &tb, B, g.K, g.N, ldb, 64)) return rc;
     }
+    CUtensorMap tc_out = ta;   // unused by the accumulate epilogue
+    if constexpr (EPI != EPI_RED_F32) {
+        if (int rc = make_map(ctx, &tc_out, g.C, g.M, g.N, g.ldc, 32)) return rc;
+    }
     MAZE_CHECK(cudaFuncSetAttribute(net_gemm_kernel<BN, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::SMEM));
     const int nkb = (g.K + BK - 1) / BK;
     if (splits < 1) splits = 1;
@@ -449,22 +501,21 @@ int launch_gemm_t(maze_ctx* ctx, const bf16* A, int lda, const bf16* B, int ldb,
     ga.splits = splits;
     const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * splits;
     const int grid = num_tiles < ctx->num_sms ? num_tiles : ctx->num_sms;   // persistent: one CTA per SM walks the tiles
-    net_gemm_kernel<BN, EPI, MN><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, st>>>(ta, tb, ga);
-    MAZE_CHECK(cudaGetLastError());
+    MAZE_CHECK(launch_pdl(net_gemm_kernel<BN, EPI, MN>, dim3(grid), dim3(GEMM_THREADS), GemmCfg<BN>::SMEM, st, ta, tb, tc_out, ga));
     return 0;
 }
 
 template <int EPI>
 int launch_gemm_pair(maze_ctx* ctx, const bf16* A, int lda, const bf16* B, int ldb, const GemmArgs& g, cudaStream_t st) {
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc_out;
     if (int rc = make_map(ctx, &ta, A, g.M, g.K, lda, 128)) return rc;
     if (int rc = make_map(ctx, &tb, B, g.N, g.K, ldb, 128)) return rc;
+    if (int rc = make_map(ctx, &tc_out, g.C, g.M, g.N, g.ldc, 32)) return rc;
     MAZE_CHECK(cudaFuncSetAttribute(net_gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
     const int num_tiles = ((g.M + 255) / 256) * ((g.N + 255) / 256);
     int pairs = ctx->num_sms / 2;
     if (num_tiles < pairs) pairs = num_tiles;
-    net_gemm_pair_kernel<EPI><<<2 * pairs, GEMM_THREADS, PAIR_SMEM, st>>>(ta, tb, g);
-    MAZE_CHECK(cudaGetLastError());
+    MAZE_CHECK(launch_pdl(net_gemm_pair_kernel<EPI>, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM, st, ta, tb, tc_out, g));
     return 0;
 }
 
@@ -544,6 +595,8 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
         tc::tmem_relinquish();
     }
     for (int i = tid * 16; i < FEAT_R_BYTES; i += FEAT_THREADS * 16) *reinterpret_cast<uint4*>(sR + i) = make_uint4(0, 0, 0, 0);
+    tc::pdl_wait();
+    tc::pdl_launch();
     // weight slices: sW[dy][o][kk] = conv_w[o][c][dy][dx], kk = c * 3 + dx (Conv2d.weight is [32, 3, 3, 3])
     for (int i = tid; i < 3 * 32 * 16; i += FEAT_THREADS) {
         const int dy = i / 512, o = (i >> 4) & 31, kk = i & 15;
@@ -712,6 +765,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(HEAD_THREADS)
 net_head_q_kernel(const bf16* __restrict__ h2, int n, const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ q) {
     __shared__ __align__(16) float sw[4 * NET_H2];
+    tc::pdl_wait();
+    tc::pdl_launch();
     for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS) sw[i] = w3[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -735,6 +790,8 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
                      float* __restrict__ gw3, float* __restrict__ gb3, float* __restrict__ loss, float* __restrict__ qsa_out) {
     __shared__ __align__(16) float sw[4 * NET_H2], stw[4 * NET_H2], sgw[4 * NET_H2];
     __shared__ float sgb[4], sloss;
+    tc::pdl_wait();
+    tc::pdl_launch();
     for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS) {
         sw[i] = w3[i];
         stw[i] = tw3[i];
@@ -815,30 +872,43 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
 }
 
 // ------------------------------------------------------------------------------------------------------
-// out[c] += sum_r in[r, c]: the bias gradients (column sums of dL/d pre-activation).  One CTA per 64 columns x 512 rows.
+// out[c] += sum_r in[r, c]: the bias gradients (column sums of dL/d pre-activation).  One CTA per 256 columns x 64 rows:
+// a warp reads 512 contiguous bytes of a row (16 bytes per lane) and keeps its eight row loads in flight together -- the
+// first version walked 64 rows per warp one 4-byte load at a time (12 us for 8 MB: a latency chain, not bandwidth).
+constexpr int COLSUM_COLS = 256, COLSUM_ROWS = 64;
 __global__ void __launch_bounds__(256)
 net_colsum_kernel(const bf16* __restrict__ in, int R, int C, int ld, float* __restrict__ out) {
-    __shared__ float part[8][64];
-    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 512;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // a warp reads 64 consecutive columns (two per lane) of one row
-    float a0 = 0.f, a1 = 0.f;
-    const int c = c0 + 2 * tx;
-    if (c < C) {
-        for (int r = r0 + ty; r < min(R, r0 + 512); r += 8) {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(in + (size_t)r * ld + c));
-            a0 += __uint_as_float(w << 16);
-            a1 += __uint_as_float(w & 0xffff0000u);
+    __shared__ float part[8][COLSUM_COLS];
+    tc::pdl_wait();
+    tc::pdl_launch();
+    const int c0 = blockIdx.x * COLSUM_COLS, r0 = blockIdx.y * COLSUM_ROWS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = c0 + 8 * lane;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c + 8 <= C) {
+        uint4 v[COLSUM_ROWS / 8];
+#pragma unroll
+        for (int i = 0; i < COLSUM_ROWS / 8; ++i) {
+            const int r = r0 + warp + 8 * i;
+            v[i] = r < R ? __ldg(reinterpret_cast<const uint4*>(in + (size_t)r * ld + c)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < COLSUM_ROWS / 8; ++i) {
+            const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc[2 * u] += __uint_as_float(w[u] << 16);
+                acc[2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
+            }
         }
     }
-    part[ty][2 * tx] = a0;
-    part[ty][2 * tx + 1] = a1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        float v = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v += part[k][threadIdx.x];
-        if (c0 + (int)threadIdx.x < C && v != 0.f) atomicAdd(out + c0 + threadIdx.x, v);
-    }
+    for (int u = 0; u < 8; ++u) part[warp][8 * lane + u] = acc[u];
+    __syncthreads();
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += part[k][threadIdx.x];
+    if (c0 + (int)threadIdx.x < C && v != 0.f) atomicAdd(out + c0 + threadIdx.x, v);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -977,6 +1047,8 @@ net_conv_bwd_tc_kernel(const bf16* __restrict__ dX, const uint8_t* __restrict__ 
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    tc::pdl_wait();
+    tc::pdl_launch();
     const uint32_t tmem_base = tmem_slot;
     const uint32_t bar_a = tc::smem_u32(&bar);
     // A units of this thread: channel o, pooled row py, half h (14 units per channel over 8 thread groups)
@@ -1114,6 +1186,8 @@ __global__ void __launch_bounds__(256)
 net_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int count, float lr, float beta1,
                  float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float clamp) {
     const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
+    tc::pdl_wait();
+    tc::pdl_launch();
     if (i >= count) return;
     float4 P = *reinterpret_cast<float4*>(p + i), G = *reinterpret_cast<float4*>(g + i), M = *reinterpret_cast<float4*>(m + i),
            V = *reinterpret_cast<float4*>(v + i);
@@ -1142,6 +1216,8 @@ net_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
 __global__ void __launch_bounds__(256)
 net_refresh_kernel(const float* __restrict__ w, int R, int C, bf16* __restrict__ wb, bf16* __restrict__ wt) {
     __shared__ float tile[32][33];
+    tc::pdl_wait();
+    tc::pdl_launch();
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int i = ty; i < 32; i += 8) {
@@ -1278,11 +1354,8 @@ inline void prof_mark(maze_ctx* ctx, cudaStream_t st, const char* label) {
 int features(maze_ctx* ctx, bool save_idx, const float* vec, const uint32_t* win, int n, const float* params, bf16* X, uint8_t* idx, cudaStream_t st) {
     const int pairs = (n + 1) / 2;   // two samples per iteration
     const int grid = pairs < ctx->num_sms * 4 ? pairs : ctx->num_sms * 4;   // 128 TMEM columns per CTA: four CTAs per SM
-    if (save_idx)
-        net_features_kernel<true><<<grid, FEAT_THREADS, 0, st>>>(vec, win, n, params + MAZE_NET_OFF_CONV_W, params + MAZE_NET_OFF_CONV_B, X, idx);
-    else
-        net_features_kernel<false><<<grid, FEAT_THREADS, 0, st>>>(vec, win, n, params + MAZE_NET_OFF_CONV_W, params + MAZE_NET_OFF_CONV_B, X, idx);
-    MAZE_CHECK(cudaGetLastError());
+    MAZE_CHECK(launch_pdl(save_idx ? net_features_kernel<true> : net_features_kernel<false>, dim3(grid), dim3(FEAT_THREADS), 0, st, vec, win, n,
+                          params + MAZE_NET_OFF_CONV_W, params + MAZE_NET_OFF_CONV_B, X, idx));
     prof_mark(ctx, st, save_idx ? "features (conv + pool, saves argmax)" : "features (conv + pool)");
     return 0;
 }
@@ -1347,8 +1420,8 @@ extern "C" int maze_dqn_net_refresh(maze_ctx* ctx, const maze_dqn_net* net, int 
     bf16* w2b = reinterpret_cast<bf16*>(which ? net->tw2_bf16 : net->w2_bf16);
     bf16* w1t = which ? nullptr : reinterpret_cast<bf16*>(net->w1t_bf16);
     bf16* w2t = which ? nullptr : reinterpret_cast<bf16*>(net->w2t_bf16);
-    net_refresh_kernel<<<dim3(NET_IN / 32, NET_H1 / 32), 256, 0, st>>>(p + MAZE_NET_OFF_W1, NET_H1, NET_IN, w1b, w1t);
-    net_refresh_kernel<<<dim3(NET_H1 / 32, NET_H2 / 32), 256, 0, st>>>(p + MAZE_NET_OFF_W2, NET_H2, NET_H1, w2b, w2t);
+    MAZE_CHECK(launch_pdl(net_refresh_kernel, dim3(NET_IN / 32, NET_H1 / 32), dim3(256), 0, st, p + MAZE_NET_OFF_W1, NET_H1, NET_IN, w1b, w1t));
+    MAZE_CHECK(launch_pdl(net_refresh_kernel, dim3(NET_H1 / 32, NET_H2 / 32), dim3(256), 0, st, p + MAZE_NET_OFF_W2, NET_H2, NET_H1, w2b, w2t));
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1378,8 +1451,7 @@ extern "C" int maze_dqn_forward(maze_ctx* ctx, const maze_dqn_net* net, int whic
                              reinterpret_cast<const bf16*>(which ? net->tw2_bf16 : net->w2_bf16), p, w.h1, w.h2, st))
         return rc;
     const int grid = (n + 7) / 8 < ctx->num_sms * 4 ? (n + 7) / 8 : ctx->num_sms * 4;
-    net_head_q_kernel<<<grid, HEAD_THREADS, 0, st>>>(w.h2, n, p + MAZE_NET_OFF_W3, p + MAZE_NET_OFF_B3, q_out);
-    MAZE_CHECK(cudaGetLastError());
+    MAZE_CHECK(launch_pdl(net_head_q_kernel, dim3(grid), dim3(HEAD_THREADS), 0, st, w.h2, n, p + MAZE_NET_OFF_W3, p + MAZE_NET_OFF_B3, q_out));
     return 0;
 }
 
@@ -1420,17 +1492,16 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
     }
     {
         const int grid = (n + 7) / 8 < ctx->num_sms ? (n + 7) / 8 : ctx->num_sms;   // one CTA per SM: the fc3 gradient is merged with one atomic per CTA and entry
-        net_head_loss_kernel<<<grid, HEAD_THREADS, 0, st>>>(w.h2, w.h2 + np * NET_H2, w.h2_tn, n, p + MAZE_NET_OFF_W3, p + MAZE_NET_OFF_B3,
-                                                           net->target + MAZE_NET_OFF_W3, net->target + MAZE_NET_OFF_B3, action, reward, gamma,
-                                                           w.dh2, gr + MAZE_NET_OFF_W3, gr + MAZE_NET_OFF_B3, net->loss, qsa_out);
-        MAZE_CHECK(cudaGetLastError());
+        MAZE_CHECK(launch_pdl(net_head_loss_kernel, dim3(grid), dim3(HEAD_THREADS), 0, st, w.h2, w.h2 + np * NET_H2, w.h2_tn, n, p + MAZE_NET_OFF_W3,
+                              p + MAZE_NET_OFF_B3, net->target + MAZE_NET_OFF_W3, net->target + MAZE_NET_OFF_B3, action, reward, gamma, w.dh2,
+                              gr + MAZE_NET_OFF_W3, gr + MAZE_NET_OFF_B3, net->loss, qsa_out));
         prof_mark(ctx, st, "head: Q, double-Q target, loss, dQ, fc3 gradients");
     }
     // fc2: dW2 = dh2^T . h1 (MN-major operands: straight from the [n, features] activations), db2 = colsum(dh2),
     //      dh1 = (dh2 . W2) * LeakyReLU'(h1)
     const int splits = n >= 4096 ? 4 : (n >= 1024 ? 2 : 1);
-    net_colsum_kernel<<<dim3(NET_H2 / 64, (n + 511) / 512), 256, 0, st>>>(w.dh2, n, NET_H2, NET_H2, gr + MAZE_NET_OFF_B2);
-    MAZE_CHECK(cudaGetLastError());
+    MAZE_CHECK(launch_pdl(net_colsum_kernel, dim3(NET_H2 / COLSUM_COLS, (n + COLSUM_ROWS - 1) / COLSUM_ROWS), dim3(256), 0, st, w.dh2, n, NET_H2, NET_H2,
+                          gr + MAZE_NET_OFF_B2));
     prof_mark(ctx, st, "fc2 bias gradient (column sums)");
     GemmArgs g{};
     g.M = NET_H2; g.N = NET_H1; g.K = n; g.C = gr + MAZE_NET_OFF_W2; g.ldc = NET_H1;
@@ -1441,8 +1512,8 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
     if (int rc = launch_gemm(ctx, EPI_MASK, fc_tile(n), w.dh2, NET_H2, w2t, NET_H2, g, 1, st)) return rc;
     prof_mark(ctx, st, "fc2 backward-data GEMM (masked)");
     // fc1: dW1 = dh1^T . X, db1 = colsum(dh1), dX = dh1 . W1
-    net_colsum_kernel<<<dim3(NET_H1 / 64, (n + 511) / 512), 256, 0, st>>>(w.dh1, n, NET_H1, NET_H1, gr + MAZE_NET_OFF_B1);
-    MAZE_CHECK(cudaGetLastError());
+    MAZE_CHECK(launch_pdl(net_colsum_kernel, dim3(NET_H1 / COLSUM_COLS, (n + COLSUM_ROWS - 1) / COLSUM_ROWS), dim3(256), 0, st, w.dh1, n, NET_H1, NET_H1,
+                          gr + MAZE_NET_OFF_B1));
     prof_mark(ctx, st, "fc1 bias gradient (column sums)");
     g = GemmArgs{};
     g.M = NET_H1; g.N = NET_IN; g.K = n; g.C = gr + MAZE_NET_OFF_W1; g.ldc = NET_IN;
@@ -1463,8 +1534,8 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
     } else {
         MAZE_CHECK(cudaFuncSetAttribute(net_conv_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM));
         const int grid = n < ctx->num_sms * 3 ? n : ctx->num_sms * 3;   // 48 KB of operands + 9 KB of staging per CTA: three fit an SM
-        net_conv_bwd_tc_kernel<<<grid, CB_THREADS, CB_SMEM, st>>>(w.dX, w.idx, win, n, gr + MAZE_NET_OFF_CONV_W, gr + MAZE_NET_OFF_CONV_B);
-        MAZE_CHECK(cudaGetLastError());
+        MAZE_CHECK(launch_pdl(net_conv_bwd_tc_kernel, dim3(grid), dim3(CB_THREADS), CB_SMEM, st, w.dX, w.idx, win, n, gr + MAZE_NET_OFF_CONV_W,
+                              gr + MAZE_NET_OFF_CONV_B));
     }
     prof_mark(ctx, st, "conv gradient (un-pool + implicit GEMM)");
     return 0;
@@ -1513,9 +1584,8 @@ extern "C" int maze_dqn_adamw(maze_ctx* ctx, const maze_dqn_net* net, float lr, 
     if (step < 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_adamw: step counts from 1");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-    net_adamw_kernel<<<(MAZE_NET_PARAMS / 4 + 255) / 256, 256, 0, st>>>(net->params, net->grads, net->adam_m, net->adam_v, MAZE_NET_PARAMS, lr, beta1,
-                                                                        beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, clamp);
-    MAZE_CHECK(cudaGetLastError());
+    MAZE_CHECK(launch_pdl(net_adamw_kernel, dim3((MAZE_NET_PARAMS / 4 + 255) / 256), dim3(256), 0, st, net->params, net->grads, net->adam_m, net->adam_v,
+                          (int)MAZE_NET_PARAMS, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, clamp));
     return maze_dqn_net_refresh(ctx, net, 0, stream);
 }
 
