@@ -743,6 +743,21 @@ __device__ __forceinline__ void head_load16(const bf16* row, int lane, float (&h
     }
 }
 
+// The same row as raw words (prefetch one sample ahead), and their expansion
+__device__ __forceinline__ void head_load_raw(const bf16* row, int lane, uint2 (&w)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = __ldg(reinterpret_cast<const uint2*>(row + k * 128 + lane * 4));
+}
+__device__ __forceinline__ void head_expand(const uint2 (&w)[4], float (&h)[16]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[4 * k + 0] = __uint_as_float(w[k].x << 16);
+        h[4 * k + 1] = __uint_as_float(w[k].x & 0xffff0000u);
+        h[4 * k + 2] = __uint_as_float(w[k].y << 16);
+        h[4 * k + 3] = __uint_as_float(w[k].y & 0xffff0000u);
+    }
+}
+
 __device__ __forceinline__ float head_dot(const float (&h)[16], const float* w_row, int lane) {   // w_row: 512 floats in shared memory
     float acc = 0.f;
 #pragma unroll
@@ -783,7 +798,7 @@ net_head_q_kernel(const bf16* __restrict__ h2, int n, const float* __restrict__ 
 // Loss and the gradient at the head (ddqn_agent.py:131-143): q(s, a) from the source net, a* = argmax_a' q_source(s', a'),
 // y = r + gamma * q_target(s', a*), loss = mean (q(s, a) - y)^2.  Writes dL/d(pre-ReLU h2) [n, 512] bf16 and accumulates the
 // fc3 gradients.
-__global__ void __launch_bounds__(HEAD_THREADS)
+__global__ void __launch_bounds__(HEAD_THREADS, 2)
 net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_sn, const bf16* __restrict__ h2_tn, int n,
                      const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ tw3, const float* __restrict__ tb3,
                      const uint8_t* __restrict__ action, const float* __restrict__ reward, float gamma, bf16* __restrict__ dh2,
@@ -802,19 +817,38 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const float inv_n = 1.f / (float)n;
-    float gacc[4][16];   // this lane's 16 columns of d fc3.weight, per action (the action is uniform over the warp)
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) gacc[a][i] = 0.f;
+    // d fc3.weight is summed in shared memory, in lane-major order (entry (a, i, lane) <-> column head_col(lane, i)): one
+    // conflict-free shared atomic per owned column and sample, and no 64 accumulator registers beside the prefetch.
     float gb_acc = 0.f, loss_acc = 0.f;   // lane a < 4 collects d fc3.bias[a]; lane 0 the loss
-    for (int s = blockIdx.x * (HEAD_THREADS / 32) + (threadIdx.x >> 5); s < n; s += gridDim.x * (HEAD_THREADS / 32)) {
+    // The loop is a chain of global loads -> dot products -> butterfly sums with two CTAs of eight warps per SM: the next
+    // sample's three rows are fetched while the current one is reduced (ncu r02t: 82 % of the cycles had no eligible warp).
+    const int stride = gridDim.x * (HEAD_THREADS / 32);
+    int s = blockIdx.x * (HEAD_THREADS / 32) + (threadIdx.x >> 5);
+    uint2 ra[4], rb[4], rc[4];
+    int act_next = 0;
+    float rew_next = 0.f;
+    if (s < n) {
+        head_load_raw(h2_s + (size_t)s * NET_H2, lane, ra);
+        head_load_raw(h2_sn + (size_t)s * NET_H2, lane, rb);
+        head_load_raw(h2_tn + (size_t)s * NET_H2, lane, rc);
+        act_next = action[s] & 3;
+        rew_next = reward[s];
+    }
+    for (; s < n; s += stride) {
         float h[16], hn[16], ht[16];
-        head_load16(h2_s + (size_t)s * NET_H2, lane, h);
-        head_load16(h2_sn + (size_t)s * NET_H2, lane, hn);
-        head_load16(h2_tn + (size_t)s * NET_H2, lane, ht);
-        const int act = action[s] & 3;
-        const float rew = reward[s];
+        head_expand(ra, h);
+        head_expand(rb, hn);
+        head_expand(rc, ht);
+        const int act = act_next;
+        const float rew = rew_next;
+        if (s + stride < n) {
+            const size_t t = (size_t)(s + stride);
+            head_load_raw(h2_s + t * NET_H2, lane, ra);
+            head_load_raw(h2_sn + t * NET_H2, lane, rb);
+            head_load_raw(h2_tn + t * NET_H2, lane, rc);
+            act_next = action[t] & 3;
+            rew_next = reward[t];
+        }
         float qs[4], qn[4], qt[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -846,27 +880,19 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
             *reinterpret_cast<uint2*>(dh2 + (size_t)s * NET_H2 + k * 128 + lane * 4) = out;
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-            if (act == a) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) gacc[a][i] = fmaf(gq, h[i], gacc[a][i]);
-            }
+        for (int i = 0; i < 16; ++i)
+            if (h[i] != 0.f) atomicAdd(&sgw[act * NET_H2 + i * 32 + lane], gq * h[i]);
         if (lane == act) gb_acc += gq;
         if (lane == 0) {
             loss_acc += d * d * inv_n;
             if (qsa_out) qsa_out[s] = qsa;
         }
     }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (gacc[a][i] != 0.f) atomicAdd(&sgw[a * NET_H2 + head_col(lane, i)], gacc[a][i]);
     if (lane < 4 && gb_acc != 0.f) atomicAdd(&sgb[lane], gb_acc);
     if (lane == 0) atomicAdd(&sloss, loss_acc);
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS)
-        if (sgw[i] != 0.f) atomicAdd(gw3 + i, sgw[i]);
+        if (sgw[i] != 0.f) atomicAdd(gw3 + (i >> 9) * NET_H2 + head_col(i & 31, (i >> 5) & 15), sgw[i]);
     if (threadIdx.x < 4) atomicAdd(gb3 + threadIdx.x, sgb[threadIdx.x]);
     if (threadIdx.x == 0) atomicAdd(loss, sloss);
 }
@@ -1312,6 +1338,23 @@ int check_net(maze_ctx* ctx, const maze_dqn_net* net, bool train) {
     return 0;
 }
 
+// Split-K factor of a weight-gradient GEMM (tiles x k-blocks, persistent over `sms` CTAs): the one that minimises
+// waves x (k-blocks per split + a fixed per-tile cost of about six k-blocks: pipeline fill, accumulator drain, atomics).
+// fc1 at n = 8192: 56 tiles x 128 k-blocks -> 5 splits (280 tiles, 1.9 waves) instead of 4 (224 tiles, 1.5 waves run as 2).
+int auto_splits(int base_tiles, int nkb, int sms) {
+    int best = 1;
+    float best_cost = 1e30f;
+    for (int s = 1; s <= 16 && nkb / s >= 8; ++s) {
+        const int waves = (base_tiles * s + sms - 1) / sms;
+        const float cost = (float)waves * ((float)nkb / (float)s + 6.f);
+        if (cost < best_cost * 0.98f) {   // a larger split has to pay for its extra atomics
+            best_cost = cost;
+            best = s;
+        }
+    }
+    return best;
+}
+
 // Rows per forward chunk of maze_dqn_backward (MAZE_NET_CHUNK_ROWS; a multiple of 256; 0 = the whole batch at once).
 int fc_chunk_rows() {
     static const int rows = [] {
@@ -1491,7 +1534,7 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
         if (int rc = mlp_forward(ctx, Xt + a * NET_IN, rows, tw1b, tw2b, net->target, w.h1t_tn + a * NET_H1, w.h2_tn + a * NET_H2, st)) return rc;
     }
     {
-        const int grid = (n + 7) / 8 < ctx->num_sms ? (n + 7) / 8 : ctx->num_sms;   // one CTA per SM: the fc3 gradient is merged with one atomic per CTA and entry
+        const int grid = (n + 7) / 8 < 2 * ctx->num_sms ? (n + 7) / 8 : 2 * ctx->num_sms;   // two CTAs per SM; the fc3 gradient is merged with one atomic per CTA and entry
         MAZE_CHECK(launch_pdl(net_head_loss_kernel, dim3(grid), dim3(HEAD_THREADS), 0, st, w.h2, w.h2 + np * NET_H2, w.h2_tn, n, p + MAZE_NET_OFF_W3,
                               p + MAZE_NET_OFF_B3, net->target + MAZE_NET_OFF_W3, net->target + MAZE_NET_OFF_B3, action, reward, gamma, w.dh2,
                               gr + MAZE_NET_OFF_W3, gr + MAZE_NET_OFF_B3, net->loss, qsa_out));
@@ -1499,13 +1542,13 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
     }
     // fc2: dW2 = dh2^T . h1 (MN-major operands: straight from the [n, features] activations), db2 = colsum(dh2),
     //      dh1 = (dh2 . W2) * LeakyReLU'(h1)
-    const int splits = n >= 4096 ? 4 : (n >= 1024 ? 2 : 1);
+    const int nkb_n = (n + BK - 1) / BK;
     MAZE_CHECK(launch_pdl(net_colsum_kernel, dim3(NET_H2 / COLSUM_COLS, (n + COLSUM_ROWS - 1) / COLSUM_ROWS), dim3(256), 0, st, w.dh2, n, NET_H2, NET_H2,
                           gr + MAZE_NET_OFF_B2));
     prof_mark(ctx, st, "fc2 bias gradient (column sums)");
     GemmArgs g{};
     g.M = NET_H2; g.N = NET_H1; g.K = n; g.C = gr + MAZE_NET_OFF_W2; g.ldc = NET_H1;
-    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh2, NET_H2, w.h1, NET_H1, g, splits * 2, st, true)) return rc;
+    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh2, NET_H2, w.h1, NET_H1, g, auto_splits((NET_H2 / BM) * (NET_H1 / 256), nkb_n, ctx->num_sms), st, true)) return rc;
     prof_mark(ctx, st, "fc2 weight gradient GEMM (split-K)");
     g = GemmArgs{};
     g.M = n; g.N = NET_H1; g.K = NET_H2; g.C = w.dh1; g.ldc = NET_H1; g.aux = w.h1; g.ldaux = NET_H1; g.act = ACT_LRELU;
@@ -1517,7 +1560,7 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
     prof_mark(ctx, st, "fc1 bias gradient (column sums)");
     g = GemmArgs{};
     g.M = NET_H1; g.N = NET_IN; g.K = n; g.C = gr + MAZE_NET_OFF_W1; g.ldc = NET_IN;
-    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh1, NET_H1, w.X, NET_IN, g, splits, st, true)) return rc;
+    if (int rc = launch_gemm(ctx, EPI_RED_F32, 256, w.dh1, NET_H1, w.X, NET_IN, g, auto_splits((NET_H1 / BM) * ((NET_IN + 255) / 256), nkb_n, ctx->num_sms), st, true)) return rc;
     prof_mark(ctx, st, "fc1 weight gradient GEMM (split-K)");
     // every gradient but the conv layer's (the first MAZE_NET_OFF_W1 floats of the flat buffer) is complete here: a caller
     // that all-reduces gradients can start on grads[MAZE_NET_OFF_W1:] while the backward-data GEMM and the conv gradient run
