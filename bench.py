@@ -583,16 +583,22 @@ def run_toroidal_regen(args, rank, local_rank, world):
     if rank != 0:
         return None
     value = world * B * args.steps / (ms * 1e-3)
-    return {"metric": "env-steps/sec (toroidal 40x40 mazes, mixed generators, regeneration on win, whole job)", "value": value, "unit": UNIT,
+    fast, slow, jobs = env.regeneration_statistics()
+    regen = ({"mode": f"{env.regenerate_depth} mazes ahead per slot (shadow ring refilled on a side stream; include/maze_b200.h maze_regen_swap)",
+              "installed_from_shadow": fast,
+              "drawn_in_place": slow, "refill_jobs": jobs, "counted": "rank 0, since construction"} if env.regenerate_ahead
+             else {"mode": "in place, on the stepping stream (MAZE_REGEN_AHEAD=0)"})
+    return {"metric": "env-steps/sec (toroidal 40x40 mazes, mixed generators, regeneration on win, whole job)", "regeneration": regen, "value": value, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int32 state+obs, f64 reward", "data": "synthetic",
             "config": {"workload": f"configs[2]: toroidal 81x81-block mazes (41 logical lines), r-prim / dfs / prim&kill mixed, {B} envs and maze slots per GPU, "
-                                   "70 % best-dir following / 30 % uniform actions, every win regenerates the env's maze (maze_generate on the device queue)",
+                                   "70 % best-dir following / 30 % uniform actions, every win installs a freshly generated maze (maze_generate on the device; drawn ahead of time into a shadow ring unless MAZE_REGEN_AHEAD=0)",
                        "envs_per_gpu": B, "l2": "inputs larger than L2 (6.5 KB table + 13 KB visits per env)",
                        "parallelism": f"env-index sharding over {world} GPU(s), no per-step collective"},
             "mazes_regenerated_per_s": (s1["wins"] - s0["wins"]) / (ms * 1e-3), "episodes_per_s": (s1["episodes"] - s0["episodes"]) / (ms * 1e-3),
             "gpu_launches": args.steps * world * 4, "clocks": clocks,
-            "launches_per_step": "policy (torch elementwise ops) + maze_generate (2 kernels, device-side queue length) + queue reset + maze_step"}
+            "launches_per_step": "policy (torch elementwise ops) + maze_regen_swap + in-place maze_generate of the not-ready slots (2 kernels, usually empty) + queue resets + maze_step; "
+                                 "refills (prepare, maze_generate per ring entry, publish) on the side stream"}
 
 
 def run_curriculum_dq(args, rank, local_rank, world):

@@ -260,6 +260,32 @@ int maze_generate(maze_ctx* ctx, uint8_t* grids, int32_t* meta, uint8_t* table, 
 int maze_curriculum(maze_ctx* ctx, int32_t* meta, int32_t* wins, const int32_t* ids, const int32_t* count_dev,
                     int n, int grow, int max_h, int max_w, int wins_a, int algo_a, int wins_b, int algo_b, void* stream);
 
+/* Regeneration ahead of time (the update_maze() of off_policy_trainer.py:60-71 / :190-214 without its latency).  A
+ * shadow ring (shadow_grids / shadow_table [depth, M, slot], shadow_meta [depth, M, 8]: ring entry j of slot m at index
+ * j * M + m, same layouts as the live pool) holds for every slot the mazes its next `depth` regenerations would draw:
+ * maze_generate keys its random stream by (seed, slot id, generation count), so M(m, g) can be drawn early; it lives in
+ * entry g % depth.  ready_gen [depth, M] int32: g + 1 once the entry holds M(m, g) completely, 0 while it is being redrawn.
+ *   maze_regen_swap     (stepping stream) for the `*queue_count` winners in `queue`: copy the entry of the live generation
+ *                       count over the live slot if it is ready, else append the slot to slow_queue (the caller then
+ *                       runs maze_generate on slow_queue / slow_count in place, as without a ring); every winner is
+ *                       appended to refill_queue once per `batch` (queued_tag [M], initialised to -1).  stats [2]
+ *                       (optional) counts fast / slow slots.  slow_count must be zero on entry.
+ *   maze_regen_prepare  (side stream) for the slots of refill_queue: ring entries that already hold the maze they should
+ *                       are left alone, the others are un-published (ready_gen = 0), get the live slot's shape and
+ *                       generator and their generation count, and are appended to work_queue [depth, M] / work_count
+ *                       [depth] of their ring index.  Then, per ring index j: maze_generate(entry-j slices of the ring,
+ *                       ids = work_queue[j], count_dev = work_count + j), and
+ *   maze_regen_publish  (side stream) ready_gen = the entry's generation count for everything in the work queues.
+ * Every path installs the same maze, so results do not depend on how far the side stream is behind. */
+int maze_regen_swap(maze_ctx* ctx, uint8_t* grids, uint8_t* table, int32_t* meta, const uint8_t* shadow_grids, const uint8_t* shadow_table,
+                    const int32_t* shadow_meta, const int32_t* ready_gen, int depth, const int32_t* queue, const int32_t* queue_count, int n,
+                    int slot, int32_t* refill_queue, int32_t* refill_count, int32_t* queued_tag, int batch, int32_t* slow_queue,
+                    int32_t* slow_count, int32_t* stats, void* stream);
+int maze_regen_prepare(maze_ctx* ctx, const int32_t* meta, int32_t* shadow_meta, int32_t* ready_gen, int depth, const int32_t* refill_queue,
+                       const int32_t* refill_count, int n, int32_t* work_queue, int32_t* work_count, void* stream);
+int maze_regen_publish(maze_ctx* ctx, const int32_t* shadow_meta, int32_t* ready_gen, int depth, const int32_t* work_queue,
+                       const int32_t* work_count, int n, void* stream);
+
 /* Enriched (-v1) observation: SimpleEnrichMazeEnv._get_obs (simple_maze_env.py:151-158) and the
  * toroidal / variable-size variants (toroidal_maze_env.py:164-172, simple_variable_maze_env.py:
  * 170-179, toroidal_variable_maze_env.py:186-194) for the current position of every env:

@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -68,7 +70,8 @@ class MazeVectorEnv(_VectorBase):
                  num_mazes: Optional[int] = None, device="cuda", seed: int = 0, autoreset: bool = True,
                  on_win: str = "keep", reference_order: bool = False, stats: bool = True,
                  slot_id_base: int = 0, pool: Optional[MazePool] = None, env_maze=None, enrich: bool = False,
-                 candidates: int = 1, start_shape=None, grow: int = 0, algorithm_schedule=None, visit_layout=None):
+                 candidates: int = 1, start_shape=None, grow: int = 0, algorithm_schedule=None, visit_layout=None,
+                 regenerate_ahead: Optional[int] = None):
         """enrich=True gives the -v1 observation (normalised agent / target, 15x15 window);
         candidates=6 makes every generated maze the least difficult of six (generate_maze).
         Curriculum (on_win="regenerate"): `shape` is the maximum block shape; mazes start at
@@ -76,6 +79,9 @@ class MazeVectorEnv(_VectorBase):
         (variable-size envs: START_SHAPE and +(4, 4), simple_variable_maze_env.py:17,97);
         `algorithm_schedule` = ((wins, algorithm), ...) switches a slot's generator by its win count
         (off_policy_trainer.py:302-310: ((5, "prim&kill"), (10, "dfs"))).
+        regenerate_ahead (on_win="regenerate" without a curriculum; default 3, MAZE_REGEN_AHEAD=0 turns it off): keep
+        the next k mazes of every slot in a shadow ring that a side stream refills, so that a win costs a 13 KB copy
+        instead of the generator's latency (include/maze_b200.h: maze_regen_swap).  Same mazes either way; k x 13 KB per slot.
         visit_layout: "cell" (default; best for one launch per step), "tile" (env-major in 4 x 4 block tiles:
         best for the fused multi-step paths -- step_many, the Q-learning rollout -- and the default with
         enrich, where the 15 x 15 window then reads <= 25 whole sectors per env), "env" (env-major rows)."""
@@ -118,6 +124,11 @@ class MazeVectorEnv(_VectorBase):
         if (self.grow or self.algorithm_schedule) and on_win != "regenerate":
             raise ValueError("grow / algorithm_schedule act when a maze is regenerated: use on_win='regenerate'")
         self.wins = torch.zeros(pool.num_mazes, dtype=torch.int32, device=self.device)
+        if regenerate_ahead is None:
+            regenerate_ahead = int(os.environ.get("MAZE_REGEN_AHEAD", "3") or 0)
+        self.regenerate_depth = min(8, int(regenerate_ahead))   # True -> 1
+        self.regenerate_ahead = self.regenerate_depth > 0 and on_win == "regenerate" and not self.grow and not self.algorithm_schedule
+        self._ahead = None   # built on the first drain (and again after load_state_dict)
         if env_maze is None:
             # contiguous envs share a maze: table reads of a warp hit the same lines
             per = max(1, self.num_envs // pool.num_mazes)
@@ -206,11 +217,87 @@ class MazeVectorEnv(_VectorBase):
         in the reference, where next_obs comes from env.step() before update_maze().  The three launches are
         device-side no-ops when the queue is empty (its length is read on the device)."""
         b = self.batch
+        if self.regenerate_ahead:
+            return self._drain_ahead()
         if self.grow or self.algorithm_schedule:
             self.pool.curriculum(b.queue, b.queue_count, self.wins, self.grow, self.algorithm_schedule)
         self.pool.generate(ids=b.queue, count_dev=b.queue_count, configure=False, seed=self.seed,
                            slot_id_base=self.slot_id_base, candidates=self.candidates)
         b.queue_count.zero_()
+
+    # -- regeneration ahead of time (include/maze_b200.h: maze_regen_swap / _prepare / _publish) -------------------
+    def _build_ahead(self):
+        pool, dev, M, K = self.pool, self.device, self.pool.num_mazes, self.regenerate_depth
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        i32 = dict(dtype=torch.int32, device=dev)
+        grids = torch.zeros((K, M, pool.slot), dtype=torch.uint8, device=dev)
+        table = torch.zeros((K, M, pool.slot), dtype=torch.uint8, device=dev)
+        meta = torch.zeros((K, M, cabi.META_WORDS), **i32)
+        ctx = cabi.Context(idx)   # own work counter / scratch: the refills run beside the live pool's generator
+        live = pool.meta[:, cabi.META_SPARE]
+        ring = []
+        for j in range(K):   # ring entry j holds M(m, g) for the g in [live, live + K) with g % K == j
+            sh = MazePool.__new__(MazePool)
+            sh.device, sh.ctx, sh.max_shape, sh.num_mazes, sh.slot = dev, ctx, pool.max_shape, M, pool.slot
+            sh.grids, sh.table, sh.meta = grids[j], table[j], meta[j]
+            sh.meta.copy_(pool.meta)
+            sh.meta[:, cabi.META_SPARE] = live + torch.remainder(j - live, K)
+            sh.generate(ids=None, configure=False, seed=self.seed, slot_id_base=self.slot_id_base, candidates=self.candidates)
+            ring.append(sh)
+        a = dict(ring=ring, grids=grids, table=table, meta=meta, ctx=ctx, ready=meta[:, :, cabi.META_SPARE].clone().contiguous(),
+                 refill=[torch.zeros(M, **i32), torch.zeros(M, **i32)], refill_count=[torch.zeros(1, **i32), torch.zeros(1, **i32)],
+                 tag=torch.full((M,), -1, **i32), slow=torch.zeros(M, **i32), slow_count=torch.zeros(1, **i32),
+                 work=torch.zeros((K, M), **i32), work_count=torch.zeros(K, **i32), stats=torch.zeros(2, **i32),
+                 side=torch.cuda.Stream(device=dev), side_done=torch.cuda.Event(), main_evt=torch.cuda.Event(), cur=0, batch=0, jobs=0)
+        for t in (grids, table, meta, a["ready"], *a["refill"], *a["refill_count"], a["work"], a["work_count"], pool.meta):
+            t.record_stream(a["side"])   # the side stream reads / writes them: the allocator must not recycle them under it
+        self._ahead = a
+
+    def _drain_ahead(self):
+        if self._ahead is None:
+            self._build_ahead()
+        a, b, pool, K = self._ahead, self.batch, self.pool, self.regenerate_depth
+        cur, M = a["cur"], pool.num_mazes
+        lib, p = cabi.lib(), cabi.ptr
+        a["slow_count"].zero_()
+        rc = lib.maze_regen_swap(pool.ctx.handle, p(pool.grids), p(pool.table), p(pool.meta), p(a["grids"]), p(a["table"]), p(a["meta"]), p(a["ready"]), K,
+                                 p(b.queue), p(b.queue_count), M, pool.slot, p(a["refill"][cur]), p(a["refill_count"][cur]), p(a["tag"]), a["batch"],
+                                 p(a["slow"]), p(a["slow_count"]), p(a["stats"]), cabi.current_stream(self.device))
+        pool.ctx.check(rc, "maze_regen_swap")
+        # slots whose ring entry was not ready (more wins than the ring is deep before a refill was published): drawn in place
+        pool.generate(ids=a["slow"], count_dev=a["slow_count"], configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
+                      candidates=self.candidates)
+        b.queue_count.zero_()
+        if a["side_done"].query():   # the previous refill has finished: start the next one on what queued up meanwhile
+            main, side, ctx = torch.cuda.current_stream(self.device), a["side"], a["ctx"]
+            a["main_evt"].record(main)
+            side.wait_event(a["main_evt"])
+            with torch.cuda.stream(side):
+                rc = lib.maze_regen_prepare(ctx.handle, p(pool.meta), p(a["meta"]), p(a["ready"]), K, p(a["refill"][cur]), p(a["refill_count"][cur]), M,
+                                            p(a["work"]), p(a["work_count"]), cabi.current_stream(self.device))
+                ctx.check(rc, "maze_regen_prepare")
+                for j, sh in enumerate(a["ring"]):
+                    sh.generate(ids=a["work"][j], count_dev=a["work_count"][j:j + 1], configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
+                                candidates=self.candidates)
+                rc = lib.maze_regen_publish(ctx.handle, p(a["meta"]), p(a["ready"]), K, p(a["work"]), p(a["work_count"]), M,
+                                            cabi.current_stream(self.device))
+                ctx.check(rc, "maze_regen_publish")
+                a["refill_count"][cur].zero_()
+                a["work_count"].zero_()
+                a["side_done"].record(side)
+            a["cur"], a["batch"], a["jobs"] = cur ^ 1, a["batch"] + 1, a["jobs"] + 1
+
+    def regeneration_statistics(self):
+        """(slots installed from the shadow pool, slots drawn in place, refill jobs launched) since construction; one small D2H."""
+        if self._ahead is None:
+            return (0, 0, 0)
+        fast, slow = (int(v) for v in self._ahead["stats"].tolist())
+        return (fast, slow, self._ahead["jobs"])
+
+    def _drop_ahead(self):
+        if self._ahead is not None:
+            self._ahead["side"].synchronize()
+            self._ahead = None
 
     def step(self, actions, extra_mode: int = 0, observe: bool = True):
         """observe=False skips building the observation dict (with enrich=True: the 2.7 KB-per-env float window) and
@@ -381,6 +468,7 @@ class MazeVectorEnv(_VectorBase):
         return {"pool": self.pool.state_dict(), "batch": self.batch.state_dict(), "wins": self.wins}
 
     def load_state_dict(self, sd):
+        self._drop_ahead()   # the shadow pool is rebuilt from the loaded generation counts on the next drain
         self.pool.load_state_dict(sd["pool"])
         self.batch.load_state_dict(sd["batch"])
         self.wins.copy_(sd["wins"])
