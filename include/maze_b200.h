@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAZE_ABI_VERSION 11
+#define MAZE_ABI_VERSION 12
 
 /* argument errors */
 #define MAZE_E_NULL   (-1) /* required pointer is NULL                        */
@@ -390,8 +390,10 @@ typedef struct maze_replay {
     int32_t   without_replacement; /* 1: a batch holds n DISTINCT transitions (random.sample, lib/replay_memory.py:20-21;
                                falls back to independent draws while fewer than n are stored); 0: independent
                                uniform draws                                                        */
-    int32_t   reserved;
+    int32_t   flags;        /* MAZE_REPLAY_BORDERED: the caller promises that no maze of the batch is toroidal -- with
+                               maze_env_batch.visit_bits, maze_dqn_push then takes its two-envs-per-half-warp path      */
 } maze_replay;
+#define MAZE_REPLAY_BORDERED 1
 
 /* Encode the current observation of every env into the staging area (after maze_reset). */
 int maze_dqn_observe(maze_ctx* ctx, const maze_env_batch* b, const maze_replay* r, void* stream);

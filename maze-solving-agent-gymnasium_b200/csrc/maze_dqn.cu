@@ -30,18 +30,11 @@ struct PackedObs {
     unsigned word[3];   // even half-lane 2 k: word k of channels 0 (wall), 1 (floor), 2 (not visited); k = 0..7
 };
 
-__device__ __forceinline__ PackedObs encode_obs16(const maze_env_batch& b, int e, bool valid, int hl) {
+// Second half of the encode: the row masks of the 16 lanes -> packed words and the state vector.
+__device__ __forceinline__ PackedObs finish_obs16(const EnvState& st, const MazeView& mz, bool valid, int hl, unsigned m0, unsigned m1, unsigned m2) {
     PackedObs o;
     o.vec = 0.f;
     o.word[0] = o.word[1] = o.word[2] = 0u;
-    unsigned m0 = 0, m1 = 0, m2 = 0;
-    EnvState st{};
-    MazeView mz{};
-    if (valid) {
-        st = unpack_state(b.state[e]);
-        mz = load_maze(b, b.env_maze[e]);
-        window_row_masks(b, e, st, mz, hl, m0, m1, m2);
-    }
     // odd rows move to the even lane above them (all 32 lanes take part in the shuffles)
     const unsigned n0 = __shfl_down_sync(FULL, m0, 1), n1 = __shfl_down_sync(FULL, m1, 1), n2 = __shfl_down_sync(FULL, m2, 1);
     if (!(hl & 1)) {
@@ -58,6 +51,18 @@ __device__ __forceinline__ PackedObs encode_obs16(const maze_env_batch& b, int e
         o.vec = (float)(hl < 4 ? q : (hl == 4 ? (double)bd.x : (double)bd.y));
     }
     return o;
+}
+
+__device__ __forceinline__ PackedObs encode_obs16(const maze_env_batch& b, int e, bool valid, int hl) {
+    unsigned m0 = 0, m1 = 0, m2 = 0;
+    EnvState st{};
+    MazeView mz{};
+    if (valid) {
+        st = unpack_state(b.state[e]);
+        mz = load_maze(b, b.env_maze[e]);
+        window_row_masks(b, e, st, mz, hl, m0, m1, m2);
+    }
+    return finish_obs16(st, mz, valid, hl, m0, m1, m2);
 }
 
 __device__ __forceinline__ void store_obs16(const PackedObs& o, int hl, float* __restrict__ vec6, uint32_t* __restrict__ words24) {
@@ -79,14 +84,113 @@ maze_dqn_observe_kernel(maze_env_batch b, maze_replay r) {
     if (valid) store_obs16(o, hl, r.stage_vec + (size_t)e * 6, r.stage_win + (size_t)e * WORDS);
 }
 
-// The kernel is bound by the latency of its dependent loads (state -> maze record -> table / visit rows -> ring), not by
-// bytes or instructions (ncu, profiles/r02i_obs_details.txt: long-scoreboard stalls, 36 % occupancy).  So everything that
-// does not depend on the gather is issued before it: the slot claim (one atomicAdd per warp for its two envs) and the loads
-// of the staged observation travel while the window rows are fetched.
+// The kernel is bound by the latency of its dependent loads (state -> maze record -> table / bitmap rows -> ring), not by
+// bytes or instructions (ncu, profiles/r02i_obs_details.txt: long-scoreboard stalls, 36 % occupancy): throughput = envs in
+// flight per SM / chain latency.  So (i) everything that does not depend on the gather is issued before it -- the slot
+// claim (one atomicAdd per warp) and the loads of the staged observations travel while the window rows are fetched -- and
+// (ii) every half-warp carries TWO envs through the chain together (four per warp): each level of the chain is issued
+// for both before either is consumed, which doubles the loads in flight at the same occupancy (1.83e9 -> 3.0e9 env-steps/s
+// with the step; four envs per half-warp or more CTAs per SM at fewer registers measured slower: 2.1 - 2.7e9).  This kernel is the
+// bordered-maze / visit-bitmap case only (maze_replay.flags & MAZE_REPLAY_BORDERED: the caller's promise that no maze of the
+// batch is toroidal); maze_dqn_push_generic_kernel below handles everything else, one env per half-warp.
 constexpr int PUSH_THREADS = 256;
+constexpr int PUSH_ENVS = 2;   // envs per 16-lane group
 
 __global__ void __launch_bounds__(PUSH_THREADS, 4)
-maze_dqn_push_kernel(maze_env_batch b, maze_replay r, const uint8_t* __restrict__ actions) {
+maze_dqn_push_bordered_kernel(maze_env_batch b, maze_replay r, const uint8_t* __restrict__ actions) {
+    const int hl = threadIdx.x & 15, lane = threadIdx.x & 31;
+    const int group = blockIdx.x * (PUSH_THREADS / 16) + (threadIdx.x >> 4);
+    int e[PUSH_ENVS];
+    bool valid[PUSH_ENVS], real[PUSH_ENVS], fast[PUSH_ENVS];
+    uint64_t raw_state[PUSH_ENVS];
+    int maze_id[PUSH_ENVS];
+    // level 1: state and maze id of both envs
+#pragma unroll
+    for (int u = 0; u < PUSH_ENVS; ++u) {
+        e[u] = group * PUSH_ENVS + u;
+        valid[u] = e[u] < b.num_envs;
+        raw_state[u] = valid[u] ? b.state[e[u]] : 0ull;
+        maze_id[u] = valid[u] ? b.env_maze[e[u]] : 0;
+    }
+    EnvState st[PUSH_ENVS];
+    MazeView mz[PUSH_ENVS];
+    // level 2: maze records; the staged observations (the `state` of the transitions), action and reward
+    float sv[PUSH_ENVS];
+    uint32_t sw0[PUSH_ENVS], sw1[PUSH_ENVS];
+    uint8_t act[PUSH_ENVS];
+    float rew[PUSH_ENVS];
+#pragma unroll
+    for (int u = 0; u < PUSH_ENVS; ++u) {
+        st[u] = unpack_state(raw_state[u]);
+        real[u] = valid[u] && st[u].steps != 0;   // a real transition (steps == 0 only right after a reset)
+        mz[u] = MazeView{};
+        if (valid[u]) mz[u] = load_maze(b, maze_id[u]);
+        sv[u] = 0.f;
+        sw0[u] = sw1[u] = 0u;
+        act[u] = 0;
+        rew[u] = 0.f;
+        if (real[u]) {
+            if (hl < 6) sv[u] = r.stage_vec[(size_t)e[u] * 6 + hl];
+            sw0[u] = r.stage_win[(size_t)e[u] * WORDS + hl];
+            if (hl < WORDS - 16) sw1[u] = r.stage_win[(size_t)e[u] * WORDS + 16 + hl];
+            if (hl == 0) {
+                act[u] = actions[e[u]] & 3;
+                rew[u] = (float)b.reward[e[u]];
+            }
+        }
+    }
+    // slot claim for the (up to) four real envs of the warp: ballot bits 0 / 16 of each env index
+    unsigned real_bits[PUSH_ENVS];
+    int n_real = 0;
+#pragma unroll
+    for (int u = 0; u < PUSH_ENVS; ++u) {
+        real_bits[u] = __ballot_sync(FULL, real[u] && hl == 0);
+        n_real += __popc(real_bits[u]);
+    }
+    unsigned long long at = 0;
+    if (lane == 0 && n_real) at = atomicAdd(r.pushed, (unsigned long long)n_real);
+    // level 3: the window rows of both envs
+    WindowRowRaw rows[PUSH_ENVS];
+#pragma unroll
+    for (int u = 0; u < PUSH_ENVS; ++u) {
+        fast[u] = valid[u] && mz[u].H >= WIN && mz[u].W >= WIN;
+        rows[u] = WindowRowRaw{};
+        if (fast[u] && hl < WIN) rows[u] = window_row_load_bits(b, e[u], st[u], mz[u], hl);
+    }
+    at = __shfl_sync(FULL, at, 0);
+    PackedObs o[PUSH_ENVS];
+#pragma unroll
+    for (int u = 0; u < PUSH_ENVS; ++u) {
+        unsigned m0 = 0, m1 = 0, m2 = 0;
+        if (fast[u] && hl < WIN) window_row_fold_bits(rows[u], mz[u], m0, m1, m2);   // mazes below 15 x 15 have no window (zeros), as in window_row_masks
+        o[u] = finish_obs16(st[u], mz[u], valid[u], hl, m0, m1, m2);
+    }
+    // ring order inside the warp: env 0 of the low half, env 0 of the high half, env 1 of the low half, env 1 of the high half
+    int before = 0;
+#pragma unroll
+    for (int u = 0; u < PUSH_ENVS; ++u) {
+        if (real[u]) {
+            const unsigned long long mine = at + (unsigned long long)(before + ((lane >= 16 && (real_bits[u] & 1u)) ? 1 : 0));
+            const size_t slot = (size_t)(mine % (unsigned long long)r.capacity);
+            if (hl < 6) r.vec[slot * 6 + hl] = sv[u];
+            r.win[slot * WORDS + hl] = sw0[u];
+            if (hl < WORDS - 16) r.win[slot * WORDS + 16 + hl] = sw1[u];
+            store_obs16(o[u], hl, r.next_vec + slot * 6, r.next_win + slot * WORDS);
+            if (hl == 0) {
+                r.action[slot] = act[u];
+                r.reward[slot] = rew[u];
+            }
+        }
+        before += __popc(real_bits[u]);
+        // (the staged observation was read into registers above, before anything re-stages it)
+        if (valid[u]) store_obs16(o[u], hl, r.stage_vec + (size_t)e[u] * 6, r.stage_win + (size_t)e[u] * WORDS);
+    }
+}
+
+// Every other case (torus, no visit bitmap): one env per half-warp, the generic row gather of maze_window.cuh.
+
+__global__ void __launch_bounds__(PUSH_THREADS, 4)
+maze_dqn_push_generic_kernel(maze_env_batch b, maze_replay r, const uint8_t* __restrict__ actions) {
     const int hl = threadIdx.x & 15, lane = threadIdx.x & 31;
     const int e = blockIdx.x * (PUSH_THREADS / 16) + (threadIdx.x >> 4);
     const bool valid = e < b.num_envs;
@@ -257,8 +361,13 @@ extern "C" int maze_dqn_push(maze_ctx* ctx, const maze_env_batch* b, const maze_
     if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_push: actions");
     if (r->capacity < b->num_envs)   // one launch claims up to num_envs slots: a smaller ring would hand one slot to several warps
         return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_push: replay capacity must be >= num_envs");
-    const int per = PUSH_THREADS / 16;
-    maze_dqn_push_kernel<<<(b->num_envs + per - 1) / per, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r, actions);
+    if ((r->flags & MAZE_REPLAY_BORDERED) && b->visit_bits) {
+        const int per = PUSH_THREADS / 16 * PUSH_ENVS;
+        maze_dqn_push_bordered_kernel<<<(b->num_envs + per - 1) / per, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r, actions);
+    } else {
+        const int per = PUSH_THREADS / 16;
+        maze_dqn_push_generic_kernel<<<(b->num_envs + per - 1) / per, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r, actions);
+    }
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

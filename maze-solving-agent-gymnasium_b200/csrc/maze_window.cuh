@@ -6,6 +6,54 @@
 #pragma once
 #include "maze_env.cuh"
 
+// The bitmap path of window_row_masks (bordered mazes with maze_env_batch.visit_bits) in two halves, so that a kernel
+// can issue the loads of several envs before it folds any of them (maze_dqn_push_kernel).
+struct WindowRowRaw {
+    uint32_t tword[5];   // the row's 15 table bytes inside five aligned words
+    uint32_t b_lo, b_hi; // the two bitmap words its 15 "visited" bits lie in
+    int first, c0;       // table index of window column 0; its maze column
+};
+
+// requires: !mz.tor, b.visit_bits, mz.H >= WIN, mz.W >= WIN, row < WIN
+__device__ __forceinline__ WindowRowRaw window_row_load_bits(const maze_env_batch& b, int e, const EnvState& st, const MazeView& mz, int row) {
+    constexpr int WIN = MAZE_WINDOW;
+    const int r0 = min(max(st.r - WIN / 2, 0), mz.H - WIN), c0 = min(max(st.c - WIN / 2, 0), mz.W - WIN);
+    const int rr = r0 + row;
+    WindowRowRaw w;
+    w.first = rr * mz.W + c0;
+    w.c0 = c0;
+    const int off = w.first & 3;
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(mz.tab + (w.first - off));   // slots are 16-byte aligned and padded
+    const uint32_t* brow = b.visit_bits + (size_t)e * b.visit_bits_stride + rr * b.visit_bits_pitch + (c0 >> 5);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w.tword[k] = (4 * k - off < WIN) ? __ldg(tw + k) : 0u;
+    w.b_lo = brow[0];
+    w.b_hi = ((c0 & 31) + WIN > 32) ? brow[1] : 0u;
+    return w;
+}
+
+__device__ __forceinline__ void window_row_fold_bits(const WindowRowRaw& w, const MazeView& mz, unsigned& m0, unsigned& m1, unsigned& m2) {
+    constexpr int WIN = MAZE_WINDOW;
+    const int off = w.first & 3;
+    const unsigned seen = __funnelshift_r(w.b_lo, w.b_hi, w.c0 & 31) & ((1u << WIN) - 1u);
+    unsigned openm = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jt = 4 * k + q - off;               // window column of table byte q of word k
+            if (jt >= 0 && jt < WIN) openm |= ((w.tword[k] >> (8 * q)) & MAZE_TAB_OPEN) << jt;
+        }
+    const unsigned all = (1u << WIN) - 1u;
+    const int start_idx = (mz.start & 0xffff) * mz.W + (mz.start >> 16);
+    const int goal_idx = (mz.goal & 0xffff) * mz.W + (mz.goal >> 16);
+    const int gj = goal_idx - w.first, sj = start_idx - w.first;   // goal / start inside this row of the window?
+    const unsigned goal_bit = (gj >= 0 && gj < WIN) ? 1u << gj : 0u, start_bit = (sj >= 0 && sj < WIN) ? 1u << sj : 0u;
+    m0 = ~openm & all;
+    m1 = openm & ~goal_bit;
+    m2 = openm & ~start_bit & ~seen;
+}
+
 __device__ __forceinline__ void window_row_masks(const maze_env_batch& b, int e, const EnvState& st, const MazeView& mz, int row,
                                                  unsigned& m0, unsigned& m1, unsigned& m2) {
     constexpr int WIN = MAZE_WINDOW;
@@ -28,28 +76,8 @@ __device__ __forceinline__ void window_row_masks(const maze_env_batch& b, int e,
         // Bitmap path (bordered mazes): the row's "visited" bits are 15 consecutive bits of one bitmap row -- two words -- and
         // its table bytes five aligned 32-bit words: 7 loads per lane, and the 15 lanes of an env read 15 consecutive bitmap
         // rows (180 contiguous bytes at 81 x 81: three 64-byte DRAM atoms where the counter tiles cost up to 25 sectors).
-        const int first = rr * W + c0, off = first & 3;
-        const uint32_t* tw = reinterpret_cast<const uint32_t*>(mz.tab + (first - off));   // slots are 16-byte aligned and padded
-        const uint32_t* brow = b.visit_bits + (size_t)e * b.visit_bits_stride + rr * b.visit_bits_pitch + (c0 >> 5);
-        uint32_t tword[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) tword[k] = (4 * k - off < WIN) ? __ldg(tw + k) : 0u;
-        const uint32_t b_lo = brow[0], b_hi = ((c0 & 31) + WIN > 32) ? brow[1] : 0u;
-        const unsigned seen = __funnelshift_r(b_lo, b_hi, c0 & 31) & ((1u << WIN) - 1u);
-        unsigned openm = 0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int jt = 4 * k + q - off;               // window column of table byte q of word k
-                if (jt >= 0 && jt < WIN) openm |= ((tword[k] >> (8 * q)) & MAZE_TAB_OPEN) << jt;
-            }
-        const unsigned all = (1u << WIN) - 1u;
-        const int gj = goal_idx - first, sj = start_idx - first;   // goal / start inside this row of the window?
-        const unsigned goal_bit = (gj >= 0 && gj < WIN) ? 1u << gj : 0u, start_bit = (sj >= 0 && sj < WIN) ? 1u << sj : 0u;
-        m0 = ~openm & all;
-        m1 = openm & ~goal_bit;
-        m2 = openm & ~start_bit & ~seen;
+        const WindowRowRaw raw = window_row_load_bits(b, e, st, mz, row);
+        window_row_fold_bits(raw, mz, m0, m1, m2);
         return;
     }
     if (!mz.tor && b.visit_tiled && b.visit_cell_stride == 1) {
