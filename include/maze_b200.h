@@ -156,7 +156,12 @@ typedef struct maze_env_batch {
                               up to 25 scattered 32-byte sectors of counters                                          */
     int32_t   visit_bits_pitch;   /* words per bitmap row: ceil(max W / 32)                                          */
     int32_t   visit_bits_stride;  /* words per env: max H * pitch rounded up to a multiple of 4                       */
+    int32_t   flags;       /* MAZE_BATCH_BORDERED: the caller promises that no maze of `meta` is toroidal.  With visit_bits,
+                              maze_window and maze_dqn_push then run their bordered kernels (two envs per half-warp in
+                              flight, no generic gather compiled in); without the flag nothing is assumed              */
+    int32_t   reserved;
 } maze_env_batch;
+#define MAZE_BATCH_BORDERED 1
 
 /* sizeof of the ABI structs as this library was compiled (a binding checks its own layout against it):
  * which = 0 maze_env_batch, 1 maze_q_agent, 2 maze_replay, 3 maze_step_trace, 4 maze_dqn_net; -1 for anything else. */
@@ -390,10 +395,8 @@ typedef struct maze_replay {
     int32_t   without_replacement; /* 1: a batch holds n DISTINCT transitions (random.sample, lib/replay_memory.py:20-21;
                                falls back to independent draws while fewer than n are stored); 0: independent
                                uniform draws                                                        */
-    int32_t   flags;        /* MAZE_REPLAY_BORDERED: the caller promises that no maze of the batch is toroidal -- with
-                               maze_env_batch.visit_bits, maze_dqn_push then takes its two-envs-per-half-warp path      */
+    int32_t   reserved;
 } maze_replay;
-#define MAZE_REPLAY_BORDERED 1
 
 /* Encode the current observation of every env into the staging area (after maze_reset). */
 int maze_dqn_observe(maze_ctx* ctx, const maze_env_batch* b, const maze_replay* r, void* stream);

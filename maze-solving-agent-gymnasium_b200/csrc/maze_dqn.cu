@@ -91,7 +91,7 @@ maze_dqn_observe_kernel(maze_env_batch b, maze_replay r) {
 // (ii) every half-warp carries TWO envs through the chain together (four per warp): each level of the chain is issued
 // for both before either is consumed, which doubles the loads in flight at the same occupancy (1.83e9 -> 3.0e9 env-steps/s
 // with the step; four envs per half-warp or more CTAs per SM at fewer registers measured slower: 2.1 - 2.7e9).  This kernel is the
-// bordered-maze / visit-bitmap case only (maze_replay.flags & MAZE_REPLAY_BORDERED: the caller's promise that no maze of the
+// bordered-maze / visit-bitmap case only (maze_env_batch.flags & MAZE_BATCH_BORDERED: the caller's promise that no maze of the
 // batch is toroidal); maze_dqn_push_generic_kernel below handles everything else, one env per half-warp.
 constexpr int PUSH_THREADS = 256;
 constexpr int PUSH_ENVS = 2;   // envs per 16-lane group
@@ -361,7 +361,7 @@ extern "C" int maze_dqn_push(maze_ctx* ctx, const maze_env_batch* b, const maze_
     if (!actions) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_push: actions");
     if (r->capacity < b->num_envs)   // one launch claims up to num_envs slots: a smaller ring would hand one slot to several warps
         return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_push: replay capacity must be >= num_envs");
-    if ((r->flags & MAZE_REPLAY_BORDERED) && b->visit_bits) {
+    if ((b->flags & MAZE_BATCH_BORDERED) && b->visit_bits) {
         const int per = PUSH_THREADS / 16 * PUSH_ENVS;
         maze_dqn_push_bordered_kernel<<<(b->num_envs + per - 1) / per, PUSH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, *r, actions);
     } else {

@@ -29,35 +29,28 @@ constexpr int WIN_FLOATS = 3 * WIN_CELLS;
 #ifndef MAZE_WIN_MINB
 #define MAZE_WIN_MINB 4
 #endif
-__global__ void __launch_bounds__(OBS_THREADS, MAZE_WIN_MINB)
-maze_window_kernel(maze_env_batch b, float* __restrict__ window, double* __restrict__ agent_norm,
-                   double* __restrict__ target_norm) {
-    __shared__ __align__(16) uint8_t s_out[WIN_ENVS * WIN_FLOATS];
-    const int hl = threadIdx.x & 15, w = threadIdx.x >> 4;
-    const int e0 = blockIdx.x * WIN_ENVS, e = e0 + w;
-    if (e < b.num_envs) {
-        const EnvState st = unpack_state(b.state[e]);
-        const MazeView mz = load_maze(b, b.env_maze[e]);
-        unsigned m0, m1, m2;
-        window_row_masks(b, e, st, mz, hl, m0, m1, m2);
-        if (hl < WIN) {
-            uint8_t* sl = s_out + w * WIN_FLOATS + hl * WIN;   // block (row, col) of channel ch is output index 225 ch + 15 row + col
+
+// masks of one window row -> the row's 3 x 15 output bytes in shared memory
+__device__ __forceinline__ void window_row_to_smem(uint8_t* sl, unsigned m0, unsigned m1, unsigned m2) {
 #pragma unroll
-            for (int j = 0; j < WIN; ++j) {
-                sl[j] = (uint8_t)((m0 >> j) & 1u);
-                sl[WIN_CELLS + j] = (uint8_t)((m1 >> j) & 1u);
-                sl[2 * WIN_CELLS + j] = (uint8_t)((m2 >> j) & 1u);
-            }
-        }
-        if (hl < 2) {
-            const double shape = (double)(hl == 0 ? mz.H : mz.W);
-            if (agent_norm) agent_norm[(size_t)e * 2 + hl] = __ddiv_rn((double)(hl == 0 ? st.r : st.c), shape);
-            if (target_norm) target_norm[(size_t)e * 2 + hl] = __ddiv_rn((double)(hl == 0 ? (mz.goal & 0xffff) : (mz.goal >> 16)), shape);
-        }
+    for (int j = 0; j < WIN; ++j) {
+        sl[j] = (uint8_t)((m0 >> j) & 1u);
+        sl[WIN_CELLS + j] = (uint8_t)((m1 >> j) & 1u);
+        sl[2 * WIN_CELLS + j] = (uint8_t)((m2 >> j) & 1u);
     }
-    __syncthreads();
-    const int n_float = min(WIN_ENVS, b.num_envs - e0) * WIN_FLOATS;
-    float* out = window + (size_t)e0 * WIN_FLOATS;   // 16-byte aligned: e0 is a multiple of 16
+}
+
+__device__ __forceinline__ void window_norms(const EnvState& st, const MazeView& mz, int e, int hl, double* __restrict__ agent_norm,
+                                             double* __restrict__ target_norm) {
+    if (hl < 2) {
+        const double shape = (double)(hl == 0 ? mz.H : mz.W);
+        if (agent_norm) agent_norm[(size_t)e * 2 + hl] = __ddiv_rn((double)(hl == 0 ? st.r : st.c), shape);
+        if (target_norm) target_norm[(size_t)e * 2 + hl] = __ddiv_rn((double)(hl == 0 ? (mz.goal & 0xffff) : (mz.goal >> 16)), shape);
+    }
+}
+
+// all threads of the CTA: `n_envs` x 2 700 bytes of shared memory -> float32 in global memory, 16 bytes per store
+__device__ __forceinline__ void window_stream_out(const uint8_t* s_out, float* __restrict__ out, int n_float) {
     for (int q = threadIdx.x; 4 * q < n_float; q += OBS_THREADS) {
         const int f = 4 * q;
         const unsigned v = *reinterpret_cast<const unsigned*>(s_out + f);   // four values, one byte each
@@ -69,6 +62,76 @@ maze_window_kernel(maze_env_batch b, float* __restrict__ window, double* __restr
             for (int i = f; i < n_float; ++i) __stcs(out + i, (float)s_out[i]);
         }
     }
+}
+
+__global__ void __launch_bounds__(OBS_THREADS, MAZE_WIN_MINB)
+maze_window_kernel(maze_env_batch b, float* __restrict__ window, double* __restrict__ agent_norm,
+                   double* __restrict__ target_norm) {
+    __shared__ __align__(16) uint8_t s_out[WIN_ENVS * WIN_FLOATS];
+    const int hl = threadIdx.x & 15, w = threadIdx.x >> 4;
+    const int e0 = blockIdx.x * WIN_ENVS, e = e0 + w;
+    if (e < b.num_envs) {
+        const EnvState st = unpack_state(b.state[e]);
+        const MazeView mz = load_maze(b, b.env_maze[e]);
+        unsigned m0, m1, m2;
+        window_row_masks(b, e, st, mz, hl, m0, m1, m2);
+        if (hl < WIN) window_row_to_smem(s_out + w * WIN_FLOATS + hl * WIN, m0, m1, m2);   // block (row, col) of channel ch is output index 225 ch + 15 row + col
+        window_norms(st, mz, e, hl, agent_norm, target_norm);
+    }
+    __syncthreads();
+    window_stream_out(s_out, window + (size_t)e0 * WIN_FLOATS, min(WIN_ENVS, b.num_envs - e0) * WIN_FLOATS);   // 16-byte aligned: e0 is a multiple of 16
+}
+
+// Bordered mazes with the visit bitmap (maze_env_batch.flags & MAZE_BATCH_BORDERED): the gather is a chain of dependent
+// loads (state -> maze record -> rows), and at four CTAs per SM its latency, not HBM, paced the kernel (each CTA spends
+// about 3 us in the chain before it can write its 43 KB).  Here every half-warp carries TWO envs through the chain, each
+// level issued for both before either is consumed: 32 envs per CTA, twice the loads in flight at the same occupancy.
+constexpr int WINB_PER = 2;   // 4 measured slower (4.7 vs 5.2 TB/s at 262 144 envs: fewer CTAs per SM by shared memory)
+constexpr int WINB_ENVS = WIN_ENVS * WINB_PER;
+
+__global__ void __launch_bounds__(OBS_THREADS, MAZE_WIN_MINB)
+maze_window_bordered_kernel(maze_env_batch b, float* __restrict__ window, double* __restrict__ agent_norm,
+                            double* __restrict__ target_norm) {
+    __shared__ __align__(16) uint8_t s_out[WINB_ENVS * WIN_FLOATS];
+    const int hl = threadIdx.x & 15, w = threadIdx.x >> 4;
+    const int e0 = blockIdx.x * WINB_ENVS;
+    int e[WINB_PER];
+    bool valid[WINB_PER];
+    uint64_t raw[WINB_PER];
+    int maze_id[WINB_PER];
+#pragma unroll
+    for (int u = 0; u < WINB_PER; ++u) {
+        e[u] = e0 + w * WINB_PER + u;
+        valid[u] = e[u] < b.num_envs;
+        raw[u] = valid[u] ? b.state[e[u]] : 0ull;
+        maze_id[u] = valid[u] ? b.env_maze[e[u]] : 0;
+    }
+    EnvState st[WINB_PER];
+    MazeView mz[WINB_PER];
+#pragma unroll
+    for (int u = 0; u < WINB_PER; ++u) {
+        st[u] = unpack_state(raw[u]);
+        mz[u] = MazeView{};
+        if (valid[u]) mz[u] = load_maze(b, maze_id[u]);
+    }
+    WindowRowRaw rows[WINB_PER];
+    bool has[WINB_PER];
+#pragma unroll
+    for (int u = 0; u < WINB_PER; ++u) {
+        has[u] = valid[u] && hl < WIN && mz[u].H >= WIN && mz[u].W >= WIN;   // smaller mazes have no window: zeros, as in window_row_masks
+        rows[u] = WindowRowRaw{};
+        if (has[u]) rows[u] = window_row_load_bits(b, e[u], st[u], mz[u], hl);
+    }
+#pragma unroll
+    for (int u = 0; u < WINB_PER; ++u) {
+        if (!valid[u]) continue;
+        unsigned m0 = 0, m1 = 0, m2 = 0;
+        if (has[u]) window_row_fold_bits(rows[u], mz[u], m0, m1, m2);
+        if (hl < WIN) window_row_to_smem(s_out + (w * WINB_PER + u) * WIN_FLOATS + hl * WIN, m0, m1, m2);
+        window_norms(st[u], mz[u], e[u], hl, agent_norm, target_norm);
+    }
+    __syncthreads();
+    window_stream_out(s_out, window + (size_t)e0 * WIN_FLOATS, min(WINB_ENVS, b.num_envs - e0) * WIN_FLOATS);
 }
 
 __global__ void __launch_bounds__(OBS_THREADS)
@@ -201,8 +264,13 @@ extern "C" int maze_window(maze_ctx* ctx, const maze_env_batch* b, float* window
     if (!window) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_window: window");
     if (((uintptr_t)window & 15) || ((uintptr_t)agent_norm & 7) || ((uintptr_t)target_norm & 7))
         return maze_fail_arg(ctx, MAZE_E_ALIGN, "maze_window pointer alignment");
-    const int grid = (b->num_envs + WIN_ENVS - 1) / WIN_ENVS;
-    maze_window_kernel<<<grid, OBS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, window, agent_norm, target_norm);
+    if ((b->flags & MAZE_BATCH_BORDERED) && b->visit_bits) {
+        const int grid = (b->num_envs + WINB_ENVS - 1) / WINB_ENVS;
+        maze_window_bordered_kernel<<<grid, OBS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, window, agent_norm, target_norm);
+    } else {
+        const int grid = (b->num_envs + WIN_ENVS - 1) / WIN_ENVS;
+        maze_window_kernel<<<grid, OBS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*b, window, agent_norm, target_norm);
+    }
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

@@ -7,7 +7,7 @@ import os
 from .build import LIB_PATH
 
 ABI_VERSION = 12
-REPLAY_BORDERED = 1
+BATCH_BORDERED = 1
 
 # constants mirrored from include/maze_b200.h
 META_WORDS = 8
@@ -40,7 +40,7 @@ class MazeEnvBatch(C.Structure):
         ("visit_cell_stride", C.c_int64), ("visit_env_stride", C.c_int64),
         ("visit_tiled", C.c_int32), ("visit_slot", C.c_int32),
         ("target_dirty", C.c_void_p), ("packed", C.c_void_p),
-        ("visit_bits", C.c_void_p), ("visit_bits_pitch", C.c_int32), ("visit_bits_stride", C.c_int32),
+        ("visit_bits", C.c_void_p), ("visit_bits_pitch", C.c_int32), ("visit_bits_stride", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -59,7 +59,7 @@ class MazeReplay(C.Structure):
     _fields_ = [
         ("capacity", C.c_int64), ("pushed", C.c_void_p), ("vec", C.c_void_p), ("next_vec", C.c_void_p),
         ("win", C.c_void_p), ("next_win", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
-        ("stage_vec", C.c_void_p), ("stage_win", C.c_void_p), ("without_replacement", C.c_int32), ("flags", C.c_int32),
+        ("stage_vec", C.c_void_p), ("stage_win", C.c_void_p), ("without_replacement", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -44,14 +44,11 @@ class DeviceReplay:
         self.stage_vec = torch.zeros((B, 6), dtype=torch.float32, device=d)
         self.stage_win = torch.zeros((B, W), dtype=torch.int32, device=d)
         self.seed, self._draw = int(seed), 0
-        # no toroidal maze in the pool (and none can appear: topology is fixed per slot) -> the push kernel's bordered path
-        pool = getattr(self.batch, "pool", None)
-        bordered = pool is not None and not bool((pool.meta[:, cabi.META_FLAGS] & cabi.FLAG_TOROIDAL).any().item())
         self._c = cabi.MazeReplay(
             capacity=self.capacity, pushed=self.pushed.data_ptr(), vec=self.vec.data_ptr(), next_vec=self.next_vec.data_ptr(),
             win=self.win.data_ptr(), next_win=self.next_win.data_ptr(), action=self.action.data_ptr(),
             reward=self.reward.data_ptr(), stage_vec=self.stage_vec.data_ptr(), stage_win=self.stage_win.data_ptr(),
-            without_replacement=int(bool(without_replacement)), flags=cabi.REPLAY_BORDERED if bordered else 0)
+            without_replacement=int(bool(without_replacement)), reserved=0)
 
     def _stream(self):
         return cabi.current_stream(self.device)

@@ -298,7 +298,9 @@ class MazeBatch:
             visit_tiled=1 if self.visit_layout == "tile" else 0, visit_slot=self.visit_slot,
             target_dirty=self.target_dirty.data_ptr(), packed=self.packed.data_ptr(),
             visit_bits=None if self.visit_bits is None else self.visit_bits.data_ptr(),
-            visit_bits_pitch=self.visit_bits_pitch, visit_bits_stride=self.visit_bits_stride)
+            visit_bits_pitch=self.visit_bits_pitch, visit_bits_stride=self.visit_bits_stride,
+            # no toroidal maze in the pool now (and regeneration keeps a slot's topology): the bordered window / push kernels
+            flags=0 if bool((p.meta[:, cabi.META_FLAGS] & cabi.FLAG_TOROIDAL).any().item()) else cabi.BATCH_BORDERED, reserved=0)
 
     def view_struct(self, lo: int, hi: int) -> cabi.MazeEnvBatch:
         """maze_env_batch over the envs [lo, hi) of this batch: the same buffers with every per-env pointer advanced by

@@ -39,7 +39,7 @@ def test_reward_luts_equal_reference_expressions():
 def test_struct_layout_matches_header():
     import ctypes as C
     from maze_b200 import cabi
-    assert C.sizeof(cabi.MazeEnvBatch) == 16 + 16 * 8 + 16 + 8 + 8 + 8 + 16
+    assert C.sizeof(cabi.MazeEnvBatch) == 16 + 16 * 8 + 16 + 8 + 8 + 8 + 16 + 8
     assert cabi.MazeEnvBatch.meta.offset == 16
     # the library reports the sizes it was compiled with (host-only call, no GPU needed)
     lib = cabi.lib()
