@@ -550,6 +550,14 @@ def _follow_best_dir(torch, best_dir, u, p_follow):
     return torch.where(u < p_follow, a, rnd).to(torch.uint8)
 
 
+def _regen_summary(env):
+    if not env.regenerate_ahead:
+        return {"mode": "in place, on the stepping stream (MAZE_REGEN_AHEAD=0)"}
+    fast, slow, jobs = env.regeneration_statistics()
+    return {"mode": f"{env.regenerate_depth} mazes ahead per slot (shadow ring refilled on a side stream; include/maze_b200.h maze_regen_swap)",
+            "installed_from_shadow": fast, "drawn_in_place": slow, "refill_jobs": jobs, "counted": "rank 0, since construction"}
+
+
 def run_toroidal_regen(args, rank, local_rank, world):
     """configs[2]: toroidal 40x40 (81x81 block; the reference's examples pass the same odd block shape to both topologies)
     mazes, r-prim / dfs / prim&kill mixed per slot, one maze slot per env, every win regenerates the env's maze on the
@@ -583,11 +591,7 @@ def run_toroidal_regen(args, rank, local_rank, world):
     if rank != 0:
         return None
     value = world * B * args.steps / (ms * 1e-3)
-    fast, slow, jobs = env.regeneration_statistics()
-    regen = ({"mode": f"{env.regenerate_depth} mazes ahead per slot (shadow ring refilled on a side stream; include/maze_b200.h maze_regen_swap)",
-              "installed_from_shadow": fast,
-              "drawn_in_place": slow, "refill_jobs": jobs, "counted": "rank 0, since construction"} if env.regenerate_ahead
-             else {"mode": "in place, on the stepping stream (MAZE_REGEN_AHEAD=0)"})
+    regen = _regen_summary(env)
     return {"metric": "env-steps/sec (toroidal 40x40 mazes, mixed generators, regeneration on win, whole job)", "regeneration": regen, "value": value, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int32 state+obs, f64 reward", "data": "synthetic",
@@ -610,7 +614,7 @@ def run_curriculum_dq(args, rank, local_rank, world):
     import maze_b200 as mb
     from maze_b200.agents import DQAgent
     device, barrier, max_over_ranks = _dist_setup(local_rank, world)
-    B = args.envs_per_gpu if args.envs_per_gpu_set else 32768
+    B = args.envs_per_gpu if args.envs_per_gpu_set else 131072
     env = mb.MazeVectorEnv(B, shape=(129, 129), start_shape=(21, 21), grow=4, algorithms="r-prim", device=device, seed=1234, slot_id_base=rank * B,
                            on_win="regenerate", algorithm_schedule=((5, "prim&kill"), (10, "dfs")), stats=True)
     agent = DQAgent(env, learning_rate=0.1, initial_epsilon=0.9, epsilon_decay=2000, final_epsilon=0.05, discount_factor=0.7, eta=1e-3,
@@ -646,7 +650,7 @@ def run_curriculum_dq(args, rank, local_rank, world):
                        "envs_per_gpu": B, "l2": "inputs larger than L2 (33 KB visits per env at the pool shape)",
                        "parallelism": f"env-index sharding over {world} GPU(s), replicas only (one Q table per env, as in the reference)"},
             "wins": stats["wins"], "mean_block_shape_after_run": float(shapes.mean().item()), "max_block_shape_after_run": float(shapes.max().item()),
-            "gpu_launches": args.steps * world * 7, "clocks": clocks}
+            "regeneration": _regen_summary(env), "gpu_launches": args.steps * world * 7, "clocks": clocks}
 
 
 def run_ddqn(args, rank, local_rank, world):

@@ -274,20 +274,25 @@ int maze_curriculum(maze_ctx* ctx, int32_t* meta, int32_t* wins, const int32_t* 
  *                       count over the live slot if it is ready, else append the slot to slow_queue (the caller then
  *                       runs maze_generate on slow_queue / slow_count in place, as without a ring); every winner is
  *                       appended to refill_queue once per `batch` (queued_tag [M], initialised to -1).  stats [2]
- *                       (optional) counts fast / slow slots.  slow_count must be zero on entry.
+ *                       (optional) counts fast / slow slots; wins [M] (optional) is the curriculum's win count, incremented
+ *                       for the slots installed from the ring (maze_curriculum does it for the slow ones).  slow_count
+ *                       must be zero on entry.
  *   maze_regen_prepare  (side stream) for the slots of refill_queue: ring entries that already hold the maze they should
- *                       are left alone, the others are un-published (ready_gen = 0), get the live slot's shape and
- *                       generator and their generation count, and are appended to work_queue [depth, M] / work_count
- *                       [depth] of their ring index.  Then, per ring index j: maze_generate(entry-j slices of the ring,
+ *                       are left alone, the others are un-published (ready_gen = 0), get their generation count and the
+ *                       shape / generator the curriculum gives that count -- maze_curriculum's rule (grow, max shape, generator
+ *                       thresholds; grow = 0 and algo = -1: none) applied in closed form to a snapshot of the slot records
+ *                       and win counts taken when the ring was built (base_meta [M, 8], base_wins [M] or NULL) -- and are
+ *                       appended to work_queue [depth, M] / work_count [depth] of their ring index.  Then, per ring index j: maze_generate(entry-j slices of the ring,
  *                       ids = work_queue[j], count_dev = work_count + j), and
  *   maze_regen_publish  (side stream) ready_gen = the entry's generation count for everything in the work queues.
  * Every path installs the same maze, so results do not depend on how far the side stream is behind. */
 int maze_regen_swap(maze_ctx* ctx, uint8_t* grids, uint8_t* table, int32_t* meta, const uint8_t* shadow_grids, const uint8_t* shadow_table,
                     const int32_t* shadow_meta, const int32_t* ready_gen, int depth, const int32_t* queue, const int32_t* queue_count, int n,
                     int slot, int32_t* refill_queue, int32_t* refill_count, int32_t* queued_tag, int batch, int32_t* slow_queue,
-                    int32_t* slow_count, int32_t* stats, void* stream);
-int maze_regen_prepare(maze_ctx* ctx, const int32_t* meta, int32_t* shadow_meta, int32_t* ready_gen, int depth, const int32_t* refill_queue,
-                       const int32_t* refill_count, int n, int32_t* work_queue, int32_t* work_count, void* stream);
+                    int32_t* slow_count, int32_t* stats, int32_t* wins, void* stream);
+int maze_regen_prepare(maze_ctx* ctx, const int32_t* meta, const int32_t* base_meta, const int32_t* base_wins, int grow, int max_h, int max_w,
+                       int wins_a, int algo_a, int wins_b, int algo_b, int32_t* shadow_meta, int32_t* ready_gen, int depth,
+                       const int32_t* refill_queue, const int32_t* refill_count, int n, int32_t* work_queue, int32_t* work_count, void* stream);
 int maze_regen_publish(maze_ctx* ctx, const int32_t* shadow_meta, int32_t* ready_gen, int depth, const int32_t* work_queue,
                        const int32_t* work_count, int n, void* stream);
 

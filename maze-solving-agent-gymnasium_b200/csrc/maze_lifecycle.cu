@@ -62,8 +62,8 @@ extern "C" int maze_curriculum(maze_ctx* ctx, int32_t* meta, int32_t* wins, cons
 //                       refill queue of the current batch once (queued_tag)
 //   maze_regen_prepare  side stream: for a queued slot with live count L the ring should hold M(m, L) .. M(m, L + depth - 1);
 //                       entries that already do are left alone (so a refill never rewrites an entry that the stepping
-//                       stream may be copying), the others are un-published, get their generation count and go to the
-//                       work queue of their ring index
+//                       stream may be copying), the others are un-published, get their generation count and the shape /
+//                       generator the curriculum gives that count, and go to the work queue of their ring index
 //   maze_regen_publish  side stream, after maze_generate on the ring entries: ready_gen = entry's count (release)
 // The live meta record is written after the slot's bytes (fence in between), so a prepare that already sees the new
 // count can only start a refill of that entry after the copy has finished reading it.
@@ -84,7 +84,8 @@ maze_regen_swap_kernel(uint8_t* __restrict__ grids, uint8_t* __restrict__ table,
                        const uint8_t* __restrict__ sh_table, const int32_t* __restrict__ sh_meta, const int32_t* __restrict__ ready_gen, int depth,
                        const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_count, int n, int slot,
                        int32_t* __restrict__ refill_queue, int32_t* __restrict__ refill_count, int32_t* __restrict__ queued_tag, int batch,
-                       int32_t* __restrict__ slow_queue, int32_t* __restrict__ slow_count, int32_t* __restrict__ stats) {
+                       int32_t* __restrict__ slow_queue, int32_t* __restrict__ slow_count, int32_t* __restrict__ stats,
+                       int32_t* __restrict__ wins) {
     __shared__ int s_entry;
     const int count = min(*queue_count, n);
     for (int k = blockIdx.x; k < count; k += gridDim.x) {
@@ -97,6 +98,7 @@ maze_regen_swap_kernel(uint8_t* __restrict__ grids, uint8_t* __restrict__ table,
             if (atomicExch(queued_tag + m, batch) != batch) refill_queue[atomicAdd(refill_count, 1)] = m;
             if (!valid) slow_queue[atomicAdd(slow_count, 1)] = m;
             if (stats) atomicAdd(stats + (valid ? 0 : 1), 1);
+            if (valid && wins) wins[m] += 1;   // the curriculum's win count (slow slots: maze_curriculum on the slow queue)
         }
         __syncthreads();
         const int j = s_entry;
@@ -118,24 +120,42 @@ maze_regen_swap_kernel(uint8_t* __restrict__ grids, uint8_t* __restrict__ table,
     }
 }
 
+// The configuration (shape, generator) of generation count g follows from a snapshot of the slot taken while nothing was
+// in flight (base_meta / base_wins, at ring construction) and the curriculum's rule applied g - base count + 1 times, in
+// closed form: maze_curriculum_kernel grows both sides together while both fit and picks the generator from the win count.
+// Reading the LIVE record's shape here instead would race with maze_regen_swap rewriting it word by word.
+struct CurriculumRule {
+    int grow, max_h, max_w, wins_a, algo_a, wins_b, algo_b;
+};
+
 // work_queue [depth, n], work_count [depth]
-__global__ void maze_regen_prepare_kernel(const int32_t* __restrict__ meta, int32_t* __restrict__ sh_meta, int32_t* __restrict__ ready_gen, int depth,
+__global__ void maze_regen_prepare_kernel(const int32_t* __restrict__ meta, const int32_t* __restrict__ base_meta, const int32_t* __restrict__ base_wins,
+                                          CurriculumRule rule, int32_t* __restrict__ sh_meta, int32_t* __restrict__ ready_gen, int depth,
                                           const int32_t* __restrict__ refill_queue, const int32_t* __restrict__ refill_count, int n,
                                           int32_t* __restrict__ work_queue, int32_t* __restrict__ work_count) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= min(*refill_count, n)) return;
     const int m = refill_queue[k];
-    const int32_t* lm = meta + (size_t)m * MAZE_META_WORDS;
-    const int live = *reinterpret_cast<const volatile int32_t*>(lm + MAZE_META_SPARE);
+    const int live = *reinterpret_cast<const volatile int32_t*>(meta + (size_t)m * MAZE_META_WORDS + MAZE_META_SPARE);
+    const int32_t* bm = base_meta + (size_t)m * MAZE_META_WORDS;
+    const int bH = bm[MAZE_META_H], bW = bm[MAZE_META_W], bflags = bm[MAZE_META_FLAGS], bcount = bm[MAZE_META_SPARE];
+    const int bwins = base_wins ? base_wins[m] : 0;
+    const int room = rule.grow > 0 ? max(0, min((rule.max_h - bH) / rule.grow, (rule.max_w - bW) / rule.grow)) : 0;
     for (int g = live; g < live + depth; ++g) {
         const int j = g % depth;
         int32_t* rg = ready_gen + (size_t)j * n + m;
         if (ld_acquire(rg) == g + 1) continue;   // already holds M(m, g): nothing to draw, and the stepping stream may be reading it
         st_release(rg, 0);
+        const int steps = g - bcount + 1;        // curriculum steps between the snapshot and the regeneration that draws M(m, g)
+        const int grown = rule.grow * min(max(steps, 0), room);
+        const int w = bwins + steps;
+        int algo = -1;
+        if (rule.algo_b >= 0 && w >= rule.wins_b) algo = rule.algo_b;
+        else if (rule.algo_a >= 0 && w >= rule.wins_a) algo = rule.algo_a;
         int32_t* sm = sh_meta + ((size_t)j * n + m) * MAZE_META_WORDS;
-        sm[MAZE_META_H] = lm[MAZE_META_H];
-        sm[MAZE_META_W] = lm[MAZE_META_W];
-        sm[MAZE_META_FLAGS] = lm[MAZE_META_FLAGS];
+        sm[MAZE_META_H] = bH + grown;
+        sm[MAZE_META_W] = bW + grown;
+        sm[MAZE_META_FLAGS] = algo >= 0 ? ((bflags & ~0xff00) | (algo << 8)) : bflags;
         sm[MAZE_META_SPARE] = g;
         work_queue[(size_t)j * n + atomicAdd(work_count + j, 1)] = m;
     }
@@ -156,7 +176,7 @@ __global__ void maze_regen_publish_kernel(const int32_t* __restrict__ sh_meta, i
 extern "C" int maze_regen_swap(maze_ctx* ctx, uint8_t* grids, uint8_t* table, int32_t* meta, const uint8_t* shadow_grids, const uint8_t* shadow_table,
                                const int32_t* shadow_meta, const int32_t* ready_gen, int depth, const int32_t* queue, const int32_t* queue_count,
                                int n, int slot, int32_t* refill_queue, int32_t* refill_count, int32_t* queued_tag, int batch, int32_t* slow_queue,
-                               int32_t* slow_count, int32_t* stats, void* stream) {
+                               int32_t* slow_count, int32_t* stats, int32_t* wins, void* stream) {
     if (!ctx) return MAZE_E_NULL;
     if (!grids || !table || !meta || !shadow_grids || !shadow_table || !shadow_meta || !ready_gen || !queue || !queue_count || !refill_queue ||
         !refill_count || !queued_tag || !slow_queue || !slow_count)
@@ -169,19 +189,24 @@ extern "C" int maze_regen_swap(maze_ctx* ctx, uint8_t* grids, uint8_t* table, in
     const int grid = n < 4 * sms ? n : 4 * sms;
     maze_regen_swap_kernel<<<grid, SWAP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(grids, table, meta, shadow_grids, shadow_table, shadow_meta, ready_gen,
                                                                                        depth, queue, queue_count, n, slot, refill_queue, refill_count,
-                                                                                       queued_tag, batch, slow_queue, slow_count, stats);
+                                                                                       queued_tag, batch, slow_queue, slow_count, stats, wins);
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int maze_regen_prepare(maze_ctx* ctx, const int32_t* meta, int32_t* shadow_meta, int32_t* ready_gen, int depth, const int32_t* refill_queue,
-                                  const int32_t* refill_count, int n, int32_t* work_queue, int32_t* work_count, void* stream) {
+extern "C" int maze_regen_prepare(maze_ctx* ctx, const int32_t* meta, const int32_t* base_meta, const int32_t* base_wins, int grow, int max_h,
+                                  int max_w, int wins_a, int algo_a, int wins_b, int algo_b, int32_t* shadow_meta, int32_t* ready_gen, int depth,
+                                  const int32_t* refill_queue, const int32_t* refill_count, int n, int32_t* work_queue, int32_t* work_count,
+                                  void* stream) {
     if (!ctx) return MAZE_E_NULL;
-    if (!meta || !shadow_meta || !ready_gen || !refill_queue || !refill_count || !work_queue || !work_count)
+    if (!meta || !base_meta || !shadow_meta || !ready_gen || !refill_queue || !refill_count || !work_queue || !work_count)
         return maze_fail_arg(ctx, MAZE_E_NULL, "maze_regen_prepare pointer");
     if (n <= 0 || depth < 1 || depth > 8) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_regen_prepare n / depth");
-    maze_regen_prepare_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(meta, shadow_meta, ready_gen, depth, refill_queue, refill_count,
-                                                                                            n, work_queue, work_count);
+    if (grow < 0 || (grow & 1)) return maze_fail_arg(ctx, MAZE_E_SHAPE, "maze_regen_prepare: grow must be even and >= 0");
+    if (algo_a > MAZE_ALGO_PRIMKILL || algo_b > MAZE_ALGO_PRIMKILL) return maze_fail_arg(ctx, MAZE_E_ALGO, "maze_regen_prepare generator id");
+    const CurriculumRule rule{grow, max_h, max_w, wins_a, algo_a, wins_b, algo_b};
+    maze_regen_prepare_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(meta, base_meta, base_wins, rule, shadow_meta, ready_gen, depth,
+                                                                                            refill_queue, refill_count, n, work_queue, work_count);
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }

@@ -136,8 +136,9 @@ SIGNATURES = {
     "maze_dqn_backward": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet)] + [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "maze_dqn_adamw": (C.c_int, [C.c_void_p, C.POINTER(MazeDqnNet)] + [C.c_float] * 5 + [C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "maze_regen_swap": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int]
-                        + [C.c_void_p] * 4),
-    "maze_regen_prepare": (C.c_int, [C.c_void_p] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 3),
+                        + [C.c_void_p] * 5),
+    "maze_regen_prepare": (C.c_int, [C.c_void_p] + [C.c_void_p] * 3 + [C.c_int] * 7 + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int]
+                           + [C.c_void_p] * 3),
     "maze_regen_publish": (C.c_int, [C.c_void_p] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]),
     "maze_dqn_net_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "maze_dqn_net_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),

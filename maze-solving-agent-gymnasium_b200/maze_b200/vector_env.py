@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import cabi
-from .engine import MazeBatch, MazePool
+from .engine import ALGO_IDS, MazeBatch, MazePool
 
 from . import _gym as _gymshim
 
@@ -79,7 +79,7 @@ class MazeVectorEnv(_VectorBase):
         (variable-size envs: START_SHAPE and +(4, 4), simple_variable_maze_env.py:17,97);
         `algorithm_schedule` = ((wins, algorithm), ...) switches a slot's generator by its win count
         (off_policy_trainer.py:302-310: ((5, "prim&kill"), (10, "dfs"))).
-        regenerate_ahead (on_win="regenerate" without a curriculum; default 3, MAZE_REGEN_AHEAD=0 turns it off): keep
+        regenerate_ahead (on_win="regenerate", with or without a curriculum; default 3, MAZE_REGEN_AHEAD=0 turns it off): keep
         the next k mazes of every slot in a shadow ring that a side stream refills, so that a win costs a 13 KB copy
         instead of the generator's latency (include/maze_b200.h: maze_regen_swap).  Same mazes either way; k x 13 KB per slot.
         visit_layout: "cell" (default; best for one launch per step), "tile" (env-major in 4 x 4 block tiles:
@@ -127,7 +127,7 @@ class MazeVectorEnv(_VectorBase):
         if regenerate_ahead is None:
             regenerate_ahead = int(os.environ.get("MAZE_REGEN_AHEAD", "3") or 0)
         self.regenerate_depth = min(8, int(regenerate_ahead))   # True -> 1
-        self.regenerate_ahead = self.regenerate_depth > 0 and on_win == "regenerate" and not self.grow and not self.algorithm_schedule
+        self.regenerate_ahead = self.regenerate_depth > 0 and on_win == "regenerate"
         self._ahead = None   # built on the first drain (and again after load_state_dict)
         if env_maze is None:
             # contiguous envs share a maze: table reads of a warp hit the same lines
@@ -226,6 +226,12 @@ class MazeVectorEnv(_VectorBase):
         b.queue_count.zero_()
 
     # -- regeneration ahead of time (include/maze_b200.h: maze_regen_swap / _prepare / _publish) -------------------
+    def _curriculum_rule(self):
+        sched = list(self.algorithm_schedule or ())
+        (wa, aa), (wb, ab) = (sched + [(0, None), (0, None)])[:2]
+        code = lambda a: -1 if a is None else (ALGO_IDS[a] if isinstance(a, str) else int(a))  # noqa: E731
+        return (int(self.grow), self.pool.max_shape[0], self.pool.max_shape[1], int(wa), code(aa), int(wb), code(ab))
+
     def _build_ahead(self):
         pool, dev, M, K = self.pool, self.device, self.pool.num_mazes, self.regenerate_depth
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -234,24 +240,43 @@ class MazeVectorEnv(_VectorBase):
         table = torch.zeros((K, M, pool.slot), dtype=torch.uint8, device=dev)
         meta = torch.zeros((K, M, cabi.META_WORDS), **i32)
         ctx = cabi.Context(idx)   # own work counter / scratch: the refills run beside the live pool's generator
-        live = pool.meta[:, cabi.META_SPARE]
         ring = []
         for j in range(K):   # ring entry j holds M(m, g) for the g in [live, live + K) with g % K == j
             sh = MazePool.__new__(MazePool)
             sh.device, sh.ctx, sh.max_shape, sh.num_mazes, sh.slot = dev, ctx, pool.max_shape, M, pool.slot
             sh.grids, sh.table, sh.meta = grids[j], table[j], meta[j]
-            sh.meta.copy_(pool.meta)
-            sh.meta[:, cabi.META_SPARE] = live + torch.remainder(j - live, K)
-            sh.generate(ids=None, configure=False, seed=self.seed, slot_id_base=self.slot_id_base, candidates=self.candidates)
             ring.append(sh)
-        a = dict(ring=ring, grids=grids, table=table, meta=meta, ctx=ctx, ready=meta[:, :, cabi.META_SPARE].clone().contiguous(),
-                 refill=[torch.zeros(M, **i32), torch.zeros(M, **i32)], refill_count=[torch.zeros(1, **i32), torch.zeros(1, **i32)],
+        curriculum = bool(self.grow or self.algorithm_schedule)
+        a = dict(ring=ring, grids=grids, table=table, meta=meta, ctx=ctx, ready=torch.zeros((K, M), **i32),
+                 # the slot records and win counts now, with nothing in flight: what maze_regen_prepare derives every later
+                 # configuration from (reading the live records there would race with maze_regen_swap)
+                 base_meta=pool.meta.clone(), base_wins=self.wins.clone() if curriculum else None, curriculum=curriculum,
+                 refill=[torch.arange(M, **i32), torch.zeros(M, **i32)], refill_count=[torch.full((1,), M, **i32), torch.zeros(1, **i32)],
                  tag=torch.full((M,), -1, **i32), slow=torch.zeros(M, **i32), slow_count=torch.zeros(1, **i32),
                  work=torch.zeros((K, M), **i32), work_count=torch.zeros(K, **i32), stats=torch.zeros(2, **i32),
                  side=torch.cuda.Stream(device=dev), side_done=torch.cuda.Event(), main_evt=torch.cuda.Event(), cur=0, batch=0, jobs=0)
-        for t in (grids, table, meta, a["ready"], *a["refill"], *a["refill_count"], a["work"], a["work_count"], pool.meta):
-            t.record_stream(a["side"])   # the side stream reads / writes them: the allocator must not recycle them under it
         self._ahead = a
+        self._refill_job(0)   # every slot, on the current stream: the ring starts complete
+        for t in (grids, table, meta, a["ready"], *a["refill"], *a["refill_count"], a["work"], a["work_count"], pool.meta, a["base_meta"]):
+            t.record_stream(a["side"])   # the side stream reads / writes them: the allocator must not recycle them under it
+        if a["base_wins"] is not None:
+            a["base_wins"].record_stream(a["side"])
+
+    def _refill_job(self, cur):
+        """prepare -> maze_generate per ring entry -> publish for refill queue `cur`, on the current stream."""
+        a, pool, K = self._ahead, self.pool, self.regenerate_depth
+        lib, p, ctx, M = cabi.lib(), cabi.ptr, a["ctx"], pool.num_mazes
+        stream = cabi.current_stream(self.device)
+        rc = lib.maze_regen_prepare(ctx.handle, p(pool.meta), p(a["base_meta"]), p(a["base_wins"]), *self._curriculum_rule(), p(a["meta"]),
+                                    p(a["ready"]), K, p(a["refill"][cur]), p(a["refill_count"][cur]), M, p(a["work"]), p(a["work_count"]), stream)
+        ctx.check(rc, "maze_regen_prepare")
+        for j, sh in enumerate(a["ring"]):
+            sh.generate(ids=a["work"][j], count_dev=a["work_count"][j:j + 1], configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
+                        candidates=self.candidates)
+        rc = lib.maze_regen_publish(ctx.handle, p(a["meta"]), p(a["ready"]), K, p(a["work"]), p(a["work_count"]), M, stream)
+        ctx.check(rc, "maze_regen_publish")
+        a["refill_count"][cur].zero_()
+        a["work_count"].zero_()
 
     def _drain_ahead(self):
         if self._ahead is None:
@@ -262,28 +287,21 @@ class MazeVectorEnv(_VectorBase):
         a["slow_count"].zero_()
         rc = lib.maze_regen_swap(pool.ctx.handle, p(pool.grids), p(pool.table), p(pool.meta), p(a["grids"]), p(a["table"]), p(a["meta"]), p(a["ready"]), K,
                                  p(b.queue), p(b.queue_count), M, pool.slot, p(a["refill"][cur]), p(a["refill_count"][cur]), p(a["tag"]), a["batch"],
-                                 p(a["slow"]), p(a["slow_count"]), p(a["stats"]), cabi.current_stream(self.device))
+                                 p(a["slow"]), p(a["slow_count"]), p(a["stats"]), p(self.wins) if a["curriculum"] else None,
+                                 cabi.current_stream(self.device))
         pool.ctx.check(rc, "maze_regen_swap")
         # slots whose ring entry was not ready (more wins than the ring is deep before a refill was published): drawn in place
+        if a["curriculum"]:
+            pool.curriculum(a["slow"], a["slow_count"], self.wins, self.grow, self.algorithm_schedule)
         pool.generate(ids=a["slow"], count_dev=a["slow_count"], configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
                       candidates=self.candidates)
         b.queue_count.zero_()
         if a["side_done"].query():   # the previous refill has finished: start the next one on what queued up meanwhile
-            main, side, ctx = torch.cuda.current_stream(self.device), a["side"], a["ctx"]
+            main, side = torch.cuda.current_stream(self.device), a["side"]
             a["main_evt"].record(main)
             side.wait_event(a["main_evt"])
             with torch.cuda.stream(side):
-                rc = lib.maze_regen_prepare(ctx.handle, p(pool.meta), p(a["meta"]), p(a["ready"]), K, p(a["refill"][cur]), p(a["refill_count"][cur]), M,
-                                            p(a["work"]), p(a["work_count"]), cabi.current_stream(self.device))
-                ctx.check(rc, "maze_regen_prepare")
-                for j, sh in enumerate(a["ring"]):
-                    sh.generate(ids=a["work"][j], count_dev=a["work_count"][j:j + 1], configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
-                                candidates=self.candidates)
-                rc = lib.maze_regen_publish(ctx.handle, p(a["meta"]), p(a["ready"]), K, p(a["work"]), p(a["work_count"]), M,
-                                            cabi.current_stream(self.device))
-                ctx.check(rc, "maze_regen_publish")
-                a["refill_count"][cur].zero_()
-                a["work_count"].zero_()
+                self._refill_job(cur)
                 a["side_done"].record(side)
             a["cur"], a["batch"], a["jobs"] = cur ^ 1, a["batch"] + 1, a["jobs"] + 1
 

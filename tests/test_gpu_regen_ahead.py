@@ -9,10 +9,10 @@ pytestmark = pytest.mark.gpu
 from test_gpu_scenarios import _greedy  # noqa: E402
 
 
-def _make(ahead, B, S, topology, seed=5):
+def _make(ahead, B, S, topology, seed=5, **kw):
     import maze_b200 as mb
-    return mb.MazeVectorEnv(B, shape=(S, S), topology=topology, algorithms=["r-prim", "dfs", "prim&kill"], seed=seed, on_win="regenerate",
-                            stats=True, regenerate_ahead=ahead)
+    kw.setdefault("algorithms", ["r-prim", "dfs", "prim&kill"])
+    return mb.MazeVectorEnv(B, shape=(S, S), topology=topology, seed=seed, on_win="regenerate", stats=True, regenerate_ahead=ahead, **kw)
 
 
 def _run(env, S, steps, seed, hook=None):
@@ -50,6 +50,38 @@ def test_shadow_ring_installs_the_mazes_the_in_place_path_draws(topology, S, dep
     wins = int(env.episode_statistics()["wins"])
     assert fast + slow == wins and wins > B and jobs >= 1
     assert fast > 0
+
+
+@pytest.mark.parametrize("topology,depth", [("euclid", 2), ("toroidal", 3)])
+def test_shadow_ring_follows_the_curriculum(topology, depth):
+    """Variable-size envs: +2 blocks per win up to the slot's maximum, generator switched after 2 and 4 wins
+    (simple_variable_maze_env.py:93-112, off_policy_trainer.py:302-310).  The ring entries are drawn with the shape and
+    generator the curriculum will have reached at their generation count -- same mazes, win counts and records as in place."""
+    B, S, steps = 1024, 21, 700
+    kw = dict(start_shape=[(9, 9), (11, 11), (13, 13)], grow=2, algorithms="r-prim", algorithm_schedule=((2, "prim&kill"), (4, "dfs")))
+    ref_env, env = _make(0, B, S, topology, **kw), _make(depth, B, S, topology, **kw)
+    assert env.regenerate_ahead and env.regenerate_depth == depth
+
+    def run(e):
+        rng = np.random.default_rng(8)
+        obs, _ = e.reset()
+        trace = []
+        for t in range(steps):
+            shape = e.pool.meta[e.batch.env_maze.long(), 0].cpu().numpy()   # the hint wraps at the slot's own size on the torus
+            acts = _greedy(obs["best dir"].cpu().numpy(), shape, rng, 0.9)
+            obs, rew, term, trunc, _ = e.step(torch.from_numpy(acts).cuda())
+            trace.append((obs["agent"].clone(), obs["target"].clone(), obs["best dir"].clone(), rew.clone(), term.clone(), trunc.clone()))
+        e.drain_regeneration()
+        torch.cuda.synchronize()
+        return trace
+
+    _same(run(ref_env), run(env))
+    assert torch.equal(ref_env.pool.meta, env.pool.meta) and torch.equal(ref_env.wins, env.wins)
+    assert torch.equal(ref_env.pool.grids, env.pool.grids) and torch.equal(ref_env.pool.table, env.pool.table)
+    meta = env.pool.meta_host()
+    assert meta[:, 0].max() > 13 and len(set(((meta[:, 5] >> 8) & 0xff).tolist())) >= 2   # shapes grew, generators switched
+    fast, slow, _ = env.regeneration_statistics()
+    assert fast > 0 and fast + slow == int(env.wins.sum().item())
 
 
 def test_slots_that_win_again_before_their_refill_are_drawn_in_place():
