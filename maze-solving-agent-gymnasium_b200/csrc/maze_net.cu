@@ -938,40 +938,6 @@ net_colsum_kernel(const bf16* __restrict__ in, int R, int C, int ld, float* __re
 }
 
 // ------------------------------------------------------------------------------------------------------
-// [R, C] bf16 -> [C, R] bf16 (the weight-gradient GEMMs contract over the batch, so their operands are the
-// transposed activations), optionally with the column sums of the input (= the bias gradient).
-__global__ void __launch_bounds__(256)
-net_transpose_kernel(const bf16* __restrict__ in, int R, int C, int ld_in, bf16* __restrict__ out, int ld_out, float* __restrict__ colsum) {
-    __shared__ bf16 tile[64][66];
-    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    for (int i = ty; i < 64; i += 8) {
-        const int r = r0 + i;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int c = c0 + tx + 32 * k;
-            tile[i][tx + 32 * k] = (r < R && c < C) ? in[(size_t)r * ld_in + c] : __float2bfloat16(0.f);
-        }
-    }
-    __syncthreads();
-    for (int i = ty; i < 64; i += 8) {
-        const int c = c0 + i;
-        float part = 0.f;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int r = r0 + tx + 32 * k;
-            const bf16 v = tile[tx + 32 * k][i];
-            if (c < C && r < R) out[(size_t)c * ld_out + r] = v;
-            part += __bfloat162float(v);
-        }
-        if (colsum) {
-            part = warp_sum(part);
-            if (tx == 0 && c < C) atomicAdd(colsum + c, part);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
 // Convolution weight / bias gradient from dL/dX (conv part), the saved pool choices and the packed windows.
 // Thread (o, sub): output channel o, pooled positions sub, sub + 8, ...; 27 tap accumulators in registers.
 __global__ void __launch_bounds__(256)
@@ -1290,7 +1256,7 @@ net_sample_packed_kernel(maze_replay r, int n, unsigned long long seed, unsigned
 // Workspace carving (bf16 activations; rows padded to a multiple of 128 so every TMA box starts in bounds)
 struct Workspace {
     int n, np;   // batch, padded batch
-    bf16 *X, *XT, *h1, *h1t_tn, *h1T, *h2, *h2_tn, *dh2, *dh2T, *dh1, *dh1T, *dX;
+    bf16 *X, *h1, *h1t_tn, *h2, *h2_tn, *dh2, *dh1, *dX;
     uint8_t* idx;
     float* q;
     size_t bytes;
@@ -1310,16 +1276,12 @@ Workspace carve(void* base, int n) {
         return p;
     };
     w.X = (bf16*)take(2 * np * NET_IN * 2);          // rows 0..np-1 state, np..2np-1 next state
-    w.XT = (bf16*)take((size_t)NET_IN * np * 2);     // state features, transposed
     w.h1 = (bf16*)take(2 * np * NET_H1 * 2);         // source net on both halves
     w.h1t_tn = (bf16*)take(np * NET_H1 * 2);         // target net on the next states
-    w.h1T = (bf16*)take((size_t)NET_H1 * np * 2);
     w.h2 = (bf16*)take(2 * np * NET_H2 * 2);
     w.h2_tn = (bf16*)take(np * NET_H2 * 2);
     w.dh2 = (bf16*)take(np * NET_H2 * 2);
-    w.dh2T = (bf16*)take((size_t)NET_H2 * np * 2);
     w.dh1 = (bf16*)take(np * NET_H1 * 2);
-    w.dh1T = (bf16*)take((size_t)NET_H1 * np * 2);
     w.dX = (bf16*)take(np * NET_IN * 2);
     w.idx = (uint8_t*)take(np * NET_CONV_OUT);
     w.q = (float*)take(2 * np * 4 * sizeof(float));
@@ -1420,13 +1382,6 @@ int mlp_forward(maze_ctx* ctx, const bf16* X, int rows, const bf16* w1b, const b
     g.M = rows; g.N = NET_H2; g.K = NET_H1; g.C = h2; g.ldc = NET_H2; g.bias = params + MAZE_NET_OFF_B2; g.act = ACT_RELU;
     if (int rc = launch_gemm(ctx, EPI_BIAS_ACT, fc_tile(rows), h1, NET_H1, w2b, NET_H1, g, 1, st)) return rc;
     prof_mark(ctx, st, "fc2 forward GEMM");
-    return 0;
-}
-
-[[maybe_unused]] int transpose(maze_ctx* ctx, const bf16* in, int R, int C, int ld_in, bf16* out, int ld_out, float* colsum, cudaStream_t st) {
-    const dim3 grid((C + 63) / 64, (R + 63) / 64);
-    net_transpose_kernel<<<grid, 256, 0, st>>>(in, R, C, ld_in, out, ld_out, colsum);
-    MAZE_CHECK(cudaGetLastError());
     return 0;
 }
 
