@@ -574,9 +574,23 @@ __device__ __forceinline__ uint32_t r_offset(int row, int chunk) {   // byte off
     return (uint32_t)((row >> 3) * 256 + chunk * 128 + (row & 7) * 16);
 }
 
+// Conv2d.weight [32, 3, 3, 3] fp32 -> the three [32, 16] bf16 B operands of net_features_kernel (one per vertical tap), in the
+// K-major no-swizzle core-matrix layout; run by maze_dqn_net_refresh.
+__global__ void __launch_bounds__(256)
+net_conv_image_kernel(const float* __restrict__ conv_w, uint8_t* __restrict__ image) {
+    tc::pdl_wait();
+    tc::pdl_launch();
+    for (int i = threadIdx.x; i < 3 * 32 * 16; i += 256) {
+        const int dy = i / 512, o = (i >> 4) & 31, kk = i & 15;
+        float w = 0.f;
+        if (kk < 9) w = conv_w[o * 27 + (kk / 3) * 9 + dy * 3 + (kk % 3)];
+        *reinterpret_cast<bf16*>(image + dy * 1024 + r_offset(o, kk >> 3) + (kk & 7) * 2) = __float2bfloat16(w);
+    }
+}
+
 template <bool SAVE_IDX>
 __global__ void __launch_bounds__(FEAT_THREADS)
-net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ win, int n, const float* __restrict__ conv_w,
+net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ win, int n, const uint4* __restrict__ conv_w_image,
                     const float* __restrict__ conv_b, bf16* __restrict__ X, uint8_t* __restrict__ pool_idx) {
     __shared__ __align__(128) uint8_t sR[FEAT_R_BYTES];
     __shared__ __align__(128) uint8_t sW[FEAT_W_BYTES];
@@ -597,13 +611,10 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
     for (int i = tid * 16; i < FEAT_R_BYTES; i += FEAT_THREADS * 16) *reinterpret_cast<uint4*>(sR + i) = make_uint4(0, 0, 0, 0);
     tc::pdl_wait();
     tc::pdl_launch();
-    // weight slices: sW[dy][o][kk] = conv_w[o][c][dy][dx], kk = c * 3 + dx (Conv2d.weight is [32, 3, 3, 3])
-    for (int i = tid; i < 3 * 32 * 16; i += FEAT_THREADS) {
-        const int dy = i / 512, o = (i >> 4) & 31, kk = i & 15;
-        float w = 0.f;
-        if (kk < 9) w = conv_w[o * 27 + (kk / 3) * 9 + dy * 3 + (kk % 3)];
-        *reinterpret_cast<bf16*>(sW + dy * 1024 + r_offset(o, kk >> 3) + (kk & 7) * 2) = __float2bfloat16(w);
-    }
+    // weight slices sW[dy][o][kk] = conv_w[o][c][dy][dx], kk = c * 3 + dx, already in the operand layout: net_conv_image_kernel
+    // builds the 3 KB image once per weight update (a CTA lives for about seven iterations: building it here from the fp32
+    // weights was 12 % of this kernel's time, ncu r02t)
+    for (int i = tid; i < FEAT_W_BYTES / 16; i += FEAT_THREADS) reinterpret_cast<uint4*>(sW)[i] = __ldg(conv_w_image + i);
     if (tid < 32) sbias[tid] = conv_b[tid];
     tc::tc_fence_before();
     __syncthreads();
@@ -1258,6 +1269,7 @@ struct Workspace {
     int n, np;   // batch, padded batch
     bf16 *X, *h1, *h1t_tn, *h2, *h2_tn, *dh2, *dh1, *dX;
     uint8_t* idx;
+    uint8_t* conv_image[2];   // source / target net: conv weights as UMMA operands (net_conv_image_kernel)
     float* q;
     size_t bytes;
 };
@@ -1285,6 +1297,8 @@ Workspace carve(void* base, int n) {
     w.dX = (bf16*)take(np * NET_IN * 2);
     w.idx = (uint8_t*)take(np * NET_CONV_OUT);
     w.q = (float*)take(2 * np * 4 * sizeof(float));
+    w.conv_image[0] = (uint8_t*)take(FEAT_W_BYTES);
+    w.conv_image[1] = (uint8_t*)take(FEAT_W_BYTES);
     w.bytes = off;
     return w;
 }
@@ -1356,11 +1370,12 @@ inline void prof_mark(maze_ctx* ctx, cudaStream_t st, const char* label) {
     cudaEventRecord(pr->ev[pr->count++], st);
 }
 
-int features(maze_ctx* ctx, bool save_idx, const float* vec, const uint32_t* win, int n, const float* params, bf16* X, uint8_t* idx, cudaStream_t st) {
+int features(maze_ctx* ctx, bool save_idx, const float* vec, const uint32_t* win, int n, const float* params, const uint8_t* conv_image, bf16* X,
+             uint8_t* idx, cudaStream_t st) {
     const int pairs = (n + 1) / 2;   // two samples per iteration
     const int grid = pairs < ctx->num_sms * 4 ? pairs : ctx->num_sms * 4;   // 128 TMEM columns per CTA: four CTAs per SM
     MAZE_CHECK(launch_pdl(save_idx ? net_features_kernel<true> : net_features_kernel<false>, dim3(grid), dim3(FEAT_THREADS), 0, st, vec, win, n,
-                          params + MAZE_NET_OFF_CONV_W, params + MAZE_NET_OFF_CONV_B, X, idx));
+                          reinterpret_cast<const uint4*>(conv_image), params + MAZE_NET_OFF_CONV_B, X, idx));
     prof_mark(ctx, st, save_idx ? "features (conv + pool, saves argmax)" : "features (conv + pool)");
     return 0;
 }
@@ -1420,6 +1435,7 @@ extern "C" int maze_dqn_net_refresh(maze_ctx* ctx, const maze_dqn_net* net, int 
     bf16* w2t = which ? nullptr : reinterpret_cast<bf16*>(net->w2t_bf16);
     MAZE_CHECK(launch_pdl(net_refresh_kernel, dim3(NET_IN / 32, NET_H1 / 32), dim3(256), 0, st, p + MAZE_NET_OFF_W1, NET_H1, NET_IN, w1b, w1t));
     MAZE_CHECK(launch_pdl(net_refresh_kernel, dim3(NET_H1 / 32, NET_H2 / 32), dim3(256), 0, st, p + MAZE_NET_OFF_W2, NET_H2, NET_H1, w2b, w2t));
+    MAZE_CHECK(launch_pdl(net_conv_image_kernel, dim3(1), dim3(256), 0, st, p + MAZE_NET_OFF_CONV_W, carve(net->workspace, net->max_batch).conv_image[which]));
     MAZE_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1430,7 +1446,8 @@ extern "C" int maze_dqn_features(maze_ctx* ctx, const maze_dqn_net* net, int whi
     if (int rc = check_net(ctx, net, false)) return rc;
     if (!vec || !win || !X) return maze_fail_arg(ctx, MAZE_E_NULL, "maze_dqn_features pointer");
     if (n < 1) return maze_fail_arg(ctx, MAZE_E_RANGE, "maze_dqn_features: n");
-    return features(ctx, pool_idx != nullptr, vec, win, n, which ? net->target : net->params, reinterpret_cast<bf16*>(X), pool_idx,
+    return features(ctx, pool_idx != nullptr, vec, win, n, which ? net->target : net->params,
+                    carve(net->workspace, net->max_batch).conv_image[which], reinterpret_cast<bf16*>(X), pool_idx,
                     static_cast<cudaStream_t>(stream));
 }
 
@@ -1444,7 +1461,7 @@ extern "C" int maze_dqn_forward(maze_ctx* ctx, const maze_dqn_net* net, int whic
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Workspace w = carve(net->workspace, net->max_batch);
     const float* p = which ? net->target : net->params;
-    if (int rc = features(ctx, false, vec, win, n, p, w.X, nullptr, st)) return rc;
+    if (int rc = features(ctx, false, vec, win, n, p, w.conv_image[which], w.X, nullptr, st)) return rc;
     if (int rc = mlp_forward(ctx, w.X, n, reinterpret_cast<const bf16*>(which ? net->tw1_bf16 : net->w1_bf16),
                              reinterpret_cast<const bf16*>(which ? net->tw2_bf16 : net->w2_bf16), p, w.h1, w.h2, st))
         return rc;
@@ -1481,11 +1498,11 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
         const float *v0 = vec + (size_t)r0 * 6, *v1 = next_vec + (size_t)r0 * 6;
         const uint32_t *w0 = win + (size_t)r0 * MAZE_WINDOW_WORDS, *w1 = next_win + (size_t)r0 * MAZE_WINDOW_WORDS;
         const size_t a = (size_t)r0, b = np + (size_t)r0;
-        if (int rc = features(ctx, true, v0, w0, rows, p, w.X + a * NET_IN, w.idx + a * NET_CONV_OUT, st)) return rc;
+        if (int rc = features(ctx, true, v0, w0, rows, p, w.conv_image[0], w.X + a * NET_IN, w.idx + a * NET_CONV_OUT, st)) return rc;
         if (int rc = mlp_forward(ctx, w.X + a * NET_IN, rows, w1b, w2b, p, w.h1 + a * NET_H1, w.h2 + a * NET_H2, st)) return rc;
-        if (int rc = features(ctx, false, v1, w1, rows, p, w.X + b * NET_IN, nullptr, st)) return rc;
+        if (int rc = features(ctx, false, v1, w1, rows, p, w.conv_image[0], w.X + b * NET_IN, nullptr, st)) return rc;
         if (int rc = mlp_forward(ctx, w.X + b * NET_IN, rows, w1b, w2b, p, w.h1 + b * NET_H1, w.h2 + b * NET_H2, st)) return rc;
-        if (int rc = features(ctx, false, v1, w1, rows, net->target, Xt + a * NET_IN, nullptr, st)) return rc;
+        if (int rc = features(ctx, false, v1, w1, rows, net->target, w.conv_image[1], Xt + a * NET_IN, nullptr, st)) return rc;
         if (int rc = mlp_forward(ctx, Xt + a * NET_IN, rows, tw1b, tw2b, net->target, w.h1t_tn + a * NET_H1, w.h2_tn + a * NET_H2, st)) return rc;
     }
     {

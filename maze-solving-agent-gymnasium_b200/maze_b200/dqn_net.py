@@ -105,8 +105,7 @@ class DQNNet:
     def update_target(self):
         """target_net.load_state_dict(source_net.state_dict()) (ddqn_agent.py:161-162)."""
         self.target.copy_(self.params)
-        self.tw1_bf16.copy_(self.w1_bf16)
-        self.tw2_bf16.copy_(self.w2_bf16)
+        self.refresh(1)   # the target net's bf16 operands: fc1 / fc2 weights and the conv weight image
 
     # ---- compute ----------------------------------------------------------------------------------------------
     def forward(self, vec: torch.Tensor, win: torch.Tensor, which: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
