@@ -1,10 +1,12 @@
 """Frame oracle (test infrastructure; see oracle/__init__.py): the drawing calls of
 lib/maze_view.py replayed on a numpy canvas.
 
-PARITY UNPINNED for this module: pygame is not installed in the build container, so no frame of the
-reference could be captured; the rules are restated from the source -- __draw_maze :88-96 (tile fill
-+ (59, 66, 82) outline), _draw_agent :98-104 (8 x 8 square at offset 4), _draw_cell :148-152 (fill +
-(208, 135, 112) outline on the block the agent leaves), move_agent :167-180 / :184-197, _reset_agent
+Parity PINNED (round 2): tests/test_oracle_render.py compares this canvas with 252 frames of the UNMODIFIED
+lib/maze_view.py (tests/golden/render.npz).  pygame is not installed in the build container, so the reference's
+views were driven on tests/golden/pygame_raster.py, a software pygame for the calls the renderer makes -- it draws
+axis-aligned rectangles only (fill and one-pixel outline), which rasterise unambiguously.  The rules: __draw_maze
+:88-96 (tile fill + (59, 66, 82) outline), _draw_agent :98-104 (8 x 8 square at offset 4), _draw_cell :148-152
+(fill + (208, 135, 112) outline on the block the agent leaves), move_agent :167-180 / :184-197, _reset_agent
 :154-158, and the layers being one pixel smaller than the window (:41-44).
 """
 from __future__ import annotations

@@ -6,7 +6,7 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-from conftest import load_golden  # noqa: E402
+from conftest import GOLDEN, load_golden  # noqa: E402
 
 
 def _replay(meta, z, visit_layout, on_step, visit_bits=False):
@@ -145,3 +145,31 @@ def test_render_matches_the_replayed_drawing_calls(toroidal):
     assert moved_any
     one = batch.render([1]).cpu().numpy()
     assert np.array_equal(one[0], batch.render().cpu().numpy()[1])
+
+
+def test_render_matches_frames_of_the_reference_view():
+    """maze_render against frames of the UNMODIFIED lib/maze_view.py (tests/golden/render.npz; the reference's views driven on a
+    software pygame -- they draw rectangles only, which rasterise exactly): frame after reset, then after every action of a
+    scripted walk (moves, blocked moves, wraps on the torus) for as long as the first episode lasts.  Deviation, by design:
+    maze_render draws the trail of the CURRENT episode (it is derived from the visit state), the reference's surface keeps
+    the trails of earlier episodes until the maze changes -- so frames after a reset are not compared."""
+    import maze_b200 as mb
+    z = np.load(f"{GOLDEN}/render.npz")
+    checked = 0
+    for k in range(int(z["count"])):
+        grid, frames, acts, pos = z[f"grid{k}"], z[f"frames{k}"], z[f"actions{k}"], z[f"pos{k}"]
+        open_grid = (grid != 0).astype(np.uint8)
+        pool = mb.MazePool.from_grids([open_grid], [tuple(z[f"start{k}"])], [tuple(z[f"goal{k}"])], bool(z[f"toroidal{k}"]))
+        batch = mb.MazeBatch(pool, 1, env_maze=torch.zeros(1, dtype=torch.int32, device="cuda"))
+        batch.reset()
+        got = batch.render().cpu().numpy()[0]
+        assert got.shape == frames[0].shape
+        np.testing.assert_array_equal(got, frames[0], err_msg=f"maze {k}: frame after reset")
+        for t, a in enumerate(acts):
+            batch.step(torch.tensor([a], dtype=torch.uint8, device="cuda"), 0)
+            if bool(batch.terminated.any()) or bool(batch.truncated.any()):
+                break
+            assert tuple(batch.agent.cpu().numpy()[0]) == tuple(pos[t]), (k, t)     # the env moves exactly when the view does
+            np.testing.assert_array_equal(batch.render().cpu().numpy()[0], frames[1 + t], err_msg=f"maze {k} step {t}")
+            checked += 1
+    assert checked > 150
