@@ -188,3 +188,31 @@ def test_shared_agent_learns_with_philox_draws():
         t = ag.core.table_host("a")
         tables.append({k: v.tobytes() for k, v in t.items()})
     assert tables[0] == tables[1] and len(tables[0]) > 64
+
+
+def test_shared_learner_runs_differ_within_bounds():
+    """With one learner behind many envs, concurrent writers of a table row race and one wins (DESIGN.md section 5,
+    deviations): this is not the reference's one-env-per-agent semantics, and runs with the same seed are not bit-identical.
+    What the race may and may not do: every run must still learn (late win rate well above the never-learning baseline, as in
+    the test above) and runs must agree with each other within the spread measured on a B200 (three runs: 0.45 / 0.48 / 0.60,
+    tools/probe_shared_learner.py); with one env per agent there is no race and runs are bit-identical (previous test)."""
+    import maze_b200 as mb
+    from maze_b200.agents import QAgent
+    z, _ = load_golden("qagent")
+    pool = mb.MazePool.from_grids([z["grid"]], [tuple(z["start"])], [tuple(z["goal"])], [False])
+    B = 2048
+
+    def late_rate(lr):
+        batch = mb.MazeBatch(pool, B, stats=True)
+        agent = QAgent(batch, envs_per_agent=B, seed=5, **dict(KW, learning_rate=lr))
+        batch.reset()
+        agent.rollout(1650)
+        mid = batch.stats.cpu().numpy().copy()
+        agent.rollout(300)
+        late = batch.stats.cpu().numpy() - mid
+        return late[1] / late[0]
+
+    base = late_rate(0.0)
+    rates = [late_rate(0.1) for _ in range(3)]
+    assert min(rates) > base + 0.15, (base, rates)
+    assert max(rates) - min(rates) < 0.3, rates
