@@ -58,6 +58,7 @@ class DeviceReplay:
 
     def observe(self):
         """Stage the current observation of every env (call after env.reset())."""
+        self.batch.sync_flags()
         rc = cabi.lib().maze_dqn_observe(self.ctx.handle, C.byref(self.batch._c), C.byref(self._c), self._stream())
         self.ctx.check(rc, "maze_dqn_observe")
 
@@ -65,6 +66,7 @@ class DeviceReplay:
         """memorize(state, action, reward, next_state) for the step just made with `actions`."""
         if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        self.batch.sync_flags()
         rc = cabi.lib().maze_dqn_push(self.ctx.handle, C.byref(self.batch._c), C.byref(self._c), cabi.ptr(actions), self._stream())
         self.ctx.check(rc, "maze_dqn_push")
 

@@ -43,6 +43,9 @@ class MazePool:
         self.grids = torch.zeros((self.num_mazes, self.slot), dtype=torch.uint8, device=d)
         self.table = torch.zeros((self.num_mazes, self.slot), dtype=torch.uint8, device=d)
         self.meta = torch.zeros((self.num_mazes, cabi.META_WORDS), dtype=torch.int32, device=d)
+        # host-side knowledge "some slot may be toroidal" (conservative: set by every path that writes slot records, cleared only
+        # when all slots are reconfigured as bordered): batches derive MAZE_BATCH_BORDERED from it without a device read
+        self.any_toroidal = False
 
     # -- construction from host block grids (parity tests, reference-generated mazes)
     @classmethod
@@ -60,6 +63,8 @@ class MazePool:
         ids = list(ids)
         hg = np.zeros((len(ids), self.slot), dtype=np.uint8)
         hm = np.zeros((len(ids), cabi.META_WORDS), dtype=np.int32)
+        toroidal = list(toroidal)
+        self.any_toroidal = self.any_toroidal or any(bool(t) for t in toroidal)
         for k, (g, s, t, tor) in enumerate(zip(grids, starts, goals, toroidal)):
             g = np.asarray(g, dtype=np.uint8)
             H, W = check_shape(g.shape)
@@ -137,6 +142,8 @@ class MazePool:
                     if key not in cache:
                         cache[key] = record(*key)
                     hm[q] = cache[key]
+            some_tor = bool((hm[:, 2] & cabi.FLAG_TOROIDAL).any())
+            self.any_toroidal = some_tor if len(ids_list) == self.num_mazes and len(set(ids_list)) == self.num_mazes else (self.any_toroidal or some_tor)
             cfg = torch.from_numpy(hm).to(self.device)
             idx = torch.as_tensor(ids_list, dtype=torch.long, device=self.device)
             self.meta[idx, cabi.META_H] = cfg[:, 0]
@@ -196,6 +203,7 @@ class MazePool:
             raise ValueError("checkpoint was taken from a pool of another size / shape")
         for k in ("grids", "table", "meta"):
             getattr(self, k).copy_(sd[k])
+        self.any_toroidal = bool((self.meta[:, cabi.META_FLAGS] & cabi.FLAG_TOROIDAL).any().item())
 
     # -- host views (tests, facade)
     def meta_host(self):
@@ -299,8 +307,14 @@ class MazeBatch:
             target_dirty=self.target_dirty.data_ptr(), packed=self.packed.data_ptr(),
             visit_bits=None if self.visit_bits is None else self.visit_bits.data_ptr(),
             visit_bits_pitch=self.visit_bits_pitch, visit_bits_stride=self.visit_bits_stride,
-            # no toroidal maze in the pool now (and regeneration keeps a slot's topology): the bordered window / push kernels
-            flags=0 if bool((p.meta[:, cabi.META_FLAGS] & cabi.FLAG_TOROIDAL).any().item()) else cabi.BATCH_BORDERED, reserved=0)
+            flags=0 if p.any_toroidal else cabi.BATCH_BORDERED, reserved=0)   # kept current by sync_flags()
+
+    def sync_flags(self):
+        """MAZE_BATCH_BORDERED follows the pool (a pool may be reconfigured after the batch was built); host-only, no device read.
+        Called before the launches that read the flag (maze_window, maze_dqn_observe / _push)."""
+        want = 0 if self.pool.any_toroidal else cabi.BATCH_BORDERED
+        if self._c.flags != want:
+            self._c.flags = want
 
     def view_struct(self, lo: int, hi: int) -> cabi.MazeEnvBatch:
         """maze_env_batch over the envs [lo, hi) of this batch: the same buffers with every per-env pointer advanced by
@@ -368,6 +382,7 @@ class MazeBatch:
             self.window = torch.empty((B, 3, cabi.WINDOW, cabi.WINDOW), dtype=torch.float32, device=d)
             self.agent_norm = torch.empty((B, 2), dtype=torch.float64, device=d)
             self.target_norm = torch.empty((B, 2), dtype=torch.float64, device=d)
+        self.sync_flags()
         rc = cabi.lib().maze_window(self.ctx.handle, C.byref(self._c), cabi.ptr(self.window), cabi.ptr(self.agent_norm),
                                     cabi.ptr(self.target_norm), cabi.current_stream(self.device))
         self.ctx.check(rc, "maze_window")

@@ -244,7 +244,7 @@ class MazeVectorEnv(_VectorBase):
         for j in range(K):   # ring entry j holds M(m, g) for the g in [live, live + K) with g % K == j
             sh = MazePool.__new__(MazePool)
             sh.device, sh.ctx, sh.max_shape, sh.num_mazes, sh.slot = dev, ctx, pool.max_shape, M, pool.slot
-            sh.grids, sh.table, sh.meta = grids[j], table[j], meta[j]
+            sh.grids, sh.table, sh.meta, sh.any_toroidal = grids[j], table[j], meta[j], pool.any_toroidal
             ring.append(sh)
         curriculum = bool(self.grow or self.algorithm_schedule)
         a = dict(ring=ring, grids=grids, table=table, meta=meta, ctx=ctx, ready=torch.zeros((K, M), **i32),

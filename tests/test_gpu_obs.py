@@ -173,3 +173,30 @@ def test_render_matches_frames_of_the_reference_view():
             np.testing.assert_array_equal(batch.render().cpu().numpy()[0], frames[1 + t], err_msg=f"maze {k} step {t}")
             checked += 1
     assert checked > 150
+
+
+def test_bordered_flag_follows_a_pool_that_is_reconfigured_after_the_batch_was_built():
+    """MAZE_BATCH_BORDERED selects the window / push kernels without torus code: a batch built over an empty (or bordered) pool
+    must drop the flag when the pool's slots become toroidal, or its windows would clamp where they have to wrap."""
+    import maze_b200 as mb
+    pool = mb.MazePool(4, (21, 21))
+    early = mb.MazeBatch(pool, 64, visit_bits=True, visit_layout="tile")
+    assert early._c.flags & mb.cabi.BATCH_BORDERED
+    pool.generate(algorithms="dfs", toroidal=True, seed=4)
+    late = mb.MazeBatch(pool, 64, visit_bits=True, visit_layout="tile")
+    assert not (late._c.flags & mb.cabi.BATCH_BORDERED)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for b in (early, late):
+        b.reset()
+    for _ in range(30):
+        acts = torch.randint(0, 4, (64,), dtype=torch.uint8, device="cuda", generator=g)
+        early.step(acts, 0)
+        late.step(acts, 0)
+    w_early, w_late = early.compute_window().clone(), late.compute_window().clone()
+    assert not (early._c.flags & mb.cabi.BATCH_BORDERED)
+    assert torch.equal(w_early, w_late)
+    pool.generate(algorithms="dfs", toroidal=False, seed=5)      # every slot bordered again
+    assert not pool.any_toroidal
+    early.reset()
+    early.compute_window()
+    assert early._c.flags & mb.cabi.BATCH_BORDERED
