@@ -16,6 +16,7 @@ device into the env's own slot, the analogue of update_maze()).
 """
 from __future__ import annotations
 
+from types import SimpleNamespace
 from typing import Optional
 
 import os
@@ -247,7 +248,7 @@ class MazeVectorEnv(_VectorBase):
             sh.grids, sh.table, sh.meta, sh.any_toroidal = grids[j], table[j], meta[j], pool.any_toroidal
             ring.append(sh)
         curriculum = bool(self.grow or self.algorithm_schedule)
-        a = dict(ring=ring, grids=grids, table=table, meta=meta, ctx=ctx, ready=torch.zeros((K, M), **i32),
+        a = SimpleNamespace(ring=ring, grids=grids, table=table, meta=meta, ctx=ctx, ready=torch.zeros((K, M), **i32),
                  # the slot records and win counts now, with nothing in flight: what maze_regen_prepare derives every later
                  # configuration from (reading the live records there would race with maze_regen_swap)
                  base_meta=pool.meta.clone(), base_wins=self.wins.clone() if curriculum else None, curriculum=curriculum,
@@ -257,64 +258,64 @@ class MazeVectorEnv(_VectorBase):
                  side=torch.cuda.Stream(device=dev), side_done=torch.cuda.Event(), main_evt=torch.cuda.Event(), cur=0, batch=0, jobs=0)
         self._ahead = a
         self._refill_job(0)   # every slot, on the current stream: the ring starts complete
-        for t in (grids, table, meta, a["ready"], *a["refill"], *a["refill_count"], a["work"], a["work_count"], pool.meta, a["base_meta"]):
-            t.record_stream(a["side"])   # the side stream reads / writes them: the allocator must not recycle them under it
-        if a["base_wins"] is not None:
-            a["base_wins"].record_stream(a["side"])
+        for t in (grids, table, meta, a.ready, *a.refill, *a.refill_count, a.work, a.work_count, pool.meta, a.base_meta):
+            t.record_stream(a.side)   # the side stream reads / writes them: the allocator must not recycle them under it
+        if a.base_wins is not None:
+            a.base_wins.record_stream(a.side)
 
     def _refill_job(self, cur):
         """prepare -> maze_generate per ring entry -> publish for refill queue `cur`, on the current stream."""
         a, pool, K = self._ahead, self.pool, self.regenerate_depth
-        lib, p, ctx, M = cabi.lib(), cabi.ptr, a["ctx"], pool.num_mazes
+        lib, p, ctx, M = cabi.lib(), cabi.ptr, a.ctx, pool.num_mazes
         stream = cabi.current_stream(self.device)
-        rc = lib.maze_regen_prepare(ctx.handle, p(pool.meta), p(a["base_meta"]), p(a["base_wins"]), *self._curriculum_rule(), p(a["meta"]),
-                                    p(a["ready"]), K, p(a["refill"][cur]), p(a["refill_count"][cur]), M, p(a["work"]), p(a["work_count"]), stream)
+        rc = lib.maze_regen_prepare(ctx.handle, p(pool.meta), p(a.base_meta), p(a.base_wins), *self._curriculum_rule(), p(a.meta),
+                                    p(a.ready), K, p(a.refill[cur]), p(a.refill_count[cur]), M, p(a.work), p(a.work_count), stream)
         ctx.check(rc, "maze_regen_prepare")
-        for j, sh in enumerate(a["ring"]):
-            sh.generate(ids=a["work"][j], count_dev=a["work_count"][j:j + 1], configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
+        for j, sh in enumerate(a.ring):
+            sh.generate(ids=a.work[j], count_dev=a.work_count[j:j + 1], configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
                         candidates=self.candidates)
-        rc = lib.maze_regen_publish(ctx.handle, p(a["meta"]), p(a["ready"]), K, p(a["work"]), p(a["work_count"]), M, stream)
+        rc = lib.maze_regen_publish(ctx.handle, p(a.meta), p(a.ready), K, p(a.work), p(a.work_count), M, stream)
         ctx.check(rc, "maze_regen_publish")
-        a["refill_count"][cur].zero_()
-        a["work_count"].zero_()
+        a.refill_count[cur].zero_()
+        a.work_count.zero_()
 
     def _drain_ahead(self):
         if self._ahead is None:
             self._build_ahead()
         a, b, pool, K = self._ahead, self.batch, self.pool, self.regenerate_depth
-        cur, M = a["cur"], pool.num_mazes
+        cur, M = a.cur, pool.num_mazes
         lib, p = cabi.lib(), cabi.ptr
-        a["slow_count"].zero_()
-        rc = lib.maze_regen_swap(pool.ctx.handle, p(pool.grids), p(pool.table), p(pool.meta), p(a["grids"]), p(a["table"]), p(a["meta"]), p(a["ready"]), K,
-                                 p(b.queue), p(b.queue_count), M, pool.slot, p(a["refill"][cur]), p(a["refill_count"][cur]), p(a["tag"]), a["batch"],
-                                 p(a["slow"]), p(a["slow_count"]), p(a["stats"]), p(self.wins) if a["curriculum"] else None,
+        a.slow_count.zero_()
+        rc = lib.maze_regen_swap(pool.ctx.handle, p(pool.grids), p(pool.table), p(pool.meta), p(a.grids), p(a.table), p(a.meta), p(a.ready), K,
+                                 p(b.queue), p(b.queue_count), M, pool.slot, p(a.refill[cur]), p(a.refill_count[cur]), p(a.tag), a.batch,
+                                 p(a.slow), p(a.slow_count), p(a.stats), p(self.wins) if a.curriculum else None,
                                  cabi.current_stream(self.device))
         pool.ctx.check(rc, "maze_regen_swap")
         # slots whose ring entry was not ready (more wins than the ring is deep before a refill was published): drawn in place
-        if a["curriculum"]:
-            pool.curriculum(a["slow"], a["slow_count"], self.wins, self.grow, self.algorithm_schedule)
-        pool.generate(ids=a["slow"], count_dev=a["slow_count"], configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
+        if a.curriculum:
+            pool.curriculum(a.slow, a.slow_count, self.wins, self.grow, self.algorithm_schedule)
+        pool.generate(ids=a.slow, count_dev=a.slow_count, configure=False, seed=self.seed, slot_id_base=self.slot_id_base,
                       candidates=self.candidates)
         b.queue_count.zero_()
-        if a["side_done"].query():   # the previous refill has finished: start the next one on what queued up meanwhile
-            main, side = torch.cuda.current_stream(self.device), a["side"]
-            a["main_evt"].record(main)
-            side.wait_event(a["main_evt"])
+        if a.side_done.query():   # the previous refill has finished: start the next one on what queued up meanwhile
+            main, side = torch.cuda.current_stream(self.device), a.side
+            a.main_evt.record(main)
+            side.wait_event(a.main_evt)
             with torch.cuda.stream(side):
                 self._refill_job(cur)
-                a["side_done"].record(side)
-            a["cur"], a["batch"], a["jobs"] = cur ^ 1, a["batch"] + 1, a["jobs"] + 1
+                a.side_done.record(side)
+            a.cur, a.batch, a.jobs = cur ^ 1, a.batch + 1, a.jobs + 1
 
     def regeneration_statistics(self):
         """(slots installed from the shadow pool, slots drawn in place, refill jobs launched) since construction; one small D2H."""
         if self._ahead is None:
             return (0, 0, 0)
-        fast, slow = (int(v) for v in self._ahead["stats"].tolist())
-        return (fast, slow, self._ahead["jobs"])
+        fast, slow = (int(v) for v in self._ahead.stats.tolist())
+        return (fast, slow, self._ahead.jobs)
 
     def _drop_ahead(self):
         if self._ahead is not None:
-            self._ahead["side"].synchronize()
+            self._ahead.side.synchronize()
             self._ahead = None
 
     def step(self, actions, extra_mode: int = 0, observe: bool = True):

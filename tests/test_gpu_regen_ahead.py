@@ -96,7 +96,7 @@ def test_slots_that_win_again_before_their_refill_are_drawn_in_place():
 
     def hook(t, e):
         if t == 0:
-            e._ahead["side_done"] = Never()
+            e._ahead.side_done = Never()
 
     _same(_run(ref_env, S, steps, 11), _run(env, S, steps, 11, hook))
     assert torch.equal(ref_env.pool.grids, env.pool.grids) and torch.equal(ref_env.pool.meta, env.pool.meta)
