@@ -736,6 +736,7 @@ net_features_kernel(const float* __restrict__ vec, const uint32_t* __restrict__ 
 // fc3 head (512 -> 4, fp32 weights, CUDA cores).  q[n, 4] for action selection.
 constexpr int HEAD_THREADS = 256;
 constexpr int NET_H2 = 512, NET_H1 = 1024;
+constexpr size_t HEAD_LOSS_SMEM = (size_t)(2 + HEAD_THREADS / 32) * 4 * NET_H2 * sizeof(float);   // fc3 weights of both nets + one gradient copy per warp: 80 KB
 
 // A warp owns one sample; lane l holds the 16 columns  k * 128 + 4 l + j  (k, j = 0..3) of its 512-wide rows: global
 // loads are 8 bytes per lane and 256 contiguous bytes per warp, shared-memory weight reads are float4 at a 16-byte lane
@@ -814,27 +815,22 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
                      const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ tw3, const float* __restrict__ tb3,
                      const uint8_t* __restrict__ action, const float* __restrict__ reward, float gamma, bf16* __restrict__ dh2,
                      float* __restrict__ gw3, float* __restrict__ gb3, float* __restrict__ loss, float* __restrict__ qsa_out) {
-    __shared__ __align__(16) float sw[4 * NET_H2], stw[4 * NET_H2], sgw[4 * NET_H2];
+    // dynamic shared memory: fc3 weights of both nets (2 x 8 KB) and ONE d fc3.weight accumulator PER WARP (8 x 8 KB), in
+    // lane-major order (entry (a, i, lane) <-> column head_col(lane, i)).  A warp's lanes own distinct entries of its copy, so
+    // the per-sample update is a plain conflict-free read-add-write: the single shared copy it replaces needed a shared
+    // float atomic per entry -- a CAS loop, 21 % of this kernel's stall samples (ncu profiles/r02zz_head_details.txt).
+    extern __shared__ __align__(16) float head_smem[];
+    float* const sw = head_smem;
+    float* const stw = sw + 4 * NET_H2;
+    float* const sgw_all = stw + 4 * NET_H2;
     __shared__ float sgb[4], sloss;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* const sgw = sgw_all + warp * (4 * NET_H2);
     tc::pdl_wait();
     tc::pdl_launch();
-    for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS) {
-        sw[i] = w3[i];
-        stw[i] = tw3[i];
-        sgw[i] = 0.f;
-    }
-    if (threadIdx.x < 4) sgb[threadIdx.x] = 0.f;
-    if (threadIdx.x == 0) sloss = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const float inv_n = 1.f / (float)n;
-    // d fc3.weight is summed in shared memory, in lane-major order (entry (a, i, lane) <-> column head_col(lane, i)): one
-    // conflict-free shared atomic per owned column and sample, and no 64 accumulator registers beside the prefetch.
-    float gb_acc = 0.f, loss_acc = 0.f;   // lane a < 4 collects d fc3.bias[a]; lane 0 the loss
-    // The loop is a chain of global loads -> dot products -> butterfly sums with two CTAs of eight warps per SM: the next
-    // sample's three rows are fetched while the current one is reduced (ncu r02t: 82 % of the cycles had no eligible warp).
+    // the first sample's rows are requested before the weights: the two round trips to memory overlap
     const int stride = gridDim.x * (HEAD_THREADS / 32);
-    int s = blockIdx.x * (HEAD_THREADS / 32) + (threadIdx.x >> 5);
+    int s = blockIdx.x * (HEAD_THREADS / 32) + warp;
     uint2 ra[4], rb[4], rc[4];
     int act_next = 0;
     float rew_next = 0.f;
@@ -845,6 +841,18 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
         act_next = action[s] & 3;
         rew_next = reward[s];
     }
+    for (int i = threadIdx.x; i < NET_H2; i += HEAD_THREADS) {   // 4 x 512 floats each, 16 bytes per load
+        reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(w3) + i);
+        reinterpret_cast<float4*>(stw)[i] = __ldg(reinterpret_cast<const float4*>(tw3) + i);
+    }
+    for (int i = threadIdx.x; i < (HEAD_THREADS / 32) * NET_H2; i += HEAD_THREADS) reinterpret_cast<float4*>(sgw_all)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < 4) sgb[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) sloss = 0.f;
+    __syncthreads();
+    const float inv_n = 1.f / (float)n;
+    float gb_acc = 0.f, loss_acc = 0.f;   // lane a < 4 collects d fc3.bias[a]; lane 0 the loss
+    // The loop is a chain of global loads -> dot products -> butterfly sums with two CTAs of eight warps per SM: the next
+    // sample's three rows are fetched while the current one is reduced (ncu r02t: 82 % of the cycles had no eligible warp).
     for (; s < n; s += stride) {
         float h[16], hn[16], ht[16];
         head_expand(ra, h);
@@ -891,8 +899,7 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
             *reinterpret_cast<uint2*>(dh2 + (size_t)s * NET_H2 + k * 128 + lane * 4) = out;
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (h[i] != 0.f) atomicAdd(&sgw[act * NET_H2 + i * 32 + lane], gq * h[i]);
+        for (int i = 0; i < 16; ++i) sgw[act * NET_H2 + i * 32 + lane] += gq * h[i];   // this warp's copy, this lane's entries
         if (lane == act) gb_acc += gq;
         if (lane == 0) {
             loss_acc += d * d * inv_n;
@@ -902,8 +909,12 @@ net_head_loss_kernel(const bf16* __restrict__ h2_s, const bf16* __restrict__ h2_
     if (lane < 4 && gb_acc != 0.f) atomicAdd(&sgb[lane], gb_acc);
     if (lane == 0) atomicAdd(&sloss, loss_acc);
     __syncthreads();
-    for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS)
-        if (sgw[i] != 0.f) atomicAdd(gw3 + (i >> 9) * NET_H2 + head_col(i & 31, (i >> 5) & 15), sgw[i]);
+    for (int i = threadIdx.x; i < 4 * NET_H2; i += HEAD_THREADS) {
+        float v = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < HEAD_THREADS / 32; ++w8) v += sgw_all[w8 * (4 * NET_H2) + i];
+        if (v != 0.f) atomicAdd(gw3 + (i >> 9) * NET_H2 + head_col(i & 31, (i >> 5) & 15), v);
+    }
     if (threadIdx.x < 4) atomicAdd(gb3 + threadIdx.x, sgb[threadIdx.x]);
     if (threadIdx.x == 0) atomicAdd(loss, sloss);
 }
@@ -1507,7 +1518,8 @@ extern "C" int maze_dqn_backward(maze_ctx* ctx, const maze_dqn_net* net, const f
     }
     {
         const int grid = (n + 7) / 8 < 2 * ctx->num_sms ? (n + 7) / 8 : 2 * ctx->num_sms;   // two CTAs per SM; the fc3 gradient is merged with one atomic per CTA and entry
-        MAZE_CHECK(launch_pdl(net_head_loss_kernel, dim3(grid), dim3(HEAD_THREADS), 0, st, w.h2, w.h2 + np * NET_H2, w.h2_tn, n, p + MAZE_NET_OFF_W3,
+        MAZE_CHECK(cudaFuncSetAttribute(net_head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_LOSS_SMEM));
+        MAZE_CHECK(launch_pdl(net_head_loss_kernel, dim3(grid), dim3(HEAD_THREADS), HEAD_LOSS_SMEM, st, w.h2, w.h2 + np * NET_H2, w.h2_tn, n, p + MAZE_NET_OFF_W3,
                               p + MAZE_NET_OFF_B3, net->target + MAZE_NET_OFF_W3, net->target + MAZE_NET_OFF_B3, action, reward, gamma, w.dh2,
                               gr + MAZE_NET_OFF_W3, gr + MAZE_NET_OFF_B3, net->loss, qsa_out));
         prof_mark(ctx, st, "head: Q, double-Q target, loss, dQ, fc3 gradients");
