@@ -674,6 +674,31 @@ def run_ddqn(args, rank, local_rank, world):
     args.warmup = args_w
     clocks = sampler.stop()
     ar_ms = sum(a.elapsed_time(b) for a, b in loop.ar_events)
+    # the dominant kernel inside the step, measured live: maze_dqn_backward records a CUDA event after every launch while the
+    # in-situ profiler is on (outside the timed region: the events cost a little)
+    kernel = None
+    try:
+        loop.net.profile(True)
+        seen = {}
+        for _ in range(8):
+            loop.iterate()
+            for i, (label, k_ms) in enumerate(loop.net.profile_read()):
+                seen.setdefault((i, label), []).append(k_ms)
+        loop.net.profile(False)
+        med = {k: sorted(v)[len(v) // 2] for k, v in seen.items()}
+        total = sum(med.values())
+        by_label = {}
+        for (_, label), k_ms in med.items():
+            by_label.setdefault(label, []).append(k_ms)
+        label, times = max(by_label.items(), key=lambda kv: sum(kv[1]))   # the kernel with the largest share of the pass
+        gemm_flop = {"fc1 forward GEMM": 2.0 * n * 1024 * 1600, "fc2 forward GEMM": 2.0 * n * 512 * 1024,
+                     "fc1 weight gradient GEMM (split-K)": 2.0 * n * 1024 * 1600, "fc1 backward-data GEMM": 2.0 * n * 1568 * 1024}.get(label)
+        k_ms = sum(times) / len(times)
+        kernel = {"label": label, "launches_per_backward": len(times), "ms_per_launch": k_ms, "share_of_backward": sum(times) / total if total else None,
+                  "flop_per_launch": gemm_flop, "tflops": gemm_flop / (k_ms * 1e-3) / 1e12 if gemm_flop else None,
+                  "how": "median of 8 in-situ measurements per launch (CUDA events between the launches of maze_dqn_backward, maze_dqn_net_profile)"}
+    except Exception as e:   # a profile that cannot be taken must not cost the bench line
+        kernel = {"error": repr(e)}
     if rank != 0:
         return None
     n_opt = loop.opt_steps - opt0
@@ -697,6 +722,7 @@ def run_ddqn(args, rank, local_rank, world):
             "allreduce_share": (ar_ms / ms) if (args.no_overlap and world > 1) else None,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None, "peak_source": peak_src,
                          "flop_per_step_per_gpu": loop.flop_per_iteration(),
+                         "dominant_kernel": (dict(kernel, frac_of_peak=(kernel["tflops"] / peak if kernel.get("tflops") else None)) if kernel else None),
                          "note": "whole loop per GPU (policy forward on B envs + forward on 3 n and backward on n samples per optimiser step; env step, "
                                  "replay, sampling, AdamW and the all-reduce included in the time)"},
             "final_loss": float(loop.net.loss.item()), "gpu_launches": args.steps * world * 40, "clocks": clocks}
