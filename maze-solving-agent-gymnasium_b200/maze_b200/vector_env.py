@@ -279,8 +279,26 @@ class MazeVectorEnv(_VectorBase):
         a.refill_count[cur].zero_()
         a.work_count.zero_()
 
+    def _fit_ahead_depth(self):
+        """The ring costs depth x (2 x slot + 36) bytes per maze slot (3 x 13 KB at 81 x 81): shrink the depth, down to in-place
+        regeneration, rather than take more than half of the free device memory."""
+        per_entry = self.pool.num_mazes * (2 * self.pool.slot + 4 * cabi.META_WORDS + 4)
+        free, _ = torch.cuda.mem_get_info(self.device)
+        depth = self.regenerate_depth
+        while depth > 0 and depth * per_entry > free // 2:
+            depth -= 1
+        if depth != self.regenerate_depth:
+            import warnings
+            warnings.warn(f"regenerate_ahead={self.regenerate_depth} needs {self.regenerate_depth * per_entry / 2**30:.1f} GiB for {self.pool.num_mazes} maze slots; "
+                          f"using depth {depth}" + (" (regeneration in place)" if depth == 0 else ""))
+            self.regenerate_depth = depth
+            self.regenerate_ahead = depth > 0
+        return self.regenerate_ahead
+
     def _drain_ahead(self):
         if self._ahead is None:
+            if not self._fit_ahead_depth():
+                return self.drain_regeneration()   # no room for a ring: in place, as with regenerate_ahead=0
             self._build_ahead()
         a, b, pool, K = self._ahead, self.batch, self.pool, self.regenerate_depth
         cur, M = a.cur, pool.num_mazes

@@ -139,3 +139,15 @@ def test_checkpoint_rebuilds_the_shadow_pool(tmp_path):
         got = (obs["agent"], obs["target"], obs["best dir"], rew, term, trunc)
         for k, (u, v) in enumerate(zip(full[t], got)):
             assert torch.equal(u, v), (t, k)
+
+
+def test_a_ring_that_does_not_fit_falls_back_to_regeneration_in_place(monkeypatch):
+    """The ring is sized against the free device memory when it is first needed: with (pretended) 64 KiB free the env warns,
+    regenerates in place and still produces the same steps."""
+    B, S = 512, 9
+    ref_env, env = _make(0, B, S, "toroidal"), _make(3, B, S, "toroidal")
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda device=None: (1 << 16, 1 << 30))
+    with pytest.warns(UserWarning, match="regeneration in place"):
+        got = _run(env, S, 120, 4)
+    assert not env.regenerate_ahead and env.regeneration_statistics() == (0, 0, 0)
+    _same(_run(ref_env, S, 120, 4), got)
